@@ -1,0 +1,145 @@
+/* libvfd_b200.so -- C-ABI of the B200-native vfd_gan training hot path.
+ *
+ * The reference (umaionigiri/vfd_gan) has no native layer: its hot path bottoms out in torch
+ * library calls (nn.Conv3d / nn.BatchNorm3d / nn.AvgPool3d / nn.Upsample / nn.Dropout ...).
+ * Each entry point below replaces one of those call sites; the citation is reference file:line.
+ * The host side (vfd_gan_b200/*.py) binds these with ctypes and registers them as torch.library
+ * ops; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer (plain void / float / double), sizes are plain integers;
+ *    no torch types cross this boundary. `stream` is a cudaStream_t passed as void*.
+ *  - Activations are channels-last bf16: element (n,d,h,w,c) lives at
+ *    ((((n*D+d)*H+h)*W+w) * ld + c); `ld` >= channel count lets a tensor be a channel slice of a
+ *    wider (concat) buffer. Channel counts are padded to a multiple of 8 and padded channels hold 0.
+ *  - Every function only enqueues work on `stream`; none synchronises the device.
+ *  - Return value 0 = success; otherwise an error code, and vfd_last_error() returns a
+ *    thread-local message. There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VFD_B200_H
+#define VFD_B200_H
+
+#ifdef __cplusplus
+#define VFD_API extern "C" __attribute__((visibility("default")))
+#else
+#define VFD_API __attribute__((visibility("default")))
+#endif
+
+VFD_API const char* vfd_last_error(void);
+VFD_API int vfd_abi_version(void);
+
+/* ---- conv3d, stride 1, "same" zero padding, kernel extents in {1,3} ------------------------------
+ * Replaces nn.Conv3d forward at models/spatiotempconv.py:49-50,59-60,63-64, conv_last at
+ * models/mygannet.py:52,97 and nn.Conv2d at models/convlstm.py:36-40,46 (D = 1).
+ * Implicit GEMM on tcgen05: out[v][n] = bias[n] + sum_{tap,c} x[v+tap][c] * w_packed[n][tap][c].
+ *   x        bf16 channels-last, `cin` visible channels (multiple of 8), row pitch x_ld
+ *   w_packed bf16 [w_rows][kd*kh*kw][cin_k]  (vfd_pack_weight), w_rows % 16 == 0, cin_k % kc == 0
+ *   bias     fp32 [w_rows] or NULL
+ *   out      bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1) channels-last, row pitch out_ld;
+ *            columns [0, out_cols) are written
+ *   kc       channel block per MMA K-slab: 16, 32 or 64 (selects the 32/64/128-byte swizzle)
+ * The input gradient (dgrad) is the same call on dy with mode-1 packed weights. */
+VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w_packed, int w_rows,
+                           int cin_k, const float* bias, void* out, long long out_ld, int out_cols,
+                           int out_fp32, int N, int D, int H, int W, int kd, int kh, int kw, int kc,
+                           void* stream);
+
+/* Weight gradient of the same conv (autograd of nn.Conv3d, reached from err_g.backward() /
+ * err_d.backward() at models/mygannet.py:311,344):
+ *   acc[tap][ci][co] += sum_v dy[v][co] * x[v+tap][ci]     (fp32, red.add across voxel splits)
+ * acc is [kd*kh*kw][ci_pad][co_pad] and must be zeroed by the caller; cout / cin are the valid
+ * channel counts. */
+VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
+                             int cin, float* acc, int co_pad, int ci_pad, int N, int D, int H, int W,
+                             int kd, int kh, int kw, void* stream);
+
+/* CUDA-core versions on the same operands; used by the tests to cross-check the tcgen05 kernels. */
+VFD_API int vfd_conv3d_fwd_direct(const void* x, long long x_ld, int cin, const void* w_packed,
+                                  int w_rows, int cin_k, const float* bias, void* out,
+                                  long long out_ld, int out_cols, int out_fp32, int N, int D, int H,
+                                  int W, int kd, int kh, int kw, void* stream);
+VFD_API int vfd_conv3d_wgrad_direct(const void* dy, long long dy_ld, int cout, const void* x,
+                                    long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int N,
+                                    int D, int H, int W, int kd, int kh, int kw, void* stream);
+
+/* ---- layout / weight packing -------------------------------------------------------------------
+ * fp32 NCDHW [N][Csrc][S] -> bf16 channels-last [N][S][ld] (Cp channels, zero beyond C).
+ * replicate = 1 repeats the source channels (gray2rgb, lib/utils.py:91-92). */
+VFD_API int vfd_pack_ncdhw(const float* src, void* dst, int N, int Csrc, long long S, int C,
+                           long long ld, int Cp, int replicate, void* stream);
+/* channels-last bf16 (src_fp32 = 0) or fp32 (1) [N][S][ld] -> fp32 NCDHW [N][C][S] */
+VFD_API int vfd_unpack_ncdhw(const void* src, int src_fp32, float* dst, int N, int C, long long S,
+                             long long ld, void* stream);
+/* fp32 nn.Conv3d weight [Cout][Cin][taps] -> bf16 GEMM operand [rows][taps][ck];
+ * mode 0: forward (row = cout, col = cin); mode 1: dgrad (row = cin, col = cout, taps mirrored). */
+VFD_API int vfd_pack_weight(const float* w, void* w_packed, int Cout, int Cin, int taps, int rows,
+                            int ck, int mode, void* stream);
+/* wgrad accumulator [taps][ci_pad][co_pad] -> fp32 weight gradient [Cout][Cin][taps] */
+VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int co_pad,
+                             int ci_pad, void* stream);
+
+/* ---- BatchNorm3d + (Leaky)ReLU (+ AvgPool3d, + Dropout) ----------------------------------------
+ * Replaces nn.BatchNorm3d + nn.ReLU (models/spatiotempconv.py:51-52,63), nn.BatchNorm3d +
+ * nn.LeakyReLU(0.2) / nn.LeakyReLU() (models/mygannet.py:19-20,25-26,109-110,114-115), the
+ * nn.AvgPool3d that always follows them (models/mygannet.py:41,132,174) and nn.Dropout(p=0.25)
+ * (models/mygannet.py:49,76,81,86,91).
+ * vfd_bn_stats accumulates per-channel sum / sum of squares into `sums` (double [2*C], must be
+ * zero on entry; vfd_bn_finalize clears it again). */
+VFD_API int vfd_bn_stats(const void* x, long long ld, int C, long long V, double* sums, void* stream);
+/* sums -> mean / invstd / scale (= gamma*invstd) / shift (= beta - mean*scale), fp32 [C] each, and
+ * the running-stat update (momentum, unbiased variance). train = 0 uses the running statistics. */
+VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* gamma,
+                            const float* beta, float* running_mean, float* running_var, float momentum,
+                            float eps, int train, float* mean, float* invstd, float* scale,
+                            float* shift, void* stream);
+/* out = dropout(act(y*scale + shift)), act(z) = z > 0 ? z : slope*z. out_full (full resolution)
+ * and out_pool (average over pd x ph x pw windows, floor semantics) are optional (NULL to skip).
+ * drop_p = 0 disables dropout; the mask is Philox4x32-10 keyed by (seed, voxel, channel group). */
+VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, int W, int C,
+                           const float* scale, const float* shift, float slope, void* out_full,
+                           long long full_ld, void* out_pool, long long pool_ld, int pd, int ph, int pw,
+                           float drop_p, unsigned long long seed, void* stream);
+/* Backward of the above through BatchNorm: given the gradients of out_full / out_pool (either may
+ * be NULL) computes dy (bf16), dgamma and dbeta (fp32 [Cvalid]). sums: zeroed double [2*C] scratch,
+ * c1 / c2: fp32 [C] scratch. */
+VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, int W, int C, int Cvalid,
+                           const float* mean, const float* invstd, const float* scale,
+                           const float* shift, float slope, const void* g_full, long long gf_ld,
+                           const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
+                           unsigned long long seed, int train, double* sums, float* c1, float* c2,
+                           float* dgamma, float* dbeta, void* dy, long long dy_ld, void* stream);
+/* out[c] += sum_v x[v][c]  (conv bias gradient when no BatchNorm follows) */
+VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream);
+
+/* ---- nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) + torch.cat -------------------
+ * (models/mygannet.py:50,77-94). Forward writes straight into a channel slice of the concat
+ * buffer (out_ld = total channels); backward gathers the gradient of the low-resolution input. */
+VFD_API int vfd_upsample2x_fwd(const void* x, long long x_ld, int N, int D, int H, int W, int C,
+                               void* out, long long out_ld, void* stream);
+VFD_API int vfd_upsample2x_bwd(const void* gout, long long go_ld, int N, int D, int H, int W, int C,
+                               void* gx, long long gx_ld, void* stream);
+
+/* ---- heads and losses ---------------------------------------------------------------------------
+ * nn.Sigmoid after conv_last (models/mygannet.py:53,99): logits fp32 [V][ld] column 0 -> predict. */
+VFD_API int vfd_sigmoid_head_fwd(const float* logits, long long ld, long long V, float* predict,
+                                 void* stream);
+VFD_API int vfd_sigmoid_head_bwd(const float* gpred, const float* predict, long long V, void* dlogit,
+                                 void* stream);
+/* weighted_bce (lib/utils.py:65-71): *loss_sum += sum(t*log p + pos_weight*(1-t)*log(1-p)) (the
+ * caller negates and divides by V); gpred (optional) = grad_scale * d(-sum)/dp. */
+VFD_API int vfd_weighted_bce(const float* predict, const float* target, long long V, float pos_weight,
+                             float grad_scale, double* loss_sum, float* gpred, void* stream);
+/* l2_loss numerator (lib/utils.py:59-63): *out += sum((a-b)^2) over channels-last bf16 tensors */
+VFD_API int vfd_sqdiff(const void* a, long long a_ld, const void* b, long long b_ld, int C, long long V,
+                       double* out, void* stream);
+
+/* ---- ConvLSTM cell update (models/convlstm.py:49-58) ---------------------------------------------
+ * gates fp32 channels-last [V][g_ld] in split order i,f,o,g; c/h fp32 [V][hid]; act (optional)
+ * receives the activated gates [V][4*hid] for the backward pass. */
+VFD_API int vfd_convlstm_cell_fwd(const float* gates, long long g_ld, const float* c_cur, int hid,
+                                  long long V, float* h_next, float* c_next, float* act, void* stream);
+VFD_API int vfd_convlstm_cell_bwd(const float* act, const float* c_cur, const float* c_next,
+                                  const float* dh, const float* dc_in, int hid, long long V,
+                                  void* dgates, long long dg_ld, float* dc_cur, void* stream);
+
+#endif /* VFD_B200_H */

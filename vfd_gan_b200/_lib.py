@@ -1,0 +1,83 @@
+"""ctypes binding of libvfd_b200.so (C-ABI declared in include/vfd_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C vfd_gan_b200/csrc``.
+There is no CPU fallback: if the shared object is missing, every op raises.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvfd_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_p, _ll, _i, _f, _ull = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong
+
+# name -> argument ctypes, in the order of include/vfd_b200.h
+SIGNATURES = {
+    "vfd_conv3d_fwd": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_wgrad": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_fwd_direct": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_wgrad_direct": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_pack_ncdhw": [_p, _p, _i, _i, _ll, _i, _ll, _i, _i, _p],
+    "vfd_unpack_ncdhw": [_p, _i, _p, _i, _i, _ll, _ll, _p],
+    "vfd_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vfd_bn_stats": [_p, _ll, _i, _ll, _p, _p],
+    "vfd_bn_finalize": [_p, _i, _i, _ll, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p],
+    "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p],
+    "vfd_bn_act_bwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i,
+                       _f, _ull, _i, _p, _p, _p, _p, _p, _p, _ll, _p],
+    "vfd_channel_sum": [_p, _ll, _i, _ll, _p, _p],
+    "vfd_upsample2x_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
+    "vfd_upsample2x_bwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
+    "vfd_sigmoid_head_fwd": [_p, _ll, _ll, _p, _p],
+    "vfd_sigmoid_head_bwd": [_p, _p, _ll, _p, _p],
+    "vfd_weighted_bce": [_p, _p, _ll, _f, _f, _p, _p, _p],
+    "vfd_sqdiff": [_p, _ll, _p, _ll, _i, _ll, _p, _p],
+    "vfd_convlstm_cell_fwd": [_p, _ll, _p, _i, _ll, _p, _p, _p, _p],
+    "vfd_convlstm_cell_bwd": [_p, _p, _p, _p, _p, _i, _ll, _p, _ll, _p, _p],
+}
+
+_lib = None
+LAUNCHES = 0  # number of C-ABI compute calls issued by this process (bench.py reports it)
+
+
+def build(force=False):
+    """Compile libvfd_b200.so for sm_100a with the in-tree Makefile (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", CSRC_DIR, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libvfd_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(vfd_gan_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.vfd_last_error.restype = ctypes.c_char_p
+        L.vfd_last_error.argtypes = []
+        L.vfd_abi_version.restype = ctypes.c_int
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; a non-zero status becomes RuntimeError (the reference's only
+    error convention on this path is torch raising RuntimeError)."""
+    global LAUNCHES
+    L = lib()
+    rc = getattr(L, name)(*args)
+    LAUNCHES += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.vfd_last_error().decode()}")

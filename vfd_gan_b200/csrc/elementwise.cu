@@ -1,0 +1,940 @@
+// HBM-bound kernels of the GAN step: layout packing, BatchNorm3d statistics / fused
+// BatchNorm + (Leaky)ReLU (+ AvgPool3d, + Dropout) forward and backward, trilinear x2 upsample
+// into a concat buffer, loss reductions and the ConvLSTM cell update.
+//
+// All activations are channels-last bf16 [N][D][H][W][ld] with the logical channel count C a
+// multiple of 8, so every thread moves one 128-bit vector (8 channels) per access and a warp
+// touches consecutive 16-byte chunks of a voxel row.
+//
+// Reference call sites replaced: nn.BatchNorm3d/ReLU (models/spatiotempconv.py:51-52,63),
+// BatchNorm3d/LeakyReLU (models/mygannet.py:19-20,25-26,109-110,114-115), AvgPool3d (:41,132,174),
+// Dropout (:49,76), Upsample+cat (:50,77-94), l2_loss / weighted_bce (lib/utils.py:59-71),
+// ConvLSTM cell update (models/convlstm.py:49-58).
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "vfd_internal.h"
+
+namespace vfd {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// Inverted-dropout multipliers (0 or 1/(1-p)) for the 8 channels of group cg at voxel vox.
+__device__ __forceinline__ void dropout8(unsigned long long seed, long long vox, int cg, float p,
+                                         float* m) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint4 a = philox4x32_10(make_uint4((uint32_t)vox, (uint32_t)(vox >> 32), (uint32_t)cg, 0u), key);
+  const uint4 b = philox4x32_10(make_uint4((uint32_t)vox, (uint32_t)(vox >> 32), (uint32_t)cg, 1u), key);
+  const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const float keep = 1.0f / (1.0f - p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = ((r[i] >> 8) * (1.0f / 16777216.0f) >= p) ? keep : 0.0f;
+}
+
+// ------------------------------------------------------------------------------ layout packing
+// fp32 NCDHW [N][Csrc][S] -> bf16 channels-last [N][S][ld]; channel c of the output reads source
+// channel (c % Csrc) when `replicate` (gray2rgb, lib/utils.py:91-92), zero beyond C.
+__global__ void pack_ncdhw_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N,
+                                  int Csrc, long long S, int C, long long ld, int Cp,
+                                  int replicate) {
+  const long long total = (long long)N * S * (Cp / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i % S;
+    const long long t = i / S;
+    const int cg = (int)(t % (Cp / 8));
+    const long long n = t / (Cp / 8);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      float x = 0.f;
+      if (c < C) {
+        const int cs = replicate ? (c % Csrc) : c;
+        x = src[((long long)n * Csrc + cs) * S + s];
+      }
+      v[j] = x;
+    }
+    store8(dst + ((long long)n * S + s) * ld + cg * 8, v);
+  }
+}
+
+// channels-last (bf16 or fp32) [N][S][ld] -> fp32 NCDHW [N][C][S]
+template <typename T>
+__global__ void unpack_ncdhw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N,
+                                    int C, long long S, long long ld) {
+  const long long total = (long long)N * C * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i % S;
+    const long long t = i / S;
+    const int c = (int)(t % C);
+    const long long n = t / C;
+    dst[i] = (float)src[((long long)n * S + s) * ld + c];
+  }
+}
+
+// fp32 conv weight [Cout][Cin][taps] -> bf16 packed GEMM operand.
+//  mode 0 (forward): Wp[row=co][tap][c=ci]
+//  mode 1 (dgrad)  : Wp[row=ci][tap][c=co] with the taps mirrored (tap -> taps-1-tap)
+__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Cout,
+                                   int Cin, int taps, int rows, int ck, int mode) {
+  const long long total = (long long)rows * taps * ck;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ck);
+    const long long t = i / ck;
+    const int tap = (int)(t % taps);
+    const int row = (int)(t / taps);
+    float v = 0.f;
+    if (mode == 0) {
+      if (row < Cout && c < Cin) v = w[((long long)row * Cin + c) * taps + tap];
+    } else {
+      if (row < Cin && c < Cout) v = w[((long long)c * Cin + row) * taps + (taps - 1 - tap)];
+    }
+    wp[i] = __float2bfloat16(v);
+  }
+}
+
+// wgrad accumulator [taps][ci_pad][co_pad] fp32 -> weight gradient [Cout][Cin][taps] fp32
+__global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ gw, int Cout,
+                                    int Cin, int taps, int co_pad, int ci_pad) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const long long t = i / taps;
+    const int ci = (int)(t % Cin);
+    const int co = (int)(t / Cin);
+    gw[i] = acc[((long long)tap * ci_pad + ci) * co_pad + co];
+  }
+}
+
+// ------------------------------------------------------------------------------ BN statistics
+// Per-channel sum / sum of squares over V voxels; fp32 per-thread partials, double across blocks.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
+                double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][C]
+  const int CG = C / 8;
+  const int rows_per_iter = 256 / CG;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const bool active = tid < rows_per_iter * CG;
+  const int cg = tid % CG;
+  const int rl = tid / CG;
+  const long long per_block = (V + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per_block;
+  const long long r1 = (r0 + per_block < V) ? (r0 + per_block) : V;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  if (active) {
+    for (long long r = r0 + rl; r < r1; r += rows_per_iter) {
+      float v[8];
+      load8(x + r * ld + cg * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        ss[j] = fmaf(v[j], v[j], ss[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], s[j]);
+      atomicAdd(&sh[C + cg * 8 + j], ss[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+// sums -> (mean, invstd, scale, shift), running-stat update, and clears the accumulator.
+// Matches nn.BatchNorm3d: biased variance for normalisation, unbiased for running_var,
+// momentum 0.1, eps 1e-5. In eval mode (train == 0) the running statistics are used instead.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, int C, int Cvalid, long long V,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, int train, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                   float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean = 0.f, invstd = 0.f, sc = 0.f, sh = 0.f;
+  if (c < Cvalid) {
+    if (train) {
+      const double m = sums[c] / (double)V;
+      double var = sums[C + c] / (double)V - m * m;
+      if (var < 0) var = 0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean != nullptr) {
+        const double unbiased = V > 1 ? var * (double)V / (double)(V - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    } else {
+      mean = running_mean[c];
+      invstd = rsqrtf(running_var[c] + eps);
+    }
+    sc = gamma[c] * invstd;
+    sh = beta[c] - mean * sc;
+  }
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  scale_out[c] = sc;
+  shift_out[c] = sh;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+struct ActGeom {
+  int N, D, H, W;     // full-resolution voxel grid
+  int pd, ph, pw;     // pooling window (1 or 2 per axis); floor semantics like nn.AvgPool3d
+  int C;              // padded channel count (multiple of 8)
+};
+
+// out = dropout(act(y * scale + shift)); optionally also the average-pooled tensor.
+// One thread per (pool window, channel group).
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
+                  const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                  bf16* __restrict__ out_full, long long full_ld, bf16* __restrict__ out_pool,
+                  long long pool_ld, float drop_p, unsigned long long seed) {
+  const int CG = g.C / 8;
+  const int WD = (g.D + g.pd - 1) / g.pd, WH = (g.H + g.ph - 1) / g.ph, WW = (g.W + g.pw - 1) / g.pw;
+  const int PD = g.D / g.pd, PH = g.H / g.ph, PW = g.W / g.pw;
+  const long long total = (long long)g.N * WD * WH * WW * CG;
+  const float inv_win = 1.0f / (float)(g.pd * g.ph * g.pw);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long t = i / CG;
+    const int ww = (int)(t % WW);
+    t /= WW;
+    const int wh = (int)(t % WH);
+    t /= WH;
+    const int wd = (int)(t % WD);
+    const int n = (int)(t / WD);
+    float sc[8], sf[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cg * 8 + j);
+      sf[j] = __ldg(shift + cg * 8 + j);
+      acc[j] = 0.f;
+    }
+    for (int a = 0; a < g.pd; ++a)
+      for (int b = 0; b < g.ph; ++b)
+        for (int c = 0; c < g.pw; ++c) {
+          const int d = wd * g.pd + a, h = wh * g.ph + b, w = ww * g.pw + c;
+          if (d >= g.D || h >= g.H || w >= g.W) continue;
+          const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+          float v[8];
+          load8(y + vox * y_ld + cg * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(v[j], sc[j], sf[j]);
+            v[j] = z > 0.f ? z : z * slope;
+          }
+          if (drop_p > 0.f) {
+            float m[8];
+            dropout8(seed, vox, cg, drop_p, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= m[j];
+          }
+          if (out_full != nullptr) store8(out_full + vox * full_ld + cg * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+    if (out_pool != nullptr && wd < PD && wh < PH && ww < PW) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv_win;
+      const long long pv = (((long long)n * PD + wd) * PH + wh) * PW + ww;
+      store8(out_pool + pv * pool_ld + cg * 8, acc);
+    }
+  }
+}
+
+// Upstream gradient of the activation output for 8 channels of voxel (n,d,h,w):
+// g_full (gradient of the full-resolution output) + g_pool / window (gradient of the pooled one),
+// times the dropout multiplier and the (leaky) ReLU slope.
+__device__ __forceinline__ void act_upstream(const bf16* __restrict__ y, long long y_ld,
+                                             const ActGeom& g, const float* sc, const float* sf,
+                                             float slope, const bf16* __restrict__ g_full,
+                                             long long gf_ld, const bf16* __restrict__ g_pool,
+                                             long long gp_ld, float drop_p, unsigned long long seed,
+                                             int n, int d, int h, int w, int cg, float* yv,
+                                             float* gv) {
+  const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+  load8(y + vox * y_ld + cg * 8, yv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+  if (g_full != nullptr) load8(g_full + vox * gf_ld + cg * 8, gv);
+  if (g_pool != nullptr) {
+    const int PD = g.D / g.pd, PH = g.H / g.ph, PW = g.W / g.pw;
+    const int qd = d / g.pd, qh = h / g.ph, qw = w / g.pw;
+    if (qd < PD && qh < PH && qw < PW) {
+      float t[8];
+      const long long pv = (((long long)n * PD + qd) * PH + qh) * PW + qw;
+      load8(g_pool + pv * gp_ld + cg * 8, t);
+      const float inv_win = 1.0f / (float)(g.pd * g.ph * g.pw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = fmaf(t[j], inv_win, gv[j]);
+    }
+  }
+  if (drop_p > 0.f) {
+    float m[8];
+    dropout8(seed, vox, cg, drop_p, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] *= m[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = fmaf(yv[j], sc[j], sf[j]);
+    gv[j] = z > 0.f ? gv[j] : gv[j] * slope;
+  }
+}
+
+// Pass 1 of BN backward: per-channel sum(g) and sum(g * xhat).
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         float slope, const bf16* __restrict__ g_full, long long gf_ld,
+                         const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
+                         unsigned long long seed, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][C]
+  const int C = g.C;
+  const int CG = C / 8;
+  const int rows_per_iter = 256 / CG;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const long long V = (long long)g.N * g.D * g.H * g.W;
+  const bool active = tid < rows_per_iter * CG;
+  const int cg = tid % CG;
+  const int rl = tid / CG;
+  const long long per_block = (V + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per_block;
+  const long long r1 = (r0 + per_block < V) ? (r0 + per_block) : V;
+  if (active) {
+    float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cg * 8 + j);
+      sf[j] = __ldg(shift + cg * 8 + j);
+      mu[j] = __ldg(mean + cg * 8 + j);
+      is[j] = __ldg(invstd + cg * 8 + j);
+      s1[j] = s2[j] = 0.f;
+    }
+    for (long long r = r0 + rl; r < r1; r += rows_per_iter) {
+      long long t = r;
+      const int w = (int)(t % g.W);
+      t /= g.W;
+      const int h = (int)(t % g.H);
+      t /= g.H;
+      const int d = (int)(t % g.D);
+      const int n = (int)(t / g.D);
+      float yv[8], gv[8];
+      act_upstream(y, y_ld, g, sc, sf, slope, g_full, gf_ld, g_pool, gp_ld, drop_p, seed, n, d, h,
+                   w, cg, yv, gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += gv[j];
+        s2[j] = fmaf(gv[j], (yv[j] - mu[j]) * is[j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], s1[j]);
+      atomicAdd(&sh[C + cg * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+// sums -> dgamma, dbeta and the two per-channel means used by pass 2; clears the accumulator.
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, int Cvalid, long long V,
+                                       int train, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ c1,
+                                       float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sg = sums[c], sgx = sums[C + c];
+  if (c < Cvalid) {
+    dbeta[c] = (float)sg;
+    dgamma[c] = (float)sgx;
+  }
+  c1[c] = train ? (float)(sg / (double)V) : 0.f;
+  c2[c] = train ? (float)(sgx / (double)V) : 0.f;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+// Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2)
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        float slope, const bf16* __restrict__ g_full, long long gf_ld,
+                        const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
+                        unsigned long long seed, const float* __restrict__ c1,
+                        const float* __restrict__ c2, bf16* __restrict__ dy, long long dy_ld) {
+  const int CG = g.C / 8;
+  const long long V = (long long)g.N * g.D * g.H * g.W;
+  const long long total = V * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const long long r = i / CG;
+    long long t = r;
+    const int w = (int)(t % g.W);
+    t /= g.W;
+    const int h = (int)(t % g.H);
+    t /= g.H;
+    const int d = (int)(t % g.D);
+    const int n = (int)(t / g.D);
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cg * 8 + j);
+      sf[j] = __ldg(shift + cg * 8 + j);
+    }
+    float yv[8], gv[8], o[8];
+    act_upstream(y, y_ld, g, sc, sf, slope, g_full, gf_ld, g_pool, gp_ld, drop_p, seed, n, d, h, w,
+                 cg, yv, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const float xh = (yv[j] - __ldg(mean + c)) * __ldg(invstd + c);
+      o[j] = sc[j] * (gv[j] - __ldg(c1 + c) - xh * __ldg(c2 + c));
+    }
+    store8(dy + r * dy_ld + cg * 8, o);
+  }
+}
+
+// Per-channel sum over voxels of a channels-last bf16 tensor (conv bias gradient).
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
+                   float* __restrict__ out) {
+  extern __shared__ float sh[];  // [C]
+  const int CG = C / 8;
+  const int rows_per_iter = 256 / CG;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const int cg = tid % CG;
+  const int rl = tid / CG;
+  const long long per_block = (V + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per_block;
+  const long long r1 = (r0 + per_block < V) ? (r0 + per_block) : V;
+  if (tid < rows_per_iter * CG) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (long long r = r0 + rl; r < r1; r += rows_per_iter) {
+      float v[8];
+      load8(x + r * ld + cg * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cg * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += 256) atomicAdd(&out[i], sh[i]);
+}
+
+// ------------------------------------------------------------------------------ upsample x2
+// nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True) (models/mygannet.py:50):
+// source index = dst * (in-1)/(out-1), computed in fp32 like ATen's upsample kernels.
+__device__ __forceinline__ void src_index(int o, int in_size, int out_size, int& i0, int& i1,
+                                          float& l0, float& l1) {
+  const float r = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  const float s = r * (float)o;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int N, int D, int H, int W,
+                      int C, bf16* __restrict__ out, long long out_ld) {
+  const int CG = C / 8;
+  const int OD = 2 * D, OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * OD * OH * OW * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long t = i / CG;
+    const long long ov = t;
+    const int ow = (int)(t % OW);
+    t /= OW;
+    const int oh = (int)(t % OH);
+    t /= OH;
+    const int od = (int)(t % OD);
+    const int n = (int)(t / OD);
+    int d0, d1, h0, h1, w0, w1;
+    float ld0, ld1, lh0, lh1, lw0, lw1;
+    src_index(od, D, OD, d0, d1, ld0, ld1);
+    src_index(oh, H, OH, h0, h1, lh0, lh1);
+    src_index(ow, W, OW, w0, w1, lw0, lw1);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int d = a ? d1 : d0, h = b ? h1 : h0, w = c ? w1 : w0;
+          const float wt = (a ? ld1 : ld0) * (b ? lh1 : lh0) * (c ? lw1 : lw0);
+          float v[8];
+          load8(x + ((((long long)n * D + d) * H + h) * W + w) * x_ld + cg * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
+        }
+    store8(out + ov * out_ld + cg * 8, acc);
+  }
+}
+
+// weights with which input index i contributes to outputs o in [2i-2, 2i+4] along one axis
+__device__ __forceinline__ void bwd_weights(int i, int in_size, float* wts) {
+  const int out_size = 2 * in_size;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int o = 2 * i - 2 + k;
+    float wt = 0.f;
+    if (o >= 0 && o < out_size) {
+      int i0, i1;
+      float l0, l1;
+      src_index(o, in_size, out_size, i0, i1, l0, l1);
+      if (i0 == i) wt += l0;
+      if (i1 == i) wt += l1;
+    }
+    wts[k] = wt;
+  }
+}
+
+// gradient of the x2 trilinear upsample w.r.t. its low-resolution input (gather form)
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const bf16* __restrict__ go, long long go_ld, int N, int D, int H, int W,
+                      int C, bf16* __restrict__ gx, long long gx_ld) {
+  const int CG = C / 8;
+  const int OD = 2 * D, OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * D * H * W * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long t = i / CG;
+    const long long iv = t;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    float wd[7], wh[7], ww[7];
+    bwd_weights(d, D, wd);
+    bwd_weights(h, H, wh);
+    bwd_weights(w, W, ww);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < 7; ++a) {
+      if (wd[a] == 0.f) continue;
+      const int od = 2 * d - 2 + a;
+      for (int b = 0; b < 7; ++b) {
+        if (wh[b] == 0.f) continue;
+        const int oh = 2 * h - 2 + b;
+        for (int c = 0; c < 7; ++c) {
+          if (ww[c] == 0.f) continue;
+          const int ow = 2 * w - 2 + c;
+          const float wt = wd[a] * wh[b] * ww[c];
+          float v[8];
+          load8(go + ((((long long)n * OD + od) * OH + oh) * OW + ow) * go_ld + cg * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
+        }
+      }
+    }
+    store8(gx + iv * gx_ld + cg * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------ heads / losses
+// predict = sigmoid(logit[:,0]) from the fp32 conv_last output [V][ld]
+__global__ void sigmoid_head_fwd_kernel(const float* __restrict__ logits, long long ld, long long V,
+                                        float* __restrict__ predict) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V;
+       i += (long long)gridDim.x * blockDim.x)
+    predict[i] = 1.f / (1.f + expf(-logits[i * ld]));
+}
+// dlogit (bf16 channels-last, 8 channels, only channel 0 non-zero) = g * p * (1 - p)
+__global__ void sigmoid_head_bwd_kernel(const float* __restrict__ gpred,
+                                        const float* __restrict__ predict, long long V,
+                                        bf16* __restrict__ dlogit) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float p = predict[i];
+    float v[8] = {gpred[i] * p * (1.f - p), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    store8(dlogit + i * 8, v);
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+// weighted_bce (lib/utils.py:65-71): p clamped to [1e-8, 1-1e-8] in fp32 (the upper bound rounds
+// to 1.0f exactly like the reference), loss = -mean(t*log p + pos_weight*(1-t)*log(1-p)).
+// Also emits d loss / d predict scaled by grad_scale (0 where the clamp is active).
+__global__ void __launch_bounds__(256)
+wbce_kernel(const float* __restrict__ predict, const float* __restrict__ target, long long V,
+            float pos_weight, float grad_scale, double* __restrict__ loss_sum,
+            float* __restrict__ gpred) {
+  double local = 0.0;
+  const float lo = 1e-8f, hi = 1.0f - 1e-8f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float p0 = predict[i], t = target[i];
+    const float p = fminf(fmaxf(p0, lo), hi);
+    const float l = t * logf(p) + pos_weight * (1.f - t) * logf(1.f - p);
+    local += (double)l;
+    if (gpred != nullptr) {
+      const bool pass = (p0 >= lo) && (p0 <= hi);
+      const float gl = t / p - pos_weight * (1.f - t) / (1.f - p);
+      gpred[i] = pass ? (-grad_scale * gl) : 0.f;
+    }
+  }
+  local = block_sum(local);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, local);
+}
+
+// l2_loss numerator (lib/utils.py:59-63) between two channels-last bf16 tensors
+__global__ void __launch_bounds__(256)
+sqdiff_kernel(const bf16* __restrict__ a, long long a_ld, const bf16* __restrict__ b, long long b_ld,
+              int C, long long V, double* __restrict__ out) {
+  const int CG = C / 8;
+  const long long total = V * CG;
+  double local = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const long long r = i / CG;
+    float x[8], y[8];
+    load8(a + r * a_ld + cg * 8, x);
+    load8(b + r * b_ld + cg * 8, y);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = x[j] - y[j];
+      s = fmaf(d, d, s);
+    }
+    local += (double)s;
+  }
+  local = block_sum(local);
+  if (threadIdx.x == 0) atomicAdd(out, local);
+}
+
+// ------------------------------------------------------------------------------ ConvLSTM cell
+// gates: fp32 channels-last [V][4*hid] in the reference's split order i,f,o,g
+// (models/convlstm.py:49-58); c, h: fp32 [V][hid].
+__global__ void convlstm_cell_fwd_kernel(const float* __restrict__ gates, long long g_ld,
+                                         const float* __restrict__ c_cur, int hid, long long V,
+                                         float* __restrict__ h_next, float* __restrict__ c_next,
+                                         float* __restrict__ act) {
+  const long long total = V * hid;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % hid);
+    const long long v = i / hid;
+    const float* gp = gates + v * g_ld;
+    const float gi = 1.f / (1.f + expf(-gp[k]));
+    const float gf = 1.f / (1.f + expf(-gp[hid + k]));
+    const float go = 1.f / (1.f + expf(-gp[2 * hid + k]));
+    const float gg = tanhf(gp[3 * hid + k]);
+    const float c = gf * c_cur[i] + gi * gg;
+    c_next[i] = c;
+    h_next[i] = go * tanhf(c);
+    if (act != nullptr) {  // saved activations for backward: [V][4*hid]
+      float* ap = act + v * 4 * hid;
+      ap[k] = gi;
+      ap[hid + k] = gf;
+      ap[2 * hid + k] = go;
+      ap[3 * hid + k] = gg;
+    }
+  }
+}
+
+// backward of the cell update: given dh_next, dc_next -> dgates (bf16 channels-last, for the gate
+// conv's dgrad/wgrad) and dc_cur.
+__global__ void convlstm_cell_bwd_kernel(const float* __restrict__ act, const float* __restrict__ c_cur,
+                                         const float* __restrict__ c_next,
+                                         const float* __restrict__ dh, const float* __restrict__ dc_in,
+                                         int hid, long long V, bf16* __restrict__ dgates,
+                                         long long dg_ld, float* __restrict__ dc_cur) {
+  const long long total = V * hid;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % hid);
+    const long long v = i / hid;
+    const float* ap = act + v * 4 * hid;
+    const float gi = ap[k], gf = ap[hid + k], go = ap[2 * hid + k], gg = ap[3 * hid + k];
+    const float tc = tanhf(c_next[i]);
+    const float dhn = dh != nullptr ? dh[i] : 0.f;
+    const float dcn = (dc_in != nullptr ? dc_in[i] : 0.f) + dhn * go * (1.f - tc * tc);
+    bf16* dg = dgates + v * dg_ld;
+    dg[k] = __float2bfloat16(dcn * gg * gi * (1.f - gi));
+    dg[hid + k] = __float2bfloat16(dcn * c_cur[i] * gf * (1.f - gf));
+    dg[2 * hid + k] = __float2bfloat16(dhn * tc * go * (1.f - go));
+    dg[3 * hid + k] = __float2bfloat16(dcn * gi * (1.f - gg * gg));
+    dc_cur[i] = dcn * gf;
+  }
+}
+
+static inline int grid_for(long long total, int block = 256, int max_blocks = 148 * 16) {
+  long long b = (total + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+static inline int check_cl(const void* p, long long ld, int C, const char* what) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld % 8) || (C % 8) || C <= 0 || C > 2048) return set_error(VFD_ERR_ARG, what);
+  return 0;
+}
+
+}  // namespace vfd
+
+using namespace vfd;
+#define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+VFD_API int vfd_pack_ncdhw(const float* src, void* dst, int N, int Csrc, long long S, int C,
+                              long long ld, int Cp, int replicate, void* stream_) {
+  if (int e = check_cl(dst, ld, Cp, "pack_ncdhw: destination must be 16-byte aligned, C%8==0")) return e;
+  const long long total = (long long)N * S * (Cp / 8);
+  if (total == 0) return 0;
+  pack_ncdhw_kernel<<<grid_for(total), 256, 0, STREAM>>>(src, (bf16*)dst, N, Csrc, S, C, ld, Cp, replicate);
+  return check_launch("pack_ncdhw");
+}
+
+VFD_API int vfd_unpack_ncdhw(const void* src, int src_fp32, float* dst, int N, int C, long long S,
+                                long long ld, void* stream_) {
+  const long long total = (long long)N * C * S;
+  if (total == 0) return 0;
+  if (src_fp32)
+    unpack_ncdhw_kernel<float><<<grid_for(total), 256, 0, STREAM>>>((const float*)src, dst, N, C, S, ld);
+  else
+    unpack_ncdhw_kernel<bf16><<<grid_for(total), 256, 0, STREAM>>>((const bf16*)src, dst, N, C, S, ld);
+  return check_launch("unpack_ncdhw");
+}
+
+VFD_API int vfd_pack_weight(const float* w, void* wp, int Cout, int Cin, int taps, int rows, int ck,
+                               int mode, void* stream_) {
+  const long long total = (long long)rows * taps * ck;
+  if (total == 0) return 0;
+  pack_weight_kernel<<<grid_for(total), 256, 0, STREAM>>>(w, (bf16*)wp, Cout, Cin, taps, rows, ck, mode);
+  return check_launch("pack_weight");
+}
+
+VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int co_pad,
+                                int ci_pad, void* stream_) {
+  const long long total = (long long)Cout * Cin * taps;
+  if (total == 0) return 0;
+  unpack_wgrad_kernel<<<grid_for(total), 256, 0, STREAM>>>(acc, gw, Cout, Cin, taps, co_pad, ci_pad);
+  return check_launch("unpack_wgrad");
+}
+
+static int stats_grid(long long V, int C) {
+  const int rows_per_iter = 256 / (C / 8);
+  long long b = (V + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+VFD_API int vfd_bn_stats(const void* x, long long ld, int C, long long V, double* sums, void* stream_) {
+  if (int e = check_cl(x, ld, C, "bn_stats: bad tensor")) return e;
+  if (V <= 0) return 0;
+  bn_stats_kernel<<<stats_grid(V, C), 256, 2 * C * sizeof(float), STREAM>>>((const bf16*)x, ld, C, V, sums);
+  return check_launch("bn_stats");
+}
+
+VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               float momentum, float eps, int train, float* mean, float* invstd,
+                               float* scale, float* shift, void* stream_) {
+  if (!train && (running_mean == nullptr || running_var == nullptr))
+    return set_error(VFD_ERR_ARG, "bn_finalize: eval mode needs running statistics");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, gamma, beta, running_mean,
+                                                          running_var, momentum, eps, train, mean,
+                                                          invstd, scale, shift);
+  return check_launch("bn_finalize");
+}
+
+static int fill_act_geom(ActGeom& g, int N, int D, int H, int W, int C, int pd, int ph, int pw) {
+  if ((pd != 1 && pd != 2) || (ph != 1 && ph != 2) || (pw != 1 && pw != 2))
+    return set_error(VFD_ERR_ARG, "pool window must be 1 or 2 per axis");
+  g.N = N; g.D = D; g.H = H; g.W = W; g.C = C; g.pd = pd; g.ph = ph; g.pw = pw;
+  return 0;
+}
+
+VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, int W, int C,
+                              const float* scale, const float* shift, float slope, void* out_full,
+                              long long full_ld, void* out_pool, long long pool_ld, int pd, int ph,
+                              int pw, float drop_p, unsigned long long seed, void* stream_) {
+  if (int e = check_cl(y, y_ld, C, "bn_act_fwd: bad input")) return e;
+  if (out_full && check_cl(out_full, full_ld, C, "bn_act_fwd: bad full output")) return VFD_ERR_ARG;
+  if (out_pool && check_cl(out_pool, pool_ld, C, "bn_act_fwd: bad pooled output")) return VFD_ERR_ARG;
+  ActGeom g;
+  if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
+  const long long total = (long long)N * ((D + pd - 1) / pd) * ((H + ph - 1) / ph) * ((W + pw - 1) / pw) * (C / 8);
+  if (total == 0) return 0;
+  bn_act_fwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)y, y_ld, g, scale, shift, slope,
+                                                         (bf16*)out_full, full_ld, (bf16*)out_pool,
+                                                         pool_ld, drop_p, seed);
+  return check_launch("bn_act_fwd");
+}
+
+VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, int W, int C, int Cvalid,
+                              const float* mean, const float* invstd, const float* scale,
+                              const float* shift, float slope, const void* g_full, long long gf_ld,
+                              const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
+                              unsigned long long seed, int train, double* sums, float* c1, float* c2,
+                              float* dgamma, float* dbeta, void* dy, long long dy_ld, void* stream_) {
+  if (int e = check_cl(y, y_ld, C, "bn_act_bwd: bad input")) return e;
+  if (int e = check_cl(dy, dy_ld, C, "bn_act_bwd: bad output")) return e;
+  if (g_full && check_cl(g_full, gf_ld, C, "bn_act_bwd: bad full-resolution gradient")) return VFD_ERR_ARG;
+  if (g_pool && check_cl(g_pool, gp_ld, C, "bn_act_bwd: bad pooled gradient")) return VFD_ERR_ARG;
+  ActGeom g;
+  if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
+  const long long V = (long long)N * D * H * W;
+  if (V == 0) return 0;
+  bn_act_bwd_reduce_kernel<<<stats_grid(V, C), 256, 2 * C * sizeof(float), STREAM>>>(
+      (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
+      (const bf16*)g_pool, gp_ld, drop_p, seed, sums);
+  if (int e = check_launch("bn_act_bwd_reduce")) return e;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
+  if (int e = check_launch("bn_bwd_finalize")) return e;
+  bn_act_bwd_apply_kernel<<<grid_for(V * (C / 8)), 256, 0, STREAM>>>(
+      (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
+      (const bf16*)g_pool, gp_ld, drop_p, seed, c1, c2, (bf16*)dy, dy_ld);
+  return check_launch("bn_act_bwd_apply");
+}
+
+VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream_) {
+  if (int e = check_cl(x, ld, C, "channel_sum: bad tensor")) return e;
+  if (V <= 0) return 0;
+  channel_sum_kernel<<<stats_grid(V, C), 256, C * sizeof(float), STREAM>>>((const bf16*)x, ld, C, V, out);
+  return check_launch("channel_sum");
+}
+
+VFD_API int vfd_upsample2x_fwd(const void* x, long long x_ld, int N, int D, int H, int W, int C,
+                                  void* out, long long out_ld, void* stream_) {
+  if (int e = check_cl(x, x_ld, C, "upsample2x_fwd: bad input")) return e;
+  if (int e = check_cl(out, out_ld, C, "upsample2x_fwd: bad output")) return e;
+  const long long total = (long long)N * D * H * W * 8 * (C / 8);
+  if (total == 0) return 0;
+  upsample2x_fwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)x, x_ld, N, D, H, W, C, (bf16*)out, out_ld);
+  return check_launch("upsample2x_fwd");
+}
+
+VFD_API int vfd_upsample2x_bwd(const void* go, long long go_ld, int N, int D, int H, int W, int C,
+                                  void* gx, long long gx_ld, void* stream_) {
+  if (int e = check_cl(go, go_ld, C, "upsample2x_bwd: bad input")) return e;
+  if (int e = check_cl(gx, gx_ld, C, "upsample2x_bwd: bad output")) return e;
+  const long long total = (long long)N * D * H * W * (C / 8);
+  if (total == 0) return 0;
+  upsample2x_bwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)go, go_ld, N, D, H, W, C, (bf16*)gx, gx_ld);
+  return check_launch("upsample2x_bwd");
+}
+
+VFD_API int vfd_sigmoid_head_fwd(const float* logits, long long ld, long long V, float* predict, void* stream_) {
+  if (V <= 0) return 0;
+  sigmoid_head_fwd_kernel<<<grid_for(V), 256, 0, STREAM>>>(logits, ld, V, predict);
+  return check_launch("sigmoid_head_fwd");
+}
+
+VFD_API int vfd_sigmoid_head_bwd(const float* gpred, const float* predict, long long V, void* dlogit, void* stream_) {
+  if (V <= 0) return 0;
+  sigmoid_head_bwd_kernel<<<grid_for(V), 256, 0, STREAM>>>(gpred, predict, V, (bf16*)dlogit);
+  return check_launch("sigmoid_head_bwd");
+}
+
+VFD_API int vfd_weighted_bce(const float* predict, const float* target, long long V, float pos_weight,
+                                float grad_scale, double* loss_sum, float* gpred, void* stream_) {
+  if (V <= 0) return 0;
+  wbce_kernel<<<grid_for(V, 256, 148 * 4), 256, 0, STREAM>>>(predict, target, V, pos_weight, grad_scale, loss_sum, gpred);
+  return check_launch("weighted_bce");
+}
+
+VFD_API int vfd_sqdiff(const void* a, long long a_ld, const void* b, long long b_ld, int C, long long V,
+                          double* out, void* stream_) {
+  if (int e = check_cl(a, a_ld, C, "sqdiff: bad a")) return e;
+  if (int e = check_cl(b, b_ld, C, "sqdiff: bad b")) return e;
+  if (V <= 0) return 0;
+  sqdiff_kernel<<<grid_for(V * (C / 8), 256, 148 * 4), 256, 0, STREAM>>>((const bf16*)a, a_ld, (const bf16*)b, b_ld, C, V, out);
+  return check_launch("sqdiff");
+}
+
+VFD_API int vfd_convlstm_cell_fwd(const float* gates, long long g_ld, const float* c_cur, int hid,
+                                     long long V, float* h_next, float* c_next, float* act, void* stream_) {
+  if (V <= 0) return 0;
+  convlstm_cell_fwd_kernel<<<grid_for(V * hid), 256, 0, STREAM>>>(gates, g_ld, c_cur, hid, V, h_next, c_next, act);
+  return check_launch("convlstm_cell_fwd");
+}
+
+VFD_API int vfd_convlstm_cell_bwd(const float* act, const float* c_cur, const float* c_next,
+                                     const float* dh, const float* dc_in, int hid, long long V,
+                                     void* dgates, long long dg_ld, float* dc_cur, void* stream_) {
+  if (V <= 0) return 0;
+  convlstm_cell_bwd_kernel<<<grid_for(V * hid), 256, 0, STREAM>>>(act, c_cur, c_next, dh, dc_in, hid, V, (bf16*)dgates, dg_ld, dc_cur);
+  return check_launch("convlstm_cell_bwd");
+}

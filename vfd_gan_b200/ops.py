@@ -1,0 +1,514 @@
+"""torch.library registration and autograd wiring of the libvfd_b200 kernels.
+
+Everything here works on *channels-last bf16* activations: a torch tensor of shape
+``[N, D, H, W, C]`` with ``stride(-1) == 1`` and ``C % 8 == 0``; the voxel pitch ``stride(3)`` may
+exceed ``C`` (channel slice of a concat buffer). The ``nn.Module`` surface in ``spatiotempconv.py``
+/ ``mygannet.py`` / ``convlstm.py`` converts from / to the reference's fp32 NCDHW at its boundary.
+
+Ops are registered in the ``vfd_b200`` torch.library namespace with CUDA implementations that call
+the C-ABI through ctypes (``_lib.call``); autograd is provided by the ``*Fn`` classes below.
+"""
+import torch
+
+from . import _lib
+
+_NS = "vfd_b200"
+_deflib = torch.library.Library(_NS, "DEF")
+_registered = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _define(schema, fn):
+    """Define ``vfd_b200::<name>`` and register ``fn`` as its CUDA implementation."""
+    name = schema.split("(")[0]
+    _deflib.define(schema)
+    _deflib.impl(name, fn, "CUDA")
+    _registered[name] = fn
+    return getattr(getattr(torch.ops, _NS), name)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pick_kc(cin_p):
+    """Channel block per MMA K-slab (16/32/64): the largest one whose padded K stays within 10 %
+    of the tightest padding."""
+    best = min(round_up(cin_p, k) for k in (16, 32, 64))
+    for kc in (64, 32, 16):
+        if round_up(cin_p, kc) <= 1.1 * best:
+            return kc
+    return 16
+
+
+def _check_cl(t, what):
+    if t.dtype != torch.bfloat16 or t.dim() != 5 or t.stride(-1) != 1 or t.shape[-1] % 8:
+        raise RuntimeError(f"{what}: expected a channels-last bf16 [N,D,H,W,C] tensor with C % 8 == 0, "
+                           f"got {tuple(t.shape)} {t.dtype} strides {t.stride()}")
+    N, D, H, W, C = t.shape
+    ld = t.stride(3)
+    if (H > 1 and t.stride(2) != W * ld) or (D > 1 and t.stride(1) != H * W * ld) or \
+            (N > 1 and t.stride(0) != D * H * W * ld):
+        raise RuntimeError(f"{what}: voxel dimensions must be densely packed (strides {t.stride()})")
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: vfd_gan_b200 has no CPU path; tensor is on {t.device}")
+    return N, D, H, W, C, ld
+
+
+# ------------------------------------------------------------------------------------------------
+# raw ops (mutating "out" style; registered with torch.library)
+# ------------------------------------------------------------------------------------------------
+def _conv3d_fwd(x, w_packed, bias, out, kd, kh, kw, kc, out_cols, direct):
+    N, D, H, W, C, ld = _check_cl(x, "conv3d_fwd input")
+    rows, taps, cin_k = w_packed.shape
+    out_fp32 = 1 if out.dtype == torch.float32 else 0
+    args = [x.data_ptr(), ld, C, w_packed.data_ptr(), rows, cin_k, _ptr(bias), out.data_ptr(),
+            out.stride(3), out_cols, out_fp32, N, D, H, W, kd, kh, kw]
+    if direct:
+        _lib.call("vfd_conv3d_fwd_direct", *args, _stream())
+    else:
+        _lib.call("vfd_conv3d_fwd", *args, kc, _stream())
+
+
+def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct):
+    N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
+    _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
+    taps, ci_pad, co_pad = acc.shape
+    _lib.call("vfd_conv3d_wgrad_direct" if direct else "vfd_conv3d_wgrad", dy.data_ptr(), dy_ld, cout,
+              x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad, ci_pad, N, D, H, W, kd, kh, kw, _stream())
+
+
+def _pack_ncdhw(src, dst, C, replicate):
+    N, Csrc = src.shape[0], src.shape[1]
+    S = src[0, 0].numel() if N > 0 else 0
+    _lib.call("vfd_pack_ncdhw", src.data_ptr(), dst.data_ptr(), N, Csrc, S, C, dst.stride(3), dst.shape[-1],
+              1 if replicate else 0, _stream())
+
+
+def _unpack_ncdhw(src, dst):
+    N, C = dst.shape[0], dst.shape[1]
+    S = dst[0, 0].numel() if N > 0 else 0
+    _lib.call("vfd_unpack_ncdhw", src.data_ptr(), 1 if src.dtype == torch.float32 else 0, dst.data_ptr(), N, C,
+              S, src.stride(3), _stream())
+
+
+def _pack_weight(w, wp, mode):
+    cout, cin = w.shape[0], w.shape[1]
+    rows, taps, ck = wp.shape
+    _lib.call("vfd_pack_weight", w.data_ptr(), wp.data_ptr(), cout, cin, taps, rows, ck, mode, _stream())
+
+
+def _unpack_wgrad(acc, gw):
+    taps, ci_pad, co_pad = acc.shape
+    _lib.call("vfd_unpack_wgrad", acc.data_ptr(), gw.data_ptr(), gw.shape[0], gw.shape[1], taps, co_pad, ci_pad,
+              _stream())
+
+
+def _bn_prepare(y, sums, cvalid, gamma, beta, running_mean, running_var, momentum, eps, train, mean, invstd,
+                scale, shift):
+    N, D, H, W, C, ld = _check_cl(y, "bn input")
+    V = N * D * H * W
+    if train:
+        _lib.call("vfd_bn_stats", y.data_ptr(), ld, C, V, sums.data_ptr(), _stream())
+    _lib.call("vfd_bn_finalize", sums.data_ptr(), C, cvalid, V, gamma.data_ptr(), beta.data_ptr(),
+              _ptr(running_mean), _ptr(running_var), momentum, eps, 1 if train else 0, mean.data_ptr(),
+              invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
+
+
+def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, seed):
+    N, D, H, W, C, ld = _check_cl(y, "bn_act_fwd input")
+    _lib.call("vfd_bn_act_fwd", y.data_ptr(), ld, N, D, H, W, C, scale.data_ptr(), shift.data_ptr(), slope,
+              _ptr(out_full), 0 if out_full is None else out_full.stride(3), _ptr(out_pool),
+              0 if out_pool is None else out_pool.stride(3), pd, ph, pw, drop_p, seed, _stream())
+
+
+def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd, ph, pw, drop_p, seed, train,
+                sums, c1, c2, dgamma, dbeta, dy):
+    N, D, H, W, C, ld = _check_cl(y, "bn_act_bwd input")
+    _lib.call("vfd_bn_act_bwd", y.data_ptr(), ld, N, D, H, W, C, cvalid, mean.data_ptr(), invstd.data_ptr(),
+              scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else g_full.stride(3),
+              _ptr(g_pool), 0 if g_pool is None else g_pool.stride(3), pd, ph, pw, drop_p, seed,
+              1 if train else 0, sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
+              dbeta.data_ptr(), dy.data_ptr(), dy.stride(3), _stream())
+
+
+def _channel_sum(x, out):
+    N, D, H, W, C, ld = _check_cl(x, "channel_sum input")
+    _lib.call("vfd_channel_sum", x.data_ptr(), ld, C, N * D * H * W, out.data_ptr(), _stream())
+
+
+def _upsample2x_fwd(x, out):
+    N, D, H, W, C, ld = _check_cl(x, "upsample2x_fwd input")
+    _lib.call("vfd_upsample2x_fwd", x.data_ptr(), ld, N, D, H, W, C, out.data_ptr(), out.stride(3), _stream())
+
+
+def _upsample2x_bwd(gout, gx):
+    N, D, H, W, C, ld = _check_cl(gx, "upsample2x_bwd output")
+    _lib.call("vfd_upsample2x_bwd", gout.data_ptr(), gout.stride(3), N, D, H, W, C, gx.data_ptr(), ld, _stream())
+
+
+def _sigmoid_head_fwd(logits, predict):
+    _lib.call("vfd_sigmoid_head_fwd", logits.data_ptr(), logits.stride(3), predict.numel(), predict.data_ptr(),
+              _stream())
+
+
+def _sigmoid_head_bwd(gpred, predict, dlogit):
+    _lib.call("vfd_sigmoid_head_bwd", gpred.data_ptr(), predict.data_ptr(), predict.numel(), dlogit.data_ptr(),
+              _stream())
+
+
+def _weighted_bce(predict, target, pos_weight, grad_scale, loss_sum, gpred):
+    _lib.call("vfd_weighted_bce", predict.data_ptr(), target.data_ptr(), predict.numel(), pos_weight, grad_scale,
+              loss_sum.data_ptr(), _ptr(gpred), _stream())
+
+
+def _sqdiff(a, b, out):
+    N, D, H, W, C, ld = _check_cl(a, "sqdiff a")
+    _check_cl(b, "sqdiff b")
+    _lib.call("vfd_sqdiff", a.data_ptr(), ld, b.data_ptr(), b.stride(3), C, N * D * H * W, out.data_ptr(),
+              _stream())
+
+
+def _convlstm_cell_fwd(gates, c_cur, h_next, c_next, act):
+    hid = c_cur.shape[-1]
+    _lib.call("vfd_convlstm_cell_fwd", gates.data_ptr(), gates.stride(3), c_cur.data_ptr(), hid,
+              c_cur.numel() // hid, h_next.data_ptr(), c_next.data_ptr(), _ptr(act), _stream())
+
+
+def _convlstm_cell_bwd(act, c_cur, c_next, dh, dc_in, dgates, dc_cur):
+    hid = c_cur.shape[-1]
+    _lib.call("vfd_convlstm_cell_bwd", act.data_ptr(), c_cur.data_ptr(), c_next.data_ptr(), _ptr(dh), _ptr(dc_in),
+              hid, c_cur.numel() // hid, dgates.data_ptr(), dgates.stride(3), dc_cur.data_ptr(), _stream())
+
+
+conv3d_fwd = _define(
+    "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, int kd, int kh, int kw, int kc, "
+    "int out_cols, bool direct) -> ()", _conv3d_fwd)
+conv3d_wgrad = _define(
+    "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct) -> ()",
+    _conv3d_wgrad)
+pack_ncdhw = _define("pack_ncdhw(Tensor src, Tensor(a!) dst, int C, bool replicate) -> ()", _pack_ncdhw)
+unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack_ncdhw)
+pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
+unpack_wgrad = _define("unpack_wgrad(Tensor acc, Tensor(a!) gw) -> ()", _unpack_wgrad)
+bn_prepare = _define(
+    "bn_prepare(Tensor y, Tensor(a!) sums, int cvalid, Tensor gamma, Tensor beta, Tensor(b!)? running_mean, "
+    "Tensor(c!)? running_var, float momentum, float eps, bool train, Tensor(d!) mean, Tensor(e!) invstd, "
+    "Tensor(f!) scale, Tensor(g!) shift) -> ()", _bn_prepare)
+bn_act_fwd = _define(
+    "bn_act_fwd(Tensor y, Tensor scale, Tensor shift, float slope, Tensor(a!)? out_full, Tensor(b!)? out_pool, "
+    "int pd, int ph, int pw, float drop_p, int seed) -> ()", _bn_act_fwd)
+bn_act_bwd = _define(
+    "bn_act_bwd(Tensor y, int cvalid, Tensor mean, Tensor invstd, Tensor scale, Tensor shift, float slope, "
+    "Tensor? g_full, Tensor? g_pool, int pd, int ph, int pw, float drop_p, int seed, bool train, "
+    "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy) -> ()",
+    _bn_act_bwd)
+channel_sum = _define("channel_sum(Tensor x, Tensor(a!) out) -> ()", _channel_sum)
+upsample2x_fwd = _define("upsample2x_fwd(Tensor x, Tensor(a!) out) -> ()", _upsample2x_fwd)
+upsample2x_bwd = _define("upsample2x_bwd(Tensor gout, Tensor(a!) gx) -> ()", _upsample2x_bwd)
+sigmoid_head_fwd = _define("sigmoid_head_fwd(Tensor logits, Tensor(a!) predict) -> ()", _sigmoid_head_fwd)
+sigmoid_head_bwd = _define("sigmoid_head_bwd(Tensor gpred, Tensor predict, Tensor(a!) dlogit) -> ()",
+                           _sigmoid_head_bwd)
+weighted_bce_op = _define(
+    "weighted_bce(Tensor predict, Tensor target, float pos_weight, float grad_scale, Tensor(a!) loss_sum, "
+    "Tensor(b!)? gpred) -> ()", _weighted_bce)
+sqdiff = _define("sqdiff(Tensor a, Tensor b, Tensor(a!) out) -> ()", _sqdiff)
+convlstm_cell_fwd = _define(
+    "convlstm_cell_fwd(Tensor gates, Tensor c_cur, Tensor(a!) h_next, Tensor(b!) c_next, Tensor(c!)? act) -> ()",
+    _convlstm_cell_fwd)
+convlstm_cell_bwd = _define(
+    "convlstm_cell_bwd(Tensor act, Tensor c_cur, Tensor c_next, Tensor? dh, Tensor? dc_in, Tensor(a!) dgates, "
+    "Tensor(b!) dc_cur) -> ()", _convlstm_cell_bwd)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers shared by the autograd functions
+# ------------------------------------------------------------------------------------------------
+CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core one
+
+_scratch = {}
+
+
+def bn_scratch(device, C):
+    """Self-clearing double [2*C] accumulator shared by every BatchNorm of width C on `device`."""
+    key = (device, C)
+    if key not in _scratch:
+        _scratch[key] = torch.zeros(2 * C, dtype=torch.float64, device=device)
+    return _scratch[key]
+
+
+class PackedWeights:
+    """bf16 GEMM operands of one conv weight, rebuilt when the fp32 master changes (Adam step)."""
+
+    def __init__(self):
+        self.version = None
+        self.key = None
+        self.fwd = None
+        self.dgrad = None
+
+    def get(self, weight):
+        cout, cin = weight.shape[0], weight.shape[1]
+        taps = weight[0, 0].numel()
+        key = (weight.data_ptr(), weight._version, weight.device)
+        if self.key != key:
+            cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
+            kc_f, kc_d = pick_kc(cin_p), pick_kc(cout_p)
+            w = weight.detach()
+            self.fwd = torch.empty(round_up(cout, 16), taps, round_up(cin_p, kc_f), dtype=torch.bfloat16,
+                                   device=weight.device)
+            self.dgrad = torch.empty(round_up(cin, 16), taps, round_up(cout_p, kc_d), dtype=torch.bfloat16,
+                                     device=weight.device)
+            pack_weight(w, self.fwd, 0)
+            pack_weight(w, self.dgrad, 1)
+            self.kc_f, self.kc_d = kc_f, kc_d
+            self.key = key
+        return self
+
+
+def _packed(weight):
+    pw = getattr(weight, "_vfd_packed", None)
+    if pw is None:
+        pw = PackedWeights()
+        weight._vfd_packed = pw
+    return pw.get(weight)
+
+
+def cl_empty(N, D, H, W, C, device, dtype=torch.bfloat16):
+    return torch.empty(N, D, H, W, C, dtype=dtype, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+class PackFn(torch.autograd.Function):
+    """fp32 NCDHW -> channels-last bf16 (C padded to 8). `replicate_to` > 0 repeats a 1-channel
+    source that many times (gray2rgb, lib/utils.py:91-92). Backward unpacks the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, replicate_to):
+        x = x.contiguous().float()
+        N, Csrc = x.shape[0], x.shape[1]
+        if replicate_to and Csrc != 1:
+            raise RuntimeError("replicate_to needs a single-channel source")
+        C = replicate_to if replicate_to else Csrc
+        out = cl_empty(N, *x.shape[2:], round_up(C, 8), x.device)
+        pack_ncdhw(x, out, C, bool(replicate_to))
+        ctx.src_shape = x.shape
+        ctx.channels = C
+        ctx.replicate = bool(replicate_to)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        N = ctx.src_shape[0]
+        gx = torch.empty(N, ctx.channels, *ctx.src_shape[2:], dtype=torch.float32, device=g.device)
+        unpack_ncdhw(g, gx)
+        if ctx.replicate:
+            gx = gx.sum(1, keepdim=True)
+        return gx, None
+
+
+class UnpackFn(torch.autograd.Function):
+    """channels-last (bf16 / fp32) -> fp32 NCDHW with `channels` valid channels."""
+
+    @staticmethod
+    def forward(ctx, x, channels):
+        N, D, H, W, Cp = x.shape
+        out = torch.empty(N, channels, D, H, W, dtype=torch.float32, device=x.device)
+        unpack_ncdhw(x, out)
+        ctx.cp = Cp
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        N, C, D, H, W = g.shape
+        gx = cl_empty(N, D, H, W, ctx.cp, g.device)
+        pack_ncdhw(g, gx, C, False)
+        return gx, None
+
+
+class ConvFn(torch.autograd.Function):
+    """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
+    training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_fp32, bias_grad_exact_zero):
+        N, D, H, W, Cin_p, _ = _check_cl(x, "conv input")
+        cout, cin, kd, kh, kw = weight.shape
+        if round_up(cin, 8) != Cin_p:
+            raise RuntimeError(f"conv input has {Cin_p} padded channels, weight expects {cin}")
+        pk = _packed(weight)
+        cout_p = round_up(cout, 8)
+        out = cl_empty(N, D, H, W, cout_p, x.device, torch.float32 if out_fp32 else torch.bfloat16)
+        b = None
+        if bias is not None:
+            b = torch.zeros(pk.fwd.shape[0], dtype=torch.float32, device=x.device)
+            b[:cout] = bias.detach()
+        conv3d_fwd(x, pk.fwd, b, out, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.bias_zero = bias_grad_exact_zero
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        cout, cin, kd, kh, kw = weight.shape
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        N, D, H, W, _, _ = _check_cl(g, "conv grad")
+        gx = gw = gb = None
+        pk = _packed(weight)
+        if ctx.needs_input_grad[0]:
+            gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
+            conv3d_fwd(g, pk.dgrad, None, gx, kd, kh, kw, pk.kc_d, x.shape[-1], CONV_IMPL_DIRECT)
+        if ctx.needs_input_grad[1]:
+            taps = kd * kh * kw
+            acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+            conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT)
+            gw = torch.empty_like(weight, dtype=torch.float32)
+            unpack_wgrad(acc, gw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if ctx.bias_zero:
+                gb = torch.zeros(cout, dtype=torch.float32, device=g.device)
+            else:
+                s = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
+                channel_sum(g, s)
+                gb = s[:cout].clone()
+        return gx, gw, gb, None, None
+
+
+class BnActFn(torch.autograd.Function):
+    """BatchNorm3d (batch statistics in training) + (Leaky)ReLU [+ Dropout] [+ AvgPool3d].
+
+    Returns (full, pooled); either is None when not requested. `full_out` may be a channel slice
+    of a concat buffer, in which case the activation is written straight into it."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, train, momentum, eps, slope, pool, drop_p, seed,
+                want_full, want_pool, full_out_holder):
+        N, D, H, W, C, _ = _check_cl(y, "bn input")
+        cvalid = gamma.numel()
+        dev = y.device
+        stats = torch.empty(4, C, dtype=torch.float32, device=dev)
+        mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        bn_prepare(y, bn_scratch(dev, C), cvalid, gamma.detach(), beta.detach(), running_mean, running_var,
+                   momentum, eps, train, mean, invstd, scale, shift)
+        pd, ph, pw = pool
+        full = pooled = None
+        if want_full:
+            full = full_out_holder[0].detach() if full_out_holder is not None else cl_empty(N, D, H, W, C, dev)
+        if want_pool:
+            pooled = cl_empty(N, D // pd, H // ph, W // pw, C, dev)
+        bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed)
+        ctx.save_for_backward(y, stats)
+        ctx.cfg = (cvalid, slope, pool, drop_p, seed, train)
+        return full, pooled
+
+    @staticmethod
+    def backward(ctx, g_full, g_pool):
+        y, stats = ctx.saved_tensors
+        cvalid, slope, (pd, ph, pw), drop_p, seed, train = ctx.cfg
+        N, D, H, W, C, _ = _check_cl(y, "bn saved input")
+        dev = y.device
+
+        def _prep(g):
+            if g is None:
+                return None
+            if g.dtype != torch.bfloat16:
+                g = g.to(torch.bfloat16)
+            if g.stride(-1) != 1:
+                g = g.contiguous()
+            return g
+
+        g_full, g_pool = _prep(g_full), _prep(g_pool)
+        dy = cl_empty(N, D, H, W, C, dev)
+        tmp = torch.empty(2, C, dtype=torch.float32, device=dev)
+        dgamma = torch.empty(cvalid, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(cvalid, dtype=torch.float32, device=dev)
+        bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw, drop_p,
+                   seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy)
+        return (dy, dgamma, dbeta) + (None,) * 12
+
+
+class UpCatFn(torch.autograd.Function):
+    """x2 trilinear upsample of `low` written into channels [0, C_low) of `buf`; `skip` already
+    lives in channels [C_low, C_low + C_skip) of the same buffer (zero-copy torch.cat)."""
+
+    @staticmethod
+    def forward(ctx, low, skip, buf_holder):
+        buf = buf_holder[0]
+        c_low = low.shape[-1]
+        upsample2x_fwd(low, buf[..., :c_low])
+        ctx.c_low = c_low
+        ctx.low_shape = low.shape
+        return buf.detach().view(buf.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        c_low = ctx.c_low
+        g_low = torch.empty(ctx.low_shape, dtype=torch.bfloat16, device=g.device)
+        upsample2x_bwd(g[..., :c_low], g_low)
+        return g_low, g[..., c_low:], None
+
+
+class SigmoidHeadFn(torch.autograd.Function):
+    """predict = sigmoid(conv_last logits) as fp32 [N,1,D,H,W] (NCDHW == channels-last for C = 1)."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        N, D, H, W, _ = logits.shape
+        predict = torch.empty(N, 1, D, H, W, dtype=torch.float32, device=logits.device)
+        sigmoid_head_fwd(logits, predict)
+        ctx.save_for_backward(predict)
+        return predict
+
+    @staticmethod
+    def backward(ctx, g):
+        (predict,) = ctx.saved_tensors
+        N, _, D, H, W = predict.shape
+        dlogit = cl_empty(N, D, H, W, 8, predict.device)
+        sigmoid_head_bwd(g.contiguous().float(), predict, dlogit)
+        return dlogit
+
+
+class WeightedBceFn(torch.autograd.Function):
+    """weighted_bce (lib/utils.py:65-71) with the gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, predict, target, pos_weight):
+        p = predict.contiguous().float()
+        t = target.contiguous().float()
+        V = p.numel()
+        loss_sum = torch.zeros((), dtype=torch.float64, device=p.device)
+        gpred = torch.empty_like(p) if predict.requires_grad else None
+        weighted_bce_op(p, t, float(pos_weight), 1.0 / V, loss_sum, gpred)
+        ctx.save_for_backward(gpred)
+        return (-(loss_sum / V)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (gpred,) = ctx.saved_tensors
+        return gpred * g, None, None
+
+
+def mse_cl(a, b, valid_channels):
+    """l2_loss (lib/utils.py:59-63) of two channels-last bf16 feature maps (no gradient)."""
+    out = torch.zeros((), dtype=torch.float64, device=a.device)
+    sqdiff(a, b, out)
+    N, D, H, W, _ = a.shape
+    return (out / (N * D * H * W * valid_channels)).float()

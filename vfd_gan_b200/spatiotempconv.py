@@ -1,0 +1,75 @@
+"""R(2+1)D factored convolution block on the B200 kernels.
+
+Drop-in for the reference's ``models/spatiotempconv.py:7-65``: same constructor arguments, same
+children (``spatial_conv``, ``bn``, ``relu``, ``temporal_conv`` -- real ``nn.Conv3d`` /
+``nn.BatchNorm3d`` parameter holders so ``weights_init`` and ``state_dict`` behave identically),
+same forward contract (fp32 NCDHW in, fp32 NCDHW out). The arithmetic runs in the tcgen05
+implicit-GEMM conv and the fused BatchNorm+ReLU kernels (``ops.ConvFn`` / ``ops.BnActFn``).
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _triple
+
+from . import ops
+
+
+def intermed_channels(in_channels, out_channels, kernel_size):
+    """Parameter-matching bottleneck width M of R(2+1)D (models/spatiotempconv.py:44-45)."""
+    kt, kh, kw = kernel_size
+    return int(math.floor((kt * kh * kw * in_channels * out_channels) /
+                          (kh * kw * in_channels + kt * out_channels)))
+
+
+def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None):
+    """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16."""
+    train = bn.training or bn.running_mean is None
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm3d(momentum=None) (cumulative average) is not supported")
+    if not bn.affine:
+        raise NotImplementedError("BatchNorm3d(affine=False) is not supported")
+    full, pooled = ops.BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, train,
+                                     float(bn.momentum), float(bn.eps), float(slope), tuple(pool), float(drop_p),
+                                     int(seed), want_full, want_pool, None if full_out is None else [full_out])
+    if train and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return full, pooled
+
+
+class SpatioTemporalConv(nn.Module):
+    """``Conv3d(1 x kh x kw)`` -> ``BatchNorm3d`` -> ``ReLU`` -> ``Conv3d(kt x 1 x 1)``.
+
+    Only what the vfd_gan hot path uses is implemented in CUDA: stride 1, kernel extents 1 or 3 and
+    "same" padding (``padding == kernel // 2`` per axis); anything else raises NotImplementedError.
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        k, s, p = _triple(kernel_size), _triple(stride), _triple(padding)
+        mid = intermed_channels(in_channels, out_channels, k)
+        self.spatial_conv = nn.Conv3d(in_channels, mid, (1, k[1], k[2]), stride=(1, s[1], s[2]),
+                                      padding=(0, p[1], p[2]), bias=bias)
+        self.bn = nn.BatchNorm3d(mid)
+        self.relu = nn.ReLU()
+        self.temporal_conv = nn.Conv3d(mid, out_channels, (k[0], 1, 1), stride=(s[0], 1, 1),
+                                       padding=(p[0], 0, 0), bias=bias)
+        self.out_channels = out_channels
+        if any(v != 1 for v in s) or any(kk not in (1, 3) for kk in k) or any(pp != kk // 2 for pp, kk in zip(p, k)):
+            self._unsupported = f"kernel={k} stride={s} padding={p}"
+        else:
+            self._unsupported = None
+
+    def forward_cl(self, xc, out_fp32=False, feeds_bn=False):
+        """channels-last bf16 in -> channels-last out (bf16, or fp32 when ``out_fp32``)."""
+        if self._unsupported:
+            raise NotImplementedError("SpatioTemporalConv on B200 supports stride 1 / kernel 1|3 / same padding "
+                                      "only, got " + self._unsupported)
+        bn_train = self.bn.training or self.bn.running_mean is None
+        y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, self.spatial_conv.bias, False, bn_train)
+        a1, _ = bn_apply(self.bn, y1, 0.0)
+        return ops.ConvFn.apply(a1, self.temporal_conv.weight, self.temporal_conv.bias, out_fp32, feeds_bn)
+
+    def forward(self, x):
+        xc = ops.PackFn.apply(x, 0)
+        return ops.UnpackFn.apply(self.forward_cl(xc, out_fp32=True), self.out_channels)
