@@ -1,0 +1,272 @@
+"""CPU oracle for the vfd_gan ``mygan`` hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file restates, as plain functions over a ``state_dict``, what the reference computes with its
+``nn.Module`` classes. It is the checker for the CUDA path: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
+it; nothing under ``vfd_gan_b200/`` does, and the product path fails loudly without its CUDA
+extension instead of falling back to this.
+
+Where the arithmetic lives: the reference has no arithmetic of its own -- every op is a PyTorch
+library call (pinned torch==1.3.1, Pipfile:14; the semantics relied on here are unchanged up to the
+torch 2.11 in this image: cross-correlation Conv3d with zero padding, BatchNorm3d eps 1e-5 /
+momentum 0.1 / biased batch variance / unbiased running variance, trilinear Upsample with
+align_corners, BCELoss log clamp at -100, Adam without amsgrad). The oracle therefore calls the same
+``torch.nn.functional`` primitives on CPU fp32; each function cites the reference lines it follows.
+
+Pinning: the reference ships no tests or golden vectors. The oracle is
+pinned instead against outputs of the reference's own modules executed in the build container
+(``tests/test_oracle_vs_reference.py`` when /root/reference is present) and against the fixtures
+under ``tests/golden/`` generated from those modules by ``tests/golden/make_golden.py``.
+
+``round_bf16=True`` makes the oracle "operand matched": it rounds to bfloat16 at exactly the points
+where the CUDA path stores bf16 (conv operands and stored activations), so the remaining
+difference is fp32 accumulation order -- this is the oracle the per-layer 1e-3 gates use.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _r(t, on):
+    """round-trip through bfloat16 when operand matching is on"""
+    return t.bfloat16().float() if on else t
+
+
+def intermed_channels(cin, cout, k):
+    """models/spatiotempconv.py:44-45"""
+    kt, kh, kw = k
+    return int(math.floor((kt * kh * kw * cin * cout) / (kh * kw * cin + kt * cout)))
+
+
+def batch_norm(sd, prefix, x, train, round_bf16=False):
+    """nn.BatchNorm3d forward incl. running-stat side effects (models/spatiotempconv.py:51,63;
+    models/mygannet.py:19,25,109,114). ``sd`` buffers are updated in place when ``train``."""
+    rm, rv = sd.get(prefix + ".running_mean"), sd.get(prefix + ".running_var")
+    out = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training=train or rm is None,
+                       momentum=0.1, eps=1e-5)
+    if train and prefix + ".num_batches_tracked" in sd:
+        sd[prefix + ".num_batches_tracked"] += 1
+    return out
+
+
+def st_conv(sd, prefix, x, kernel, train=True, round_bf16=False):
+    """SpatioTemporalConv.forward: temporal_conv(relu(bn(spatial_conv(x))))
+    (models/spatiotempconv.py:62-65); stride 1, padding kernel//2 as every hot-path use has."""
+    kt, kh, kw = kernel
+    rb = round_bf16
+    y = F.conv3d(_r(x, rb), _r(sd[prefix + ".spatial_conv.weight"], rb), sd.get(prefix + ".spatial_conv.bias"),
+                 padding=(0, kh // 2, kw // 2))
+    y = _r(y, rb)
+    a = _r(F.relu(batch_norm(sd, prefix + ".bn", y, train)), rb)
+    return F.conv3d(a, _r(sd[prefix + ".temporal_conv.weight"], rb), sd.get(prefix + ".temporal_conv.bias"),
+                    padding=(kt // 2, 0, 0))
+
+
+def net_conv(sd, prefix, x, kernel, slope, train=True, round_bf16=False):
+    """NetgConv / NetdConv forward: SpatioTemporalConv -> BatchNorm3d -> LeakyReLU(slope)
+    (models/mygannet.py:22-28, 112-116)."""
+    y = _r(st_conv(sd, prefix + ".conv", x, kernel, train, round_bf16), round_bf16)
+    return _r(F.leaky_relu(batch_norm(sd, prefix + ".bn", y, train), slope), round_bf16)
+
+
+# ------------------------------------------------------------------------------------------------
+# networks
+# ------------------------------------------------------------------------------------------------
+def netg_forward(sd, x, train=True, dropout_masks=None, dropout_p=0.25, round_bf16=False, return_latent=False):
+    """NetG.forward (models/mygannet.py:55-101). ``dropout_masks``: optional list of four
+    multiplier tensors (already scaled by 1/(1-p)) applied after uconv5..uconv2, replacing
+    nn.Dropout so a test can share masks with the CUDA path; otherwise F.dropout draws from the
+    torch RNG in the reference's order."""
+    rb = round_bf16
+    k = (3, 3, 3)
+    skips = []
+    h = x
+    for i in range(1, 5):
+        d = net_conv(sd, f"dconv{i}", h, k, 0.2, train, rb)
+        skips.append(d)
+        h = _r(F.avg_pool3d(d, 2), rb)
+    latent = net_conv(sd, "dconv5", h, k, 0.2, train, rb)
+
+    def drop(t, i):
+        if dropout_masks is not None:
+            return _r(t * dropout_masks[i], rb)
+        return F.dropout(t, dropout_p, training=train)
+
+    h = drop(net_conv(sd, "uconv5", latent, k, 0.2, train, rb), 0)
+    for n, i in enumerate((4, 3, 2, 1)):
+        h = _r(F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True), rb)
+        h = torch.cat([h, skips[i - 1]], dim=1)
+        h = net_conv(sd, f"uconv{i}", h, k, 0.2, train, rb)
+        if i > 1:
+            h = drop(h, n + 1)
+    logits = F.conv3d(h, _r(sd["conv_last.weight"], rb), None, padding=1)
+    predict = torch.sigmoid(logits)
+    return (predict, latent) if return_latent else predict
+
+
+def sdisc_forward(sd, prefix, x, train=True, round_bf16=False):
+    """SDisc.forward (models/mygannet.py:138-162)"""
+    rb = round_bf16
+    h = x
+    for i in range(1, 7):
+        h = net_conv(sd, f"{prefix}dconv{i}", h, (1, 3, 3), 0.01, train, rb)
+        h = _r(F.avg_pool3d(h, (1, 2, 2)), rb)
+    feat = h
+    g = F.avg_pool3d(feat, (feat.shape[2], 1, 1), stride=1)
+    cls = torch.sigmoid(F.linear(g.reshape(g.shape[0], -1), sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]))
+    return cls.squeeze(1), feat
+
+
+def tdisc_forward(sd, prefix, x, train=True, round_bf16=False):
+    """TDisc.forward (models/mygannet.py:180-196)"""
+    rb = round_bf16
+    h = x
+    for i in range(1, 4):
+        h = net_conv(sd, f"{prefix}dconv{i}", h, (3, 1, 1), 0.01, train, rb)
+        h = _r(F.avg_pool3d(h, (2, 1, 1)), rb)
+    feat = h
+    g = F.avg_pool3d(feat, (1, feat.shape[3], feat.shape[4]), stride=1)
+    cls = torch.sigmoid(F.linear(g.reshape(g.shape[0], -1), sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]))
+    return cls.squeeze(1), feat
+
+
+def netd_forward(sd, x, y, train=True, round_bf16=False):
+    """NetD.forward (models/mygannet.py:208-213)"""
+    s_cls, s_feat = sdisc_forward(sd, "spatdisc.", x, train, round_bf16)
+    t_cls, t_feat = tdisc_forward(sd, "tempdisc.", y, train, round_bf16)
+    return s_cls, s_feat, t_cls, t_feat
+
+
+def convlstm_cell(sd, prefix, x, h_cur, c_cur, round_bf16=False):
+    """ConvLSTMCell.forward (models/convlstm.py:42-58): gates split in the order i, f, o, g."""
+    w = sd[prefix + "conv.weight"]
+    hid = w.shape[0] // 4
+    comb = torch.cat([x, h_cur], dim=1)
+    cc = F.conv2d(_r(comb, round_bf16), _r(w, round_bf16), sd.get(prefix + "conv.bias"),
+                  padding=(w.shape[2] // 2, w.shape[3] // 2))
+    cc_i, cc_f, cc_o, cc_g = torch.split(cc, hid, dim=1)
+    i, f, o, g = torch.sigmoid(cc_i), torch.sigmoid(cc_f), torch.sigmoid(cc_o), torch.tanh(cc_g)
+    c_next = f * c_cur + i * g
+    return o * torch.tanh(c_next), c_next
+
+
+def convlstm_unroll(sd, prefix, x_btchw, round_bf16=False):
+    """ConvLSTM.forward for one layer, batch_first, zero initial state (models/convlstm.py:101-151)."""
+    w = sd[prefix + "conv.weight"]
+    hid = w.shape[0] // 4
+    B, T, _, H, W = x_btchw.shape
+    h = torch.zeros(B, hid, H, W)
+    c = torch.zeros(B, hid, H, W)
+    outs = []
+    for t in range(T):
+        h, c = convlstm_cell(sd, prefix, x_btchw[:, t], h, c, round_bf16)
+        outs.append(h)
+    return torch.stack(outs, dim=1), (h, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def l2_loss(a, b):
+    """lib/utils.py:59-63"""
+    return torch.mean(torch.pow(a - b, 2))
+
+
+def weighted_bce(p, t, pos_weight=2):
+    """lib/utils.py:65-71 (pos_weight multiplies the (1 - target) term; the clamp's upper bound
+    1 - 1e-8 is 1.0 in fp32, as in the reference)."""
+    p = torch.clamp(p, min=1e-8, max=1 - 1e-8)
+    loss = t * torch.log(p) + pos_weight * (1 - t) * torch.log(1 - p)
+    return torch.neg(torch.mean(loss))
+
+
+def gray2rgb(v):
+    """lib/utils.py:91-92"""
+    return torch.cat([v, v, v], dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# the train step
+# ------------------------------------------------------------------------------------------------
+class OracleTrainer:
+    """MyGAN.optimize_params restated on CPU (models/mygannet.py:275-366).
+
+    Holds fp32 copies of both state_dicts; parameters become autograd leaves, buffers are updated
+    in place. Optical flow is an input (the reference computes it on the host with cv2 Farneback,
+    lib/utils.py:94-129 -- outside the hot path). Adam follows
+    ``optim.Adam(lr, betas=(beta1, 0.999))`` (models/mygannet.py:270-273) via torch.optim.Adam on
+    the leaves. Dead work is not skipped: ``err_g`` includes the adversarial term and is
+    back-propagated with ``retain_graph`` exactly like the reference (its D gradients are wiped by
+    ``optimizer_d.zero_grad()``)."""
+
+    def __init__(self, sd_g, sd_d, lr=2e-5, beta1=0.5, w_adv=1, w_con=10, round_bf16=False):
+        def split(sd):
+            params, bufs = {}, {}
+            for k, v in sd.items():
+                v = v.detach().clone().cpu()
+                if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                    bufs[k] = v
+                else:
+                    params[k] = v.float().requires_grad_(True)
+            return params, bufs
+
+        self.pg, self.bg = split(sd_g)
+        self.pd, self.bd = split(sd_d)
+        self.opt_g = torch.optim.Adam(list(self.pg.values()), lr=lr, betas=(beta1, 0.999))
+        self.opt_d = torch.optim.Adam(list(self.pd.values()), lr=lr, betas=(beta1, 0.999))
+        self.w_adv, self.w_con = w_adv, w_con
+        self.rb = round_bf16
+        self.bce = torch.nn.BCELoss()
+
+    def sd_g(self):
+        return {**self.pg, **self.bg}
+
+    def sd_d(self):
+        return {**self.pd, **self.bd}
+
+    def step(self, inp, gt, gt_flow, pre_flow, dropout_masks=None):
+        sd_g, sd_d = self.sd_g(), self.sd_d()
+        # forward_g (:275-276)
+        predict = netg_forward(sd_g, inp, True, dropout_masks, round_bf16=self.rb)
+        # forward_d (:278-286): every D input is detached
+        pre_3ch, gt_3ch = gray2rgb(predict.detach()), gray2rgb(gt)
+        s_pr, s_fr, t_pr, t_fr = netd_forward(sd_d, gt_3ch, gt_flow, True, self.rb)
+        s_pf, s_ff, t_pf, t_ff = netd_forward(sd_d, pre_3ch, pre_flow, True, self.rb)
+        # backward_g (:305-320)
+        self.opt_g.zero_grad()
+        err_g_adv_s, err_g_adv_t = l2_loss(s_fr, s_ff), l2_loss(t_fr, t_ff)
+        err_g_adv = err_g_adv_s + err_g_adv_t
+        err_g_con = weighted_bce(predict, gt)
+        err_g = err_g_adv * self.w_adv + err_g_con * self.w_con
+        err_g.backward(retain_graph=True)
+        self.opt_g.step()
+        # backward_d (:323-344)
+        self.opt_d.zero_grad()
+        ones, zeros = torch.ones_like(s_pr), torch.zeros_like(s_pf)
+        e_rs, e_rt = self.bce(s_pr, ones), self.bce(t_pr, ones)
+        e_fs, e_ft = self.bce(s_pf, zeros), self.bce(t_pf, zeros)
+        err_d_real, err_d_fake = (e_rs + e_rt) * 0.5, (e_fs + e_ft) * 0.5
+        err_d = (err_d_real + err_d_fake) * 0.5
+        err_d.backward()
+        self.opt_d.step()
+        return {
+            "g/err_g": err_g.item(), "g/err_g_adv": err_g_adv.item(), "g/err_g_adv_s": err_g_adv_s.item(),
+            "g/err_g_adv_t": err_g_adv_t.item(), "g/err_g_con": err_g_con.item(),
+            "d/err_d_real_s": e_rs.item(), "d/err_d_real_t": e_rt.item(), "d/err_d_fake_s": e_fs.item(),
+            "d/err_d_fake_t": e_ft.item(), "d/err_d_real": err_d_real.item(), "d/err_d_fake": err_d_fake.item(),
+            "d/err_d": err_d.item(),
+        }, predict.detach()
+
+
+def synthetic_batch(batch, nfr, isize, seed=0):
+    """Synthetic inputs of SURVEY.md section 8d: clips in [-1,1], sparse binary mask, random flows."""
+    g = torch.Generator().manual_seed(seed)
+    inp = torch.rand(batch, 3, nfr, isize, isize, generator=g) * 2 - 1
+    gt = (torch.rand(batch, 1, nfr, isize, isize, generator=g) > 0.9).float()
+    gt_flow = torch.rand(batch, 3, nfr, isize, isize, generator=g) * 2 - 1
+    pre_flow = torch.rand(batch, 3, nfr, isize, isize, generator=g) * 2 - 1
+    return inp, gt, gt_flow, pre_flow

@@ -11,6 +11,7 @@ int set_error(int code, const char* msg) {
   return code;
 }
 int set_cuda_error(cudaError_t e, const char* where) {
+  (void)cudaGetLastError();  // clear the (non-sticky) error so later launches are judged on their own
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
   return VFD_ERR_CUDA;
 }

@@ -521,7 +521,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel<KC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_tc)");
     attr_set = true;
   }
@@ -610,7 +610,7 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_tc)");
     attr_set = true;
   }
