@@ -1,0 +1,17 @@
+"""vfd_gan_b200 -- B200-native (sm_100a) implementation of the vfd_gan ``mygan`` training hot path.
+
+Public surface mirrors the reference's modules (models/spatiotempconv.py, models/mygannet.py,
+models/convlstm.py, lib/utils.py losses) so it drops into trainer.py / lib/train_gan.py unchanged;
+see INTEGRATION.md. Compute happens only in libvfd_b200.so (include/vfd_b200.h) -- there is no CPU
+or eager-PyTorch fallback for the kernels.
+"""
+from . import _lib, ops  # noqa: F401
+from .spatiotempconv import SpatioTemporalConv  # noqa: F401
+from .mygannet import NetgConv, NetG, NetdConv, SDisc, TDisc, NetD  # noqa: F401
+from .convlstm import ConvLSTMCell, ConvLSTM  # noqa: F401
+from .losses import weights_init, l2_loss, weighted_bce, gray2rgb  # noqa: F401
+from .step import GanTrainStep, HostBatchStep, GradAllReducer, LOSS_KEYS  # noqa: F401
+
+__all__ = ["SpatioTemporalConv", "NetgConv", "NetG", "NetdConv", "SDisc", "TDisc", "NetD", "ConvLSTMCell",
+           "ConvLSTM", "weights_init", "l2_loss", "weighted_bce", "gray2rgb", "GanTrainStep", "HostBatchStep",
+           "GradAllReducer", "LOSS_KEYS"]

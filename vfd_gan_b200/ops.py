@@ -337,6 +337,13 @@ class UnpackFn(torch.autograd.Function):
         return gx, None
 
 
+def _wshape(weight):
+    """(cout, cin, kd, kh, kw) of an nn.Conv3d weight, or of an nn.Conv2d weight seen as kd = 1."""
+    if weight.dim() == 4:
+        return weight.shape[0], weight.shape[1], 1, weight.shape[2], weight.shape[3]
+    return tuple(weight.shape)
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
     training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
@@ -344,7 +351,7 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, out_fp32, bias_grad_exact_zero):
         N, D, H, W, Cin_p, _ = _check_cl(x, "conv input")
-        cout, cin, kd, kh, kw = weight.shape
+        cout, cin, kd, kh, kw = _wshape(weight)
         if round_up(cin, 8) != Cin_p:
             raise RuntimeError(f"conv input has {Cin_p} padded channels, weight expects {cin}")
         pk = _packed(weight)
@@ -363,7 +370,7 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        cout, cin, kd, kh, kw = weight.shape
+        cout, cin, kd, kh, kw = _wshape(weight)
         if g.dtype != torch.bfloat16:
             g = g.to(torch.bfloat16)
         if g.stride(-1) != 1:

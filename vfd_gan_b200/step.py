@@ -1,0 +1,214 @@
+"""The GAN training step (``MyGAN.optimize_params``, models/mygannet.py:275-366) on the B200 kernels.
+
+``GanTrainStep.step`` performs exactly the parameter updates of the reference step:
+
+    predict = netg(input)                                     forward_g   :275-276
+    netd(gray2rgb(gt), gt_flow), netd(gray2rgb(predict.detach()), pre_flow)   forward_d :278-286
+    err_g = w_adv * (l2(s_feat) + l2(t_feat)) + w_con * weighted_bce(predict, gt)
+    optimizer_g.zero_grad(); err_g.backward(); optimizer_g.step()             :359-361
+    err_d = ((bce(s_r,1)+bce(t_r,1))/2 + (bce(s_f,0)+bce(t_f,0))/2)/2
+    optimizer_d.zero_grad(); err_d.backward(); optimizer_d.step()             :364-366
+
+with two deliberate differences that do not change any result:
+  * every discriminator input is detached in the reference, so the adversarial term has no path
+    to NetG and its backward through NetD only deposits gradients that ``optimizer_d.zero_grad()``
+    wipes; the term is evaluated for logging (fused squared-difference reduction) but not
+    back-propagated;
+  * the 12 logged scalars are written into one device tensor and read back once, instead of 12
+    ``.item()`` synchronisations.
+
+Optical flow (``video_to_flow``, host cv2 Farneback, lib/utils.py:94-129) is an *input* here, as in
+SURVEY.md section 8d.
+
+Data parallelism (one process per GPU): ``GradAllReducer`` averages gradients over ranks with NCCL
+in buckets, launched from post-accumulate-grad hooks on a side stream so the collectives overlap
+the rest of backward. BatchNorm statistics stay per rank (DataParallel semantics).
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+
+LOSS_KEYS = ("g/err_g", "g/err_g_adv", "g/err_g_adv_s", "g/err_g_adv_t", "g/err_g_con",
+             "d/err_d_real_s", "d/err_d_real_t", "d/err_d_fake_s", "d/err_d_fake_t",
+             "d/err_d_real", "d/err_d_fake", "d/err_d")
+
+
+class GradAllReducer:
+    """Bucketed, backward-overlapped gradient averaging over the default process group.
+
+    Gradients live as views into flat fp32 bucket buffers. A bucket is all-reduced (SUM, then scaled
+    by 1/world) on ``comm_stream`` as soon as the last of its parameters has accumulated its
+    gradient; ``finish()`` makes the compute stream wait for the collectives."""
+
+    def __init__(self, params, bucket_mb=16.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        cur, cur_n = [], 0
+        for p in reversed(self.params):  # backward produces gradients roughly in reverse order
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n >= cap:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self.pending, self.bucket_of = [], [], {}
+        for bi, bucket in enumerate(self.buckets):
+            n = sum(p.numel() for p in bucket)
+            flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
+            off = 0
+            for p in bucket:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self.bucket_of[p] = bi
+            self.flat.append(flat)
+            self.pending.append(0)
+        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and torch.cuda.is_available()) else None
+        self.handles = []
+        self.active = False
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero(self):
+        for f in self.flat:
+            f.zero_()
+
+    def begin(self):
+        """Arm the hooks for one backward pass."""
+        self.pending = [len(b) for b in self.buckets]
+        self.handles = []
+        self.active = True
+
+    def _hook(self, p):
+        if not self.active:
+            return
+        bi = self.bucket_of[p]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        flat = self.flat[bi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.mul_(1.0 / self.world)
+        else:  # CPU / gloo (tests)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(1.0 / self.world)
+
+    def finish(self):
+        """Reduce whatever the hooks did not cover (unused parameters) and join the side stream."""
+        if self.world > 1:
+            for bi, left in enumerate(self.pending):
+                if left > 0:
+                    self._launch(bi)
+                    self.pending[bi] = 0
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.active = False
+
+
+class GanTrainStep:
+    """One ``optimize_params``-equivalent step; see the module docstring."""
+
+    def __init__(self, netg, netd, lr=2e-5, beta1=0.5, w_adv=1, w_con=10, pos_weight=2, distributed=None,
+                 bucket_mb=16.0):
+        self.netg, self.netd = netg, netd
+        self.w_adv, self.w_con, self.pos_weight = w_adv, w_con, pos_weight
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.red_g = GradAllReducer(list(netg.parameters()), bucket_mb)
+        self.red_d = GradAllReducer(list(netd.parameters()), bucket_mb)
+        dev = next(netg.parameters()).device
+        fused = dev.type == "cuda"
+        # Same hyper-parameters as models/mygannet.py:270-273
+        self.optimizer_g = torch.optim.Adam(netg.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused)
+        self.optimizer_d = torch.optim.Adam(netd.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused)
+        self.losses = torch.zeros(len(LOSS_KEYS), dtype=torch.float32, device=dev)
+        self.predict = None
+
+    def step(self, inp, gt, gt_flow, pre_flow, dropout_seeds=None):
+        """inp (B,3,D,H,W) in [-1,1]; gt (B,1,D,H,W) in {0,1}; flows (B,3,D,H,W). Returns the device
+        tensor of the 12 logged scalars in LOSS_KEYS order (no host synchronisation)."""
+        netg, netd = self.netg, self.netd
+        netg.train()
+        netd.train()
+
+        # forward_g
+        logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds)
+        predict = ops.SigmoidHeadFn.apply(logits)
+        self.predict = predict.detach()
+
+        # forward_d: gray2rgb folded into the layout pack (1 -> 3 replicated channels)
+        gt_cl = ops.PackFn.apply(gt, 3)
+        pre_cl = ops.PackFn.apply(self.predict, 3)
+        s_pr, s_fr, t_pr, t_fr = netd.forward_cl(gt_cl, ops.PackFn.apply(gt_flow, 0))
+        s_pf, s_ff, t_pf, t_ff = netd.forward_cl(pre_cl, ops.PackFn.apply(pre_flow, 0))
+
+        # backward_g
+        with torch.no_grad():
+            adv_s = ops.mse_cl(s_fr, s_ff, netd.spatdisc.feat_channels)
+            adv_t = ops.mse_cl(t_fr, t_ff, netd.tempdisc.feat_channels)
+        err_g_con = ops.WeightedBceFn.apply(predict, gt, float(self.pos_weight))
+        self.red_g.zero()
+        self.red_g.begin()
+        (err_g_con * self.w_con).backward()
+        self.red_g.finish()
+        self.optimizer_g.step()
+
+        # backward_d
+        ones, zeros = torch.ones_like(s_pr), torch.zeros_like(s_pf)
+        e_rs, e_rt = F.binary_cross_entropy(s_pr, ones), F.binary_cross_entropy(t_pr, ones)
+        e_fs, e_ft = F.binary_cross_entropy(s_pf, zeros), F.binary_cross_entropy(t_pf, zeros)
+        err_d_real, err_d_fake = (e_rs + e_rt) * 0.5, (e_fs + e_ft) * 0.5
+        err_d = (err_d_real + err_d_fake) * 0.5
+        self.red_d.zero()
+        self.red_d.begin()
+        err_d.backward()
+        self.red_d.finish()
+        self.optimizer_d.step()
+
+        with torch.no_grad():
+            adv = adv_s + adv_t
+            con = err_g_con.detach()
+            torch.stack([adv * self.w_adv + con * self.w_con, adv, adv_s, adv_t, con,
+                         e_rs.detach(), e_rt.detach(), e_fs.detach(), e_ft.detach(),
+                         err_d_real.detach(), err_d_fake.detach(), err_d.detach()], out=self.losses)
+        return self.losses
+
+    def losses_dict(self):
+        """One device->host read of the 12 scalars (keys as logged at models/mygannet.py:314-342)."""
+        vals = self.losses.tolist()
+        return dict(zip(LOSS_KEYS, vals))
+
+
+class HostBatchStep:
+    """End-to-end entry: pinned host buffers in, loss scalars out.
+
+    Every call copies the step's inputs host->device (async, from pinned memory), runs
+    ``GanTrainStep.step`` and reads the 12 loss scalars back -- the same boundary as
+    ``lib/train_gan.py:69-70`` (``d.to('cuda')`` then ``optimize_params()``)."""
+
+    def __init__(self, trainer, batch, nfr, isize, device):
+        self.trainer = trainer
+        shp3, shp1 = (batch, 3, nfr, isize, isize), (batch, 1, nfr, isize, isize)
+        self.dev = [torch.empty(shp3, device=device), torch.empty(shp1, device=device),
+                    torch.empty(shp3, device=device), torch.empty(shp3, device=device)]
+        self.host_losses = torch.empty(len(LOSS_KEYS), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.dev)
+        self.d2h_bytes = self.host_losses.numel() * 4
+
+    def __call__(self, host_inp, host_gt, host_gt_flow, host_pre_flow):
+        for d, h in zip(self.dev, (host_inp, host_gt, host_gt_flow, host_pre_flow)):
+            d.copy_(h, non_blocking=True)
+        losses = self.trainer.step(*self.dev)
+        self.host_losses.copy_(losses, non_blocking=True)
+        return self.host_losses
