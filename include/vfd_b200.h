@@ -87,9 +87,11 @@ VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int
  * zero on entry; vfd_bn_finalize clears it again). */
 VFD_API int vfd_bn_stats(const void* x, long long ld, int C, long long V, double* sums, void* stream);
 /* sums -> mean / invstd / scale (= gamma*invstd) / shift (= beta - mean*scale), fp32 [C] each, and
- * the running-stat update (momentum, unbiased variance). train = 0 uses the running statistics. */
-VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* gamma,
-                            const float* beta, float* running_mean, float* running_var, float momentum,
+ * the running-stat update (momentum, unbiased variance). train = 0 uses the running statistics.
+ * pre_bias (fp32 [Cvalid] or NULL) is the producing conv's bias when it was deliberately not added
+ * to the stored tensor: it cancels in the normalisation and only enters running_mean / shift. */
+VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* pre_bias,
+                            const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
                             float eps, int train, float* mean, float* invstd, float* scale,
                             float* shift, void* stream);
 /* out = dropout(act(y*scale + shift)), act(z) = z > 0 ? z : slope*z. out_full (full resolution)

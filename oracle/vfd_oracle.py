@@ -42,35 +42,56 @@ def intermed_channels(cin, cout, k):
     return int(math.floor((kt * kh * kw * cin * cout) / (kh * kw * cin + kt * cout)))
 
 
-def batch_norm(sd, prefix, x, train, round_bf16=False):
+def batch_norm(sd, prefix, x, train, pre_bias=None):
     """nn.BatchNorm3d forward incl. running-stat side effects (models/spatiotempconv.py:51,63;
-    models/mygannet.py:19,25,109,114). ``sd`` buffers are updated in place when ``train``."""
+    models/mygannet.py:19,25,109,114). ``sd`` buffers are updated in place when ``train``.
+    ``pre_bias`` (operand-matched mode only): a conv bias that was left out of ``x``; a per-channel
+    constant cancels in training-mode normalisation and only shifts ``running_mean``."""
     rm, rv = sd.get(prefix + ".running_mean"), sd.get(prefix + ".running_var")
-    out = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training=train or rm is None,
-                       momentum=0.1, eps=1e-5)
+    if train and pre_bias is not None and rm is not None:
+        tmp = rm.clone()  # autograd keeps the tensor handed to batch_norm; update a copy of it
+        out = F.batch_norm(x, tmp, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training=True, momentum=0.1,
+                           eps=1e-5)
+        rm.copy_(tmp + 0.1 * pre_bias.detach())
+    else:
+        out = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training=train or rm is None,
+                           momentum=0.1, eps=1e-5)
     if train and prefix + ".num_batches_tracked" in sd:
         sd[prefix + ".num_batches_tracked"] += 1
     return out
 
 
-def st_conv(sd, prefix, x, kernel, train=True, round_bf16=False):
-    """SpatioTemporalConv.forward: temporal_conv(relu(bn(spatial_conv(x))))
-    (models/spatiotempconv.py:62-65); stride 1, padding kernel//2 as every hot-path use has."""
-    kt, kh, kw = kernel
-    rb = round_bf16
-    y = F.conv3d(_r(x, rb), _r(sd[prefix + ".spatial_conv.weight"], rb), sd.get(prefix + ".spatial_conv.bias"),
-                 padding=(0, kh // 2, kw // 2))
-    y = _r(y, rb)
-    a = _r(F.relu(batch_norm(sd, prefix + ".bn", y, train)), rb)
-    return F.conv3d(a, _r(sd[prefix + ".temporal_conv.weight"], rb), sd.get(prefix + ".temporal_conv.bias"),
-                    padding=(kt // 2, 0, 0))
+def _conv_bn(sd, conv_prefix, bn_prefix, x, padding, train, rb):
+    """conv -> BatchNorm. Operand-matched mode mirrors the CUDA path's storage points: the bias is
+    kept out of the bf16-stored conv output when a training-mode BatchNorm follows."""
+    w, b = sd[conv_prefix + ".weight"], sd.get(conv_prefix + ".bias")
+    if rb and train:
+        y = _r(F.conv3d(_r(x, rb), _r(w, rb), None, padding=padding), rb)
+        return batch_norm(sd, bn_prefix, y, train, pre_bias=b)
+    y = _r(F.conv3d(_r(x, rb), _r(w, rb), b, padding=padding), rb)
+    return batch_norm(sd, bn_prefix, y, train)
 
 
 def net_conv(sd, prefix, x, kernel, slope, train=True, round_bf16=False):
     """NetgConv / NetdConv forward: SpatioTemporalConv -> BatchNorm3d -> LeakyReLU(slope)
-    (models/mygannet.py:22-28, 112-116)."""
-    y = _r(st_conv(sd, prefix + ".conv", x, kernel, train, round_bf16), round_bf16)
-    return _r(F.leaky_relu(batch_norm(sd, prefix + ".bn", y, train), slope), round_bf16)
+    (models/mygannet.py:22-28, 112-116), with SpatioTemporalConv.forward =
+    temporal_conv(relu(bn(spatial_conv(x)))) (models/spatiotempconv.py:62-65); stride 1 and
+    padding kernel//2 as every hot-path use has."""
+    kt, kh, kw = kernel
+    rb = round_bf16
+    c = prefix + ".conv"
+    a = _r(F.relu(_conv_bn(sd, c + ".spatial_conv", c + ".bn", x, (0, kh // 2, kw // 2), train, rb)), rb)
+    z = _conv_bn(sd, c + ".temporal_conv", prefix + ".bn", a, (kt // 2, 0, 0), train, rb)
+    return _r(F.leaky_relu(z, slope), rb)
+
+
+def st_conv(sd, prefix, x, kernel, train=True, round_bf16=False):
+    """Stand-alone SpatioTemporalConv.forward (models/spatiotempconv.py:62-65)."""
+    kt, kh, kw = kernel
+    rb = round_bf16
+    a = _r(F.relu(_conv_bn(sd, prefix + ".spatial_conv", prefix + ".bn", x, (0, kh // 2, kw // 2), train, rb)), rb)
+    return F.conv3d(a, _r(sd[prefix + ".temporal_conv.weight"], rb), sd.get(prefix + ".temporal_conv.bias"),
+                    padding=(kt // 2, 0, 0))
 
 
 # ------------------------------------------------------------------------------------------------

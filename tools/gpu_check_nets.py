@@ -48,27 +48,44 @@ def check_netg(B=2, D=16, S=32, ngf=32):
               (B, 2 * g, D // 2, S // 2, S // 2)]
     masks = dropout_masks(net, seeds, shapes, 0.25, dev)
     print("dropout keep fractions", [round(float((m > 0).float().mean()), 4) for m in masks])
-    ok = True
+    res = {}
     for rb in (True, False):
         sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
         po = O.netg_forward(sdo, x, True, masks, round_bf16=rb)
         lo = O.weighted_bce(po, gt)
         lo.backward()
-        e_p = rel(pred, po)
-        print(f"[netg oracle round_bf16={rb}] predict rel {e_p:.3e}  loss cuda {loss.item():.6f} oracle {lo.item():.6f}")
-        worst = 0.0
-        for k, p_ in net.named_parameters():
-            if sdo[k].grad is None or k.endswith("conv.bias") or ".bias" in k and "bn" not in k:
-                continue
-            e = rel(p_.grad, sdo[k].grad)
-            worst = max(worst, e)
-            if e > 2e-2:
-                print(f"   grad {k}: rel {e:.3e}")
-        print(f"   worst param-grad rel {worst:.3e}")
-        e_rm = max(rel(net.state_dict()[k], sdo[k]) for k in sd if "running" in k)
-        print(f"   worst running-stat rel {e_rm:.3e}")
-        if rb:
-            ok &= e_p < 5e-3 and worst < 5e-2
+        res[rb] = (po.detach(), lo.item(), sdo)
+    print(f"[netg] predict rel: cuda-fp32 {rel(pred, res[False][0]):.2e} cuda-matched {rel(pred, res[True][0]):.2e} "
+          f"matched-fp32 {rel(res[True][0], res[False][0]):.2e}; loss cuda {loss.item():.6f} fp32 {res[False][1]:.6f}")
+    ok = rel(pred, res[True][0]) < 5e-3
+    ok &= report_grads(net, res)
+    e_rm = max(rel(net.state_dict()[k], res[False][2][k]) for k in sd if "running" in k)
+    print(f"   worst running-stat rel vs fp32 oracle {e_rm:.3e}")
+    return ok and e_rm < 2e-2
+
+
+def report_grads(net, res, verbose_over=None):
+    """Parameter gradients: the CUDA path must sit inside the bf16 noise envelope, i.e. its distance to
+    the fp32 oracle may not exceed twice the distance of the operand-matched oracle to the fp32 one."""
+    ok = True
+    worst = (0.0, None)
+    for k, p_ in net.named_parameters():
+        gf, gm = res[False][2][k].grad, res[True][2][k].grad
+        if gf is None or (k.endswith(".bias") and ".bn." not in k and "linear" not in k):
+            continue  # conv biases in front of a BatchNorm: gradient is identically zero (noise in torch)
+        e_cf, e_cm, e_mf = rel(p_.grad, gf), rel(p_.grad, gm), rel(gm, gf)
+        good = e_cf <= max(2.0 * e_mf, 2e-2)
+        ok &= good
+        if not good or e_cf > worst[0]:
+            worst = max(worst, (e_cf, k))
+        if not good:
+            print(f"   grad {k}: cuda-fp32 {e_cf:.2e} cuda-matched {e_cm:.2e} matched-fp32 {e_mf:.2e}  FAIL")
+    names = [k for k, _ in net.named_parameters() if k.endswith("weight") and "bn" not in k]
+    for k in (names[0], names[len(names) // 2], names[-1]):
+        p_ = dict(net.named_parameters())[k]
+        print(f"   grad {k}: cuda-fp32 {rel(p_.grad, res[False][2][k].grad):.2e} cuda-matched "
+              f"{rel(p_.grad, res[True][2][k].grad):.2e} matched-fp32 {rel(res[True][2][k].grad, res[False][2][k].grad):.2e}")
+    print(f"   worst cuda-fp32 param-grad rel {worst[0]:.3e} ({worst[1]}) -> {'ok' if ok else 'FAIL'}")
     return ok
 
 
@@ -86,26 +103,21 @@ def check_netd(B=2, D=16, S=64):
     loss = (torch.nn.functional.binary_cross_entropy(s_cls, torch.ones_like(s_cls)) +
             torch.nn.functional.binary_cross_entropy(t_cls, torch.ones_like(t_cls)))
     loss.backward()
-    ok = True
+    res = {}
     for rb in (True, False):
         sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
-        so, sfo, to, tfo = O.netd_forward(sdo, x, y, True, rb)
-        lo = (torch.nn.functional.binary_cross_entropy(so, torch.ones_like(so)) +
-              torch.nn.functional.binary_cross_entropy(to, torch.ones_like(to)))
+        outs = O.netd_forward(sdo, x, y, True, rb)
+        lo = (torch.nn.functional.binary_cross_entropy(outs[0], torch.ones_like(outs[0])) +
+              torch.nn.functional.binary_cross_entropy(outs[2], torch.ones_like(outs[2])))
         lo.backward()
-        print(f"[netd oracle round_bf16={rb}] s_cls {rel(s_cls, so):.3e} t_cls {rel(t_cls, to):.3e} "
-              f"s_feat {rel(s_feat, sfo):.3e} t_feat {rel(t_feat, tfo):.3e}")
-        worst = 0.0
-        for k, p_ in net.named_parameters():
-            if sdo[k].grad is None or (k.endswith(".bias") and "bn" not in k and "linear" not in k):
-                continue
-            e = rel(p_.grad, sdo[k].grad)
-            worst = max(worst, e)
-            if e > 5e-2:
-                print(f"   grad {k}: rel {e:.3e}")
-        print(f"   worst param-grad rel {worst:.3e}")
-        if rb:
-            ok &= rel(s_feat, sfo) < 1e-2 and rel(t_feat, tfo) < 1e-2 and worst < 1e-1
+        res[rb] = ([o.detach() for o in outs], lo.item(), sdo)
+    ok = True
+    for name, got, i in (("s_cls", s_cls, 0), ("s_feat", s_feat, 1), ("t_cls", t_cls, 2), ("t_feat", t_feat, 3)):
+        e_cf, e_cm, e_mf = rel(got, res[False][0][i]), rel(got, res[True][0][i]), rel(res[True][0][i], res[False][0][i])
+        good = e_cf <= max(2.0 * e_mf, 5e-3)
+        ok &= good
+        print(f"[netd] {name}: cuda-fp32 {e_cf:.2e} cuda-matched {e_cm:.2e} matched-fp32 {e_mf:.2e} {'ok' if good else 'FAIL'}")
+    ok &= report_grads(net, res)
     return ok
 
 
@@ -164,7 +176,7 @@ def check_lstm():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["netg", "netd", "lstm", "step"]
+    which = sys.argv[1:] or ["netd", "lstm", "step", "netg"]
     ok = True
     for w in which:
         t0 = time.time()

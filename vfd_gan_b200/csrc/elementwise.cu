@@ -182,7 +182,11 @@ bn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
 // sums -> (mean, invstd, scale, shift), running-stat update, and clears the accumulator.
 // Matches nn.BatchNorm3d: biased variance for normalisation, unbiased for running_var,
 // momentum 0.1, eps 1e-5. In eval mode (train == 0) the running statistics are used instead.
+// pre_bias (optional): bias of the producing conv that was NOT added to the stored tensor -- a
+// per-channel constant cancels in the normalisation, so it only enters the running mean (train)
+// or the shift (eval). Keeping it out of the bf16 tensor keeps the stored values centred.
 __global__ void bn_finalize_kernel(double* __restrict__ sums, int C, int Cvalid, long long V,
+                                   const float* __restrict__ pre_bias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float momentum, float eps, int train, float* __restrict__ mean_out,
@@ -192,6 +196,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int C, int Cvalid,
   if (c >= C) return;
   float mean = 0.f, invstd = 0.f, sc = 0.f, sh = 0.f;
   if (c < Cvalid) {
+    const float pb = pre_bias != nullptr ? pre_bias[c] : 0.f;
     if (train) {
       const double m = sums[c] / (double)V;
       double var = sums[C + c] / (double)V - m * m;
@@ -200,11 +205,11 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int C, int Cvalid,
       invstd = (float)(1.0 / sqrt(var + (double)eps));
       if (running_mean != nullptr) {
         const double unbiased = V > 1 ? var * (double)V / (double)(V - 1) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + pb);
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
       }
     } else {
-      mean = running_mean[c];
+      mean = running_mean[c] - pb;
       invstd = rsqrtf(running_var[c] + eps);
     }
     sc = gamma[c] * invstd;
@@ -807,13 +812,13 @@ VFD_API int vfd_bn_stats(const void* x, long long ld, int C, long long V, double
   return check_launch("bn_stats");
 }
 
-VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* gamma,
-                               const float* beta, float* running_mean, float* running_var,
+VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const float* pre_bias,
+                               const float* gamma, const float* beta, float* running_mean, float* running_var,
                                float momentum, float eps, int train, float* mean, float* invstd,
                                float* scale, float* shift, void* stream_) {
   if (!train && (running_mean == nullptr || running_var == nullptr))
     return set_error(VFD_ERR_ARG, "bn_finalize: eval mode needs running statistics");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, pre_bias, gamma, beta, running_mean,
                                                           running_var, momentum, eps, train, mean,
                                                           invstd, scale, shift);
   return check_launch("bn_finalize");

@@ -34,8 +34,10 @@ class NetgConv(nn.Module):
         self.out_fi = out_fi
 
     def forward_cl(self, xc, **kw):
-        y = self.conv.forward_cl(xc, feeds_bn=self.bn.training or self.bn.running_mean is None)
-        return bn_apply(self.bn, y, self.lrelu.negative_slope, **kw)
+        if self.bn.training or self.bn.running_mean is None:
+            y, tb = self.conv.forward_cl(xc, fold_bias=True)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, **kw)
+        return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):
         full, _ = self.forward_cl(ops.PackFn.apply(x, 0))
@@ -126,8 +128,10 @@ class NetdConv(nn.Module):
         self.out_fi = out_fi
 
     def forward_cl(self, xc, **kw):
-        y = self.conv.forward_cl(xc, feeds_bn=self.bn.training or self.bn.running_mean is None)
-        return bn_apply(self.bn, y, self.lrelu.negative_slope, **kw)
+        if self.bn.training or self.bn.running_mean is None:
+            y, tb = self.conv.forward_cl(xc, fold_bias=True)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, **kw)
+        return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):
         full, _ = self.forward_cl(ops.PackFn.apply(x, 0))

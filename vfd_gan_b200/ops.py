@@ -48,18 +48,45 @@ def pick_kc(cin_p):
     return 16
 
 
-def _check_cl(t, what):
-    if t.dtype != torch.bfloat16 or t.dim() != 5 or t.stride(-1) != 1 or t.shape[-1] % 8:
-        raise RuntimeError(f"{what}: expected a channels-last bf16 [N,D,H,W,C] tensor with C % 8 == 0, "
-                           f"got {tuple(t.shape)} {t.dtype} strides {t.stride()}")
+def _ld(t):
+    """Voxel pitch (elements) of a channels-last tensor; singleton voxel dims carry no stride info."""
+    if t.is_contiguous():
+        return t.shape[-1]
     N, D, H, W, C = t.shape
-    ld = t.stride(3)
-    if (H > 1 and t.stride(2) != W * ld) or (D > 1 and t.stride(1) != H * W * ld) or \
-            (N > 1 and t.stride(0) != D * H * W * ld):
-        raise RuntimeError(f"{what}: voxel dimensions must be densely packed (strides {t.stride()})")
+    for dim, inner in ((3, 1), (2, W), (1, H * W), (0, D * H * W)):
+        if t.shape[dim] > 1:
+            return t.stride(dim) // inner
+    return C
+
+
+def _is_cl(t):
+    if t.dim() != 5 or t.shape[-1] % 8 or (t.numel() and t.stride(-1) != 1):
+        return False
+    N, D, H, W, C = t.shape
+    ld = _ld(t)
+    if ld < C or ld % 8 or t.data_ptr() % 16:
+        return False
+    return not ((W > 1 and t.stride(3) != ld) or (H > 1 and t.stride(2) != W * ld) or
+                (D > 1 and t.stride(1) != H * W * ld) or (N > 1 and t.stride(0) != D * H * W * ld))
+
+
+def _check_cl(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: vfd_gan_b200 has no CPU path; tensor is on {t.device}")
-    return N, D, H, W, C, ld
+    if t.dtype != torch.bfloat16 or not _is_cl(t):
+        raise RuntimeError(f"{what}: expected a channels-last bf16 [N,D,H,W,C] tensor (C % 8 == 0, dense voxel "
+                           f"dims, 16-byte aligned), got {tuple(t.shape)} {t.dtype} strides {t.stride()}")
+    N, D, H, W, C = t.shape
+    return N, D, H, W, C, _ld(t)
+
+
+def as_cl_grad(g):
+    """Bring an incoming gradient to channels-last bf16 (autograd may hand us fp32 or expanded views)."""
+    if g is None:
+        return None
+    if g.dtype != torch.bfloat16:
+        g = g.to(torch.bfloat16)
+    return g if _is_cl(g) else g.contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -70,7 +97,7 @@ def _conv3d_fwd(x, w_packed, bias, out, kd, kh, kw, kc, out_cols, direct):
     rows, taps, cin_k = w_packed.shape
     out_fp32 = 1 if out.dtype == torch.float32 else 0
     args = [x.data_ptr(), ld, C, w_packed.data_ptr(), rows, cin_k, _ptr(bias), out.data_ptr(),
-            out.stride(3), out_cols, out_fp32, N, D, H, W, kd, kh, kw]
+            _ld(out), out_cols, out_fp32, N, D, H, W, kd, kh, kw]
     if direct:
         _lib.call("vfd_conv3d_fwd_direct", *args, _stream())
     else:
@@ -88,7 +115,7 @@ def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct):
 def _pack_ncdhw(src, dst, C, replicate):
     N, Csrc = src.shape[0], src.shape[1]
     S = src[0, 0].numel() if N > 0 else 0
-    _lib.call("vfd_pack_ncdhw", src.data_ptr(), dst.data_ptr(), N, Csrc, S, C, dst.stride(3), dst.shape[-1],
+    _lib.call("vfd_pack_ncdhw", src.data_ptr(), dst.data_ptr(), N, Csrc, S, C, _ld(dst), dst.shape[-1],
               1 if replicate else 0, _stream())
 
 
@@ -96,7 +123,7 @@ def _unpack_ncdhw(src, dst):
     N, C = dst.shape[0], dst.shape[1]
     S = dst[0, 0].numel() if N > 0 else 0
     _lib.call("vfd_unpack_ncdhw", src.data_ptr(), 1 if src.dtype == torch.float32 else 0, dst.data_ptr(), N, C,
-              S, src.stride(3), _stream())
+              S, _ld(src), _stream())
 
 
 def _pack_weight(w, wp, mode):
@@ -111,13 +138,13 @@ def _unpack_wgrad(acc, gw):
               _stream())
 
 
-def _bn_prepare(y, sums, cvalid, gamma, beta, running_mean, running_var, momentum, eps, train, mean, invstd,
-                scale, shift):
+def _bn_prepare(y, sums, cvalid, pre_bias, gamma, beta, running_mean, running_var, momentum, eps, train, mean,
+                invstd, scale, shift):
     N, D, H, W, C, ld = _check_cl(y, "bn input")
     V = N * D * H * W
     if train:
         _lib.call("vfd_bn_stats", y.data_ptr(), ld, C, V, sums.data_ptr(), _stream())
-    _lib.call("vfd_bn_finalize", sums.data_ptr(), C, cvalid, V, gamma.data_ptr(), beta.data_ptr(),
+    _lib.call("vfd_bn_finalize", sums.data_ptr(), C, cvalid, V, _ptr(pre_bias), gamma.data_ptr(), beta.data_ptr(),
               _ptr(running_mean), _ptr(running_var), momentum, eps, 1 if train else 0, mean.data_ptr(),
               invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
 
@@ -125,18 +152,18 @@ def _bn_prepare(y, sums, cvalid, gamma, beta, running_mean, running_var, momentu
 def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, seed):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_fwd input")
     _lib.call("vfd_bn_act_fwd", y.data_ptr(), ld, N, D, H, W, C, scale.data_ptr(), shift.data_ptr(), slope,
-              _ptr(out_full), 0 if out_full is None else out_full.stride(3), _ptr(out_pool),
-              0 if out_pool is None else out_pool.stride(3), pd, ph, pw, drop_p, seed, _stream())
+              _ptr(out_full), 0 if out_full is None else _ld(out_full), _ptr(out_pool),
+              0 if out_pool is None else _ld(out_pool), pd, ph, pw, drop_p, seed, _stream())
 
 
 def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd, ph, pw, drop_p, seed, train,
                 sums, c1, c2, dgamma, dbeta, dy):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_bwd input")
     _lib.call("vfd_bn_act_bwd", y.data_ptr(), ld, N, D, H, W, C, cvalid, mean.data_ptr(), invstd.data_ptr(),
-              scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else g_full.stride(3),
-              _ptr(g_pool), 0 if g_pool is None else g_pool.stride(3), pd, ph, pw, drop_p, seed,
+              scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
+              _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed,
               1 if train else 0, sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
-              dbeta.data_ptr(), dy.data_ptr(), dy.stride(3), _stream())
+              dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
 
 
 def _channel_sum(x, out):
@@ -146,16 +173,16 @@ def _channel_sum(x, out):
 
 def _upsample2x_fwd(x, out):
     N, D, H, W, C, ld = _check_cl(x, "upsample2x_fwd input")
-    _lib.call("vfd_upsample2x_fwd", x.data_ptr(), ld, N, D, H, W, C, out.data_ptr(), out.stride(3), _stream())
+    _lib.call("vfd_upsample2x_fwd", x.data_ptr(), ld, N, D, H, W, C, out.data_ptr(), _ld(out), _stream())
 
 
 def _upsample2x_bwd(gout, gx):
     N, D, H, W, C, ld = _check_cl(gx, "upsample2x_bwd output")
-    _lib.call("vfd_upsample2x_bwd", gout.data_ptr(), gout.stride(3), N, D, H, W, C, gx.data_ptr(), ld, _stream())
+    _lib.call("vfd_upsample2x_bwd", gout.data_ptr(), _ld(gout), N, D, H, W, C, gx.data_ptr(), ld, _stream())
 
 
 def _sigmoid_head_fwd(logits, predict):
-    _lib.call("vfd_sigmoid_head_fwd", logits.data_ptr(), logits.stride(3), predict.numel(), predict.data_ptr(),
+    _lib.call("vfd_sigmoid_head_fwd", logits.data_ptr(), _ld(logits), predict.numel(), predict.data_ptr(),
               _stream())
 
 
@@ -172,20 +199,20 @@ def _weighted_bce(predict, target, pos_weight, grad_scale, loss_sum, gpred):
 def _sqdiff(a, b, out):
     N, D, H, W, C, ld = _check_cl(a, "sqdiff a")
     _check_cl(b, "sqdiff b")
-    _lib.call("vfd_sqdiff", a.data_ptr(), ld, b.data_ptr(), b.stride(3), C, N * D * H * W, out.data_ptr(),
+    _lib.call("vfd_sqdiff", a.data_ptr(), ld, b.data_ptr(), _ld(b), C, N * D * H * W, out.data_ptr(),
               _stream())
 
 
 def _convlstm_cell_fwd(gates, c_cur, h_next, c_next, act):
     hid = c_cur.shape[-1]
-    _lib.call("vfd_convlstm_cell_fwd", gates.data_ptr(), gates.stride(3), c_cur.data_ptr(), hid,
+    _lib.call("vfd_convlstm_cell_fwd", gates.data_ptr(), _ld(gates), c_cur.data_ptr(), hid,
               c_cur.numel() // hid, h_next.data_ptr(), c_next.data_ptr(), _ptr(act), _stream())
 
 
 def _convlstm_cell_bwd(act, c_cur, c_next, dh, dc_in, dgates, dc_cur):
     hid = c_cur.shape[-1]
     _lib.call("vfd_convlstm_cell_bwd", act.data_ptr(), c_cur.data_ptr(), c_next.data_ptr(), _ptr(dh), _ptr(dc_in),
-              hid, c_cur.numel() // hid, dgates.data_ptr(), dgates.stride(3), dc_cur.data_ptr(), _stream())
+              hid, c_cur.numel() // hid, dgates.data_ptr(), _ld(dgates), dc_cur.data_ptr(), _stream())
 
 
 conv3d_fwd = _define(
@@ -199,7 +226,8 @@ unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack
 pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
 unpack_wgrad = _define("unpack_wgrad(Tensor acc, Tensor(a!) gw) -> ()", _unpack_wgrad)
 bn_prepare = _define(
-    "bn_prepare(Tensor y, Tensor(a!) sums, int cvalid, Tensor gamma, Tensor beta, Tensor(b!)? running_mean, "
+    "bn_prepare(Tensor y, Tensor(a!) sums, int cvalid, Tensor? pre_bias, Tensor gamma, Tensor beta, "
+    "Tensor(b!)? running_mean, "
     "Tensor(c!)? running_var, float momentum, float eps, bool train, Tensor(d!) mean, Tensor(e!) invstd, "
     "Tensor(f!) scale, Tensor(g!) shift) -> ()", _bn_prepare)
 bn_act_fwd = _define(
@@ -244,6 +272,20 @@ def bn_scratch(device, C):
     return _scratch[key]
 
 
+# Bumped after every optimizer step (fused optimizers update parameters without touching
+# Tensor._version, so the version counter alone cannot invalidate the packed copies).
+_weight_epoch = [0]
+
+
+def invalidate_packed_weights(*_args, **_kwargs):
+    _weight_epoch[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook  # noqa: E402
+
+_reg_post_hook(invalidate_packed_weights)
+
+
 class PackedWeights:
     """bf16 GEMM operands of one conv weight, rebuilt when the fp32 master changes (Adam step)."""
 
@@ -256,7 +298,7 @@ class PackedWeights:
     def get(self, weight):
         cout, cin = weight.shape[0], weight.shape[1]
         taps = weight[0, 0].numel()
-        key = (weight.data_ptr(), weight._version, weight.device)
+        key = (weight.data_ptr(), weight._version, weight.device, _weight_epoch[0])
         if self.key != key:
             cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
             kc_f, kc_d = pick_kc(cin_p), pick_kc(cout_p)
@@ -307,8 +349,7 @@ class PackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        if g.dtype != torch.bfloat16:
-            g = g.to(torch.bfloat16)
+        g = as_cl_grad(g)
         N = ctx.src_shape[0]
         gx = torch.empty(N, ctx.channels, *ctx.src_shape[2:], dtype=torch.float32, device=g.device)
         unpack_ncdhw(g, gx)
@@ -371,10 +412,7 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         cout, cin, kd, kh, kw = _wshape(weight)
-        if g.dtype != torch.bfloat16:
-            g = g.to(torch.bfloat16)
-        if g.stride(-1) != 1:
-            g = g.contiguous()
+        g = as_cl_grad(g)
         N, D, H, W, _, _ = _check_cl(g, "conv grad")
         gx = gw = gb = None
         pk = _packed(weight)
@@ -404,14 +442,15 @@ class BnActFn(torch.autograd.Function):
     of a concat buffer, in which case the activation is written straight into it."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, train, momentum, eps, slope, pool, drop_p, seed,
-                want_full, want_pool, full_out_holder):
+    def forward(ctx, y, gamma, beta, pre_bias, running_mean, running_var, train, momentum, eps, slope, pool, drop_p,
+                seed, want_full, want_pool, full_out_holder):
         N, D, H, W, C, _ = _check_cl(y, "bn input")
         cvalid = gamma.numel()
         dev = y.device
         stats = torch.empty(4, C, dtype=torch.float32, device=dev)
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        bn_prepare(y, bn_scratch(dev, C), cvalid, gamma.detach(), beta.detach(), running_mean, running_var,
+        bn_prepare(y, bn_scratch(dev, C), cvalid, None if pre_bias is None else pre_bias.detach(), gamma.detach(),
+                   beta.detach(), running_mean, running_var,
                    momentum, eps, train, mean, invstd, scale, shift)
         pd, ph, pw = pool
         full = pooled = None
@@ -422,6 +461,7 @@ class BnActFn(torch.autograd.Function):
         bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed)
         ctx.save_for_backward(y, stats)
         ctx.cfg = (cvalid, slope, pool, drop_p, seed, train)
+        ctx.has_pre_bias = pre_bias is not None
         return full, pooled
 
     @staticmethod
@@ -430,24 +470,16 @@ class BnActFn(torch.autograd.Function):
         cvalid, slope, (pd, ph, pw), drop_p, seed, train = ctx.cfg
         N, D, H, W, C, _ = _check_cl(y, "bn saved input")
         dev = y.device
-
-        def _prep(g):
-            if g is None:
-                return None
-            if g.dtype != torch.bfloat16:
-                g = g.to(torch.bfloat16)
-            if g.stride(-1) != 1:
-                g = g.contiguous()
-            return g
-
-        g_full, g_pool = _prep(g_full), _prep(g_pool)
+        g_full, g_pool = as_cl_grad(g_full), as_cl_grad(g_pool)
         dy = cl_empty(N, D, H, W, C, dev)
         tmp = torch.empty(2, C, dtype=torch.float32, device=dev)
         dgamma = torch.empty(cvalid, dtype=torch.float32, device=dev)
         dbeta = torch.empty(cvalid, dtype=torch.float32, device=dev)
         bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw, drop_p,
                    seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy)
-        return (dy, dgamma, dbeta) + (None,) * 12
+        # a conv bias folded into training-mode BN has an identically zero gradient
+        gpb = torch.zeros(cvalid, dtype=torch.float32, device=dev) if ctx.has_pre_bias else None
+        return (dy, dgamma, dbeta, gpb) + (None,) * 12
 
 
 class UpCatFn(torch.autograd.Function):
@@ -465,8 +497,7 @@ class UpCatFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        if g.dtype != torch.bfloat16:
-            g = g.to(torch.bfloat16)
+        g = as_cl_grad(g)
         c_low = ctx.c_low
         g_low = torch.empty(ctx.low_shape, dtype=torch.bfloat16, device=g.device)
         upsample2x_bwd(g[..., :c_low], g_low)

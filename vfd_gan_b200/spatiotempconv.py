@@ -22,14 +22,17 @@ def intermed_channels(in_channels, out_channels, kernel_size):
                           (kh * kw * in_channels + kt * out_channels)))
 
 
-def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None):
-    """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16."""
+def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None,
+             pre_bias=None):
+    """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16.
+    ``pre_bias``: bias of the conv that produced ``y`` when it was left out of ``y`` (see
+    ``SpatioTemporalConv.forward_cl``)."""
     train = bn.training or bn.running_mean is None
     if bn.momentum is None:
         raise NotImplementedError("BatchNorm3d(momentum=None) (cumulative average) is not supported")
     if not bn.affine:
         raise NotImplementedError("BatchNorm3d(affine=False) is not supported")
-    full, pooled = ops.BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, train,
+    full, pooled = ops.BnActFn.apply(y, bn.weight, bn.bias, pre_bias, bn.running_mean, bn.running_var, train,
                                      float(bn.momentum), float(bn.eps), float(slope), tuple(pool), float(drop_p),
                                      int(seed), want_full, want_pool, None if full_out is None else [full_out])
     if train and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -60,15 +63,29 @@ class SpatioTemporalConv(nn.Module):
         else:
             self._unsupported = None
 
-    def forward_cl(self, xc, out_fp32=False, feeds_bn=False):
-        """channels-last bf16 in -> channels-last out (bf16, or fp32 when ``out_fp32``)."""
+    def forward_cl(self, xc, out_fp32=False, fold_bias=False):
+        """channels-last bf16 in -> channels-last out (bf16, or fp32 when ``out_fp32``).
+
+        A conv bias that feeds a training-mode BatchNorm cancels in the normalisation, so it is not
+        added to the stored bf16 tensor (which keeps that tensor centred and its rounding error
+        small); it is handed to the BatchNorm kernel instead, where it only shifts ``running_mean``.
+        The inner ``spatial_conv -> bn`` pair always does this; with ``fold_bias`` the caller promises
+        the same for ``temporal_conv`` and receives ``(y, temporal_bias)``."""
         if self._unsupported:
             raise NotImplementedError("SpatioTemporalConv on B200 supports stride 1 / kernel 1|3 / same padding "
                                       "only, got " + self._unsupported)
         bn_train = self.bn.training or self.bn.running_mean is None
-        y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, self.spatial_conv.bias, False, bn_train)
-        a1, _ = bn_apply(self.bn, y1, 0.0)
-        return ops.ConvFn.apply(a1, self.temporal_conv.weight, self.temporal_conv.bias, out_fp32, feeds_bn)
+        sb = self.spatial_conv.bias
+        if bn_train and sb is not None:
+            y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, None, False, False)
+            a1, _ = bn_apply(self.bn, y1, 0.0, pre_bias=sb)
+        else:
+            y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, sb, False, False)
+            a1, _ = bn_apply(self.bn, y1, 0.0)
+        tb = self.temporal_conv.bias
+        if fold_bias:
+            return ops.ConvFn.apply(a1, self.temporal_conv.weight, None, out_fp32, False), tb
+        return ops.ConvFn.apply(a1, self.temporal_conv.weight, tb, out_fp32, False)
 
     def forward(self, x):
         xc = ops.PackFn.apply(x, 0)
