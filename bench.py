@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the vfd_gan ``mygan`` training step on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one ``optimize_params``-equivalent GAN training step (models/mygannet.py:350-366) on one
+batch of synthetic clips. Workload at every N: BASELINE.json configs[1] -- 16x3x112x112 clips,
+batch 32 PER GPU (weak scaling), bf16 tensor-core convs with fp32 accumulation / fp32 master weights.
+Prints ONE JSON line on rank 0.
+
+``--impl reference`` times the reference's own CPU implementation of the step (the oracle port in
+oracle/vfd_oracle.py, validated bit-exact against the reference modules; the reference itself is
+pure Python importing /root/reference, which does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NFR, ISIZE, BATCH_PER_GPU = 16, 112, 32
+WORKLOAD = f"GANomaly-3D (mygan NetG+NetD, R(2+1)D) train step, synthetic {NFR}x3x{ISIZE}x{ISIZE} clips, batch {BATCH_PER_GPU}/GPU"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class KernelProfiler:
+    """CUDA-event timing of individual kernel calls on the launching stream (ops.PROFILER hook)."""
+
+    def __init__(self):
+        self.records = []
+
+    def run(self, kind, work, thunk):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        thunk()
+        b.record()
+        self.records.append((kind, work, a, b))
+
+    def summary(self, steps):
+        out = {}
+        for kind, work, a, b in self.records:
+            d = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["work"] += work
+            d["launches"] += 1
+        for d in out.values():
+            d["ms_per_step"] = d["ms"] / steps
+            d["launches_per_step"] = d["launches"] / steps
+        return out
+
+
+def conv_macs_per_clip(net, shapes):
+    """Algorithmic conv MACs per clip (no channel / tile padding): sum over Conv3d of voxels*Cin*Cout*taps."""
+    total = 0
+    for name, vox in shapes:
+        conv = dict(net.named_modules())[name]
+        w = conv.weight
+        total += vox * w.shape[0] * w.shape[1] * w[0, 0].numel()
+    return total
+
+
+def model_conv_shapes(nfr, s):
+    g, sd, td = [], [], []
+    vox = lambda lvl: (nfr >> lvl) * (s >> lvl) * (s >> lvl)
+    for i in range(1, 6):
+        g += [(f"dconv{i}.conv.spatial_conv", vox(i - 1)), (f"dconv{i}.conv.temporal_conv", vox(i - 1))]
+    for i, lvl in ((5, 4), (4, 3), (3, 2), (2, 1), (1, 0)):
+        g += [(f"uconv{i}.conv.spatial_conv", vox(lvl)), (f"uconv{i}.conv.temporal_conv", vox(lvl))]
+    g.append(("conv_last", vox(0)))
+    hs = s
+    for i in range(1, 7):
+        sd += [(f"spatdisc.dconv{i}.conv.spatial_conv", nfr * hs * hs), (f"spatdisc.dconv{i}.conv.temporal_conv", nfr * hs * hs)]
+        hs //= 2
+    d = nfr
+    for i in range(1, 4):
+        td += [(f"tempdisc.dconv{i}.conv.spatial_conv", d * s * s), (f"tempdisc.dconv{i}.conv.temporal_conv", d * s * s)]
+        d //= 2
+    return g, sd + td
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of optimize_params on the host cores, bounded sample of the workload."""
+    from oracle import vfd_oracle as O
+    import vfd_gan_b200 as V
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_batch = 2
+    torch.manual_seed(0)
+    a = types.SimpleNamespace(nfr=NFR, isize=ISIZE)
+    netg, netd = V.NetG(), V.NetD(a)
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    tr = O.OracleTrainer(netg.state_dict(), netd.state_dict())
+    batch = O.synthetic_batch(sample_batch, NFR, ISIZE, seed=0)
+    for _ in range(args.warmup):
+        tr.step(*batch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(*batch)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample_batch / dt
+    sample = f"{args.steps} steps of batch {sample_batch} (of the {BATCH_PER_GPU}-clip workload), {NFR}x3x{ISIZE}x{ISIZE}, fp32, torch CPU"
+    line = {"impl": "reference", "metric": "train_clips_per_sec", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample timed next to the GPU number on rank 0 (N = 1 only)."""
+    from oracle import vfd_oracle as O
+    import vfd_gan_b200 as V
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    a = types.SimpleNamespace(nfr=NFR, isize=ISIZE)
+    netg, netd = V.NetG(), V.NetD(a)
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    tr = O.OracleTrainer(netg.state_dict(), netd.state_dict())
+    batch = O.synthetic_batch(2, NFR, ISIZE, seed=0)
+    tr.step(*batch)
+    t0 = time.perf_counter()
+    n = 2
+    for _ in range(n):
+        tr.step(*batch)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 2 / dt, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of batch 2 of the same {NFR}x3x{ISIZE}x{ISIZE} workload (oracle port, fp32, torch CPU)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: the headline config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch.distributed as dist
+    import vfd_gan_b200 as V
+    from vfd_gan_b200 import _lib, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: vfd_gan_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    torch.manual_seed(0)
+    a = types.SimpleNamespace(nfr=NFR, isize=ISIZE)
+    netg, netd = V.NetG(), V.NetD(a)
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    netg, netd = netg.to(dev), netd.to(dev)
+    trainer = V.GanTrainStep(netg, netd)
+    host = V.HostBatchStep(trainer, B, NFR, ISIZE, dev)
+
+    g = torch.Generator().manual_seed(1 + rank)
+    shp3, shp1 = (B, 3, NFR, ISIZE, ISIZE), (B, 1, NFR, ISIZE, ISIZE)
+    h_inp = (torch.rand(shp3, generator=g) * 2 - 1).pin_memory()
+    h_gt = (torch.rand(shp1, generator=g) > 0.9).float().pin_memory()
+    h_gf = (torch.rand(shp3, generator=g) * 2 - 1).pin_memory()
+    h_pf = (torch.rand(shp3, generator=g) * 2 - 1).pin_memory()
+    d_inp, d_gt, d_gf, d_pf = (t.to(dev) for t in (h_inp, h_gt, h_gf, h_pf))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident inputs ("value")
+    for _ in range(max(args.warmup, 3)):
+        trainer.step(d_inp, d_gt, d_gf, d_pf)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.KERNEL_LAUNCHES
+    ms = timed(lambda: trainer.step(d_inp, d_gt, d_gf, d_pf), args.steps)
+    launches = _lib.KERNEL_LAUNCHES - l0
+    losses = trainer.losses_dict()
+    # ---- host buffers in, losses out ("e2e")
+    for _ in range(2):
+        host(h_inp, h_gt, h_gf, h_pf)
+
+    def e2e_step():
+        host(h_inp, h_gt, h_gf, h_pf)
+        torch.cuda.current_stream().synchronize()  # the caller reads the losses every step
+
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event pass (same step, instrumented; not part of the numbers above)
+    roofline, kernels = None, None
+    peaks = load_peaks()
+    if not args.no_profile:
+        prof = KernelProfiler()
+        ops.PROFILER = prof
+        psteps = 2
+        for _ in range(psteps):
+            trainer.step(d_inp, d_gt, d_gf, d_pf)
+        torch.cuda.synchronize()
+        ops.PROFILER = None
+        kernels = prof.summary(psteps)
+        conv = {k: v for k, v in kernels.items() if k.startswith("conv")}
+        dom = max(conv, key=lambda k: conv[k]["ms"])
+        dd = conv[dom]
+        achieved = dd["work"] / (dd["ms"] * 1e-3) / 1e12
+        conv_ms = sum(v["ms_per_step"] for v in conv.values())
+        conv_flops = sum(v["work"] for v in conv.values()) / psteps
+        roofline = {"bound": "tensor", "kernel": {"conv_fwd": "conv_fwd_tc_kernel (forward)", "conv_dgrad":
+                    "conv_fwd_tc_kernel (dgrad)", "conv_wgrad": "conv_wgrad_tc_kernel"}[dom],
+                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "launches_per_step": dd["launches_per_step"], "avg_launch_ms": dd["ms"] / dd["launches"],
+                    "all_conv": {"tflops": conv_flops / (conv_ms * 1e-3) / 1e12, "ms_per_step": conv_ms,
+                                 "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}}
+        for k, v in kernels.items():
+            if k.startswith("bn"):
+                v["gbs"] = v["work"] / (v["ms"] * 1e-3) / 1e9
+                v["frac_hbm"] = v["gbs"] / peaks["hbm_gbs"]
+            else:
+                v["tflops"] = v["work"] / (v["ms"] * 1e-3) / 1e12
+            del v["work"]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    gshapes, dshapes = model_conv_shapes(NFR, ISIZE)
+    g_macs, d_macs = conv_macs_per_clip(netg, gshapes), conv_macs_per_clip(netd, dshapes)
+    flop_per_clip = 2.0 * (3 * g_macs + 6 * d_macs)
+    clips = B * world
+    value = clips * args.steps / (ms * 1e-3)
+    e2e = clips * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": "train_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": clips, "nfr": NFR, "isize": ISIZE, "parallelism": f"dp{world}",
+                   "l2": "per-step inputs (257 MB) and activations (GBs) exceed the 126 MB L2; no explicit flush",
+                   "algorithmic_conv_gflop_per_clip": flop_per_clip / 1e9,
+                   "conv_tflops_whole_step": flop_per_clip * clips * args.steps / (ms * 1e-3) / 1e12 / world,
+                   "optical_flow": "precomputed input (reference computes it on the host, SURVEY 8d)"},
+        "e2e": {"value": e2e, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "losses_last_step": {k: round(v, 6) for k, v in losses.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,7 +40,9 @@ SIGNATURES = {
 }
 
 _lib = None
-LAUNCHES = 0  # number of C-ABI compute calls issued by this process (bench.py reports it)
+LAUNCHES = 0         # C-ABI compute calls issued by this process
+KERNEL_LAUNCHES = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
+_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3}
 
 
 def build(force=False):
@@ -75,9 +77,10 @@ def lib():
 def call(name, *args):
     """Invoke a C-ABI entry point; a non-zero status becomes RuntimeError (the reference's only
     error convention on this path is torch raising RuntimeError)."""
-    global LAUNCHES
+    global LAUNCHES, KERNEL_LAUNCHES
     L = lib()
     rc = getattr(L, name)(*args)
     LAUNCHES += 1
+    KERNEL_LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {L.vfd_last_error().decode()}")

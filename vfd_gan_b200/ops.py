@@ -260,6 +260,14 @@ convlstm_cell_bwd = _define(
 # helpers shared by the autograd functions
 # ------------------------------------------------------------------------------------------------
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core one
+PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
+
+
+def _timed(kind, work, thunk):
+    if PROFILER is None:
+        thunk()
+    else:
+        PROFILER.run(kind, work, thunk)
 
 _scratch = {}
 
@@ -402,7 +410,8 @@ class ConvFn(torch.autograd.Function):
         if bias is not None:
             b = torch.zeros(pk.fwd.shape[0], dtype=torch.float32, device=x.device)
             b[:cout] = bias.detach()
-        conv3d_fwd(x, pk.fwd, b, out, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT)
+        flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
+        _timed("conv_fwd", flops, lambda: conv3d_fwd(x, pk.fwd, b, out, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT))
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_zero = bias_grad_exact_zero
@@ -418,11 +427,14 @@ class ConvFn(torch.autograd.Function):
         pk = _packed(weight)
         if ctx.needs_input_grad[0]:
             gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
-            conv3d_fwd(g, pk.dgrad, None, gx, kd, kh, kw, pk.kc_d, x.shape[-1], CONV_IMPL_DIRECT)
+            flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
+            _timed("conv_dgrad", flops,
+                   lambda: conv3d_fwd(g, pk.dgrad, None, gx, kd, kh, kw, pk.kc_d, x.shape[-1], CONV_IMPL_DIRECT))
         if ctx.needs_input_grad[1]:
             taps = kd * kh * kw
             acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
-            conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT)
+            flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
+            _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
             gw = torch.empty_like(weight, dtype=torch.float32)
             unpack_wgrad(acc, gw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -449,16 +461,18 @@ class BnActFn(torch.autograd.Function):
         dev = y.device
         stats = torch.empty(4, C, dtype=torch.float32, device=dev)
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        bn_prepare(y, bn_scratch(dev, C), cvalid, None if pre_bias is None else pre_bias.detach(), gamma.detach(),
-                   beta.detach(), running_mean, running_var,
-                   momentum, eps, train, mean, invstd, scale, shift)
+        pb = None if pre_bias is None else pre_bias.detach()
+        _timed("bn_stats", 2.0 * y.numel(), lambda: bn_prepare(y, bn_scratch(dev, C), cvalid, pb, gamma.detach(), beta.detach(),
+                                                   running_mean, running_var, momentum, eps, train, mean, invstd,
+                                                   scale, shift))
         pd, ph, pw = pool
         full = pooled = None
         if want_full:
             full = full_out_holder[0].detach() if full_out_holder is not None else cl_empty(N, D, H, W, C, dev)
         if want_pool:
             pooled = cl_empty(N, D // pd, H // ph, W // pw, C, dev)
-        bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed)
+        nbytes = 2.0 * y.numel() * (1 + (1 if want_full else 0)) + (2.0 * pooled.numel() if want_pool else 0)
+        _timed("bn_act_fwd", nbytes, lambda: bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed))
         ctx.save_for_backward(y, stats)
         ctx.cfg = (cvalid, slope, pool, drop_p, seed, train)
         ctx.has_pre_bias = pre_bias is not None
@@ -475,8 +489,10 @@ class BnActFn(torch.autograd.Function):
         tmp = torch.empty(2, C, dtype=torch.float32, device=dev)
         dgamma = torch.empty(cvalid, dtype=torch.float32, device=dev)
         dbeta = torch.empty(cvalid, dtype=torch.float32, device=dev)
-        bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw, drop_p,
-                   seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy)
+        nbytes = 2.0 * y.numel() * 3 + 2.0 * 2 * sum(g.numel() for g in (g_full, g_pool) if g is not None)
+        _timed("bn_act_bwd", nbytes,
+               lambda: bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw,
+                                  drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy))
         # a conv bias folded into training-mode BN has an identically zero gradient
         gpb = torch.zeros(cvalid, dtype=torch.float32, device=dev) if ctx.has_pre_bias else None
         return (dy, dgamma, dbeta, gpb) + (None,) * 12
