@@ -1,0 +1,374 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle / torch fp32 and the
+golden fixtures. Tolerances (BASELINE north_star): per-layer outputs and gradients rel <= 1e-3 against
+the bf16-operand-matched fp32 oracle when the kernel emits fp32 (bf16-stored results additionally carry
+the bf16 rounding of the stored value, 2^-9 max / ~1.7e-3 rms, so those use 3e-3); losses <= 1e-2 after 10
+steps against the pure-fp32 reference trajectory."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vfd_gan_b200 as V
+from vfd_gan_b200 import ops
+from oracle import vfd_oracle as O
+from helpers import golden, rel, build_cfg1_nets, build_small_nets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CONV_CASES = [
+    (8, 16, (1, 3, 3), 1, 2, 16, 16), (3, 21, (1, 3, 3), 2, 4, 16, 16), (32, 48, (1, 3, 3), 2, 2, 16, 32),
+    (64, 64, (3, 1, 1), 1, 4, 16, 16), (96, 86, (1, 3, 3), 1, 2, 32, 32), (128, 300, (1, 1, 1), 1, 2, 16, 16),
+    (32, 1, (3, 3, 3), 1, 4, 16, 16), (24, 40, (1, 3, 3), 16, 1, 7, 7), (2, 32, (3, 1, 1), 1, 8, 12, 20),
+    (256, 72, (3, 3, 3), 1, 2, 8, 8), (512, 658, (1, 3, 3), 2, 1, 8, 8), (14, 32, (1, 1, 1), 3, 5, 9, 11),
+]
+
+
+def _conv_all(x, w, b, gy, direct):
+    ops.CONV_IMPL_DIRECT = direct
+    try:
+        xc = ops.PackFn.apply(x, 0).requires_grad_(True)
+        wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        yc = ops.ConvFn.apply(xc, wp, bp, True, False)
+        y = ops.UnpackFn.apply(yc, w.shape[0])
+        yc.backward(ops.PackFn.apply(gy, 0))
+        gx = torch.empty_like(x)
+        ops.unpack_ncdhw(xc.grad, gx)
+        return y.detach(), gx, wp.grad, bp.grad
+    finally:
+        ops.CONV_IMPL_DIRECT = False
+
+
+@pytest.mark.parametrize("cin,cout,k,N,D,H,W", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(cin, cout, k, N, D, H, W):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(N, cin, D, H, W, generator=g).to(DEV)
+    w = (torch.randn(cout, cin, *k, generator=g) * 0.1).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    gy = torch.randn(N, cout, D, H, W, generator=g).to(DEV)
+    xr = x.bfloat16().float().requires_grad_(True)          # operand-matched fp32 reference
+    wr = w.bfloat16().float().requires_grad_(True)
+    gyr = gy.bfloat16().float()
+    yr = F.conv3d(xr, wr, b, padding=tuple(kk // 2 for kk in k))
+    yr.backward(gyr)
+    tc = _conv_all(x, w, b, gy, direct=False)
+    di = _conv_all(x, w, b, gy, direct=True)
+    assert rel(tc[0], yr) < 1e-4 and rel(tc[0], di[0]) < 1e-4          # fp32-out forward
+    assert rel(tc[1], xr.grad) < 3e-3 and rel(tc[1], di[1]) < 1e-3     # bf16-stored dgrad
+    assert rel(tc[2], wr.grad) < 1e-4 and rel(tc[2], di[2]) < 1e-4     # fp32 wgrad
+    assert rel(tc[3], gyr.sum((0, 2, 3, 4))) < 1e-4
+
+
+def test_conv_dgrad_fp32_output_meets_1e3():
+    """dgrad with the fp32 epilogue: only accumulation order differs from the matched oracle."""
+    x = torch.randn(2, 64, 2, 16, 16, device=DEV)
+    w = torch.randn(48, 64, 1, 3, 3, device=DEV) * 0.1
+    gy = torch.randn(2, 48, 2, 16, 16, device=DEV)
+    xr = x.bfloat16().float().requires_grad_(True)
+    F.conv3d(xr, w.bfloat16().float(), None, padding=(0, 1, 1)).backward(gy.bfloat16().float())
+    pk = ops._packed(w)
+    gyc = ops.PackFn.apply(gy, 0)
+    out = torch.empty(2, 2, 16, 16, 64, dtype=torch.float32, device=DEV)
+    ops.conv3d_fwd(gyc, pk.dgrad, None, out, 1, 3, 3, pk.kc_d, 64, False)
+    assert rel(out.permute(0, 4, 1, 2, 3), xr.grad) < 1e-4
+
+
+def test_conv_linearity_and_adjoint_at_full_size():
+    """Size-independent properties on the dominant layer at BASELINE size (uconv1.spatial_conv, B=8 of
+    the 32-clip batch: 1.6M voxels, 96 -> 86 channels): conv(2x) == 2 conv(x) exactly (power-of-two scale)
+    and <conv(x), g> == <x, dgrad(g)> == <w, wgrad(x, g)>."""
+    N, D, S, cin, cout = 8, 16, 112, 96, 86
+    x = torch.randn(N, D, S, S, cin, device=DEV).bfloat16()
+    w = (torch.randn(cout, cin, 1, 3, 3, device=DEV) * 0.05)
+    gy = torch.randn(N, D, S, S, 88, device=DEV).bfloat16()
+    gy[..., cout:] = 0
+    xg = x.clone().requires_grad_(True)
+    wp = w.clone().requires_grad_(True)
+    y = ops.ConvFn.apply(xg, wp, None, True, False)
+    y2 = ops.ConvFn.apply((x * 2), wp, None, True, False)
+    assert torch.equal(y2, y * 2)
+    y.backward(gy)
+    ip_y = float((y.double() * gy.double()).sum())
+    ip_x = float((xg.grad.double() * x.double()).sum())
+    ip_w = float((wp.grad.double() * w.bfloat16().double()).sum())
+    assert abs(ip_x - ip_y) <= 3e-3 * abs(ip_y)       # dgrad is stored in bf16
+    assert abs(ip_w - ip_y) <= 1e-4 * abs(ip_y)
+
+
+def test_empty_batch_is_a_no_op():
+    x = torch.zeros(0, 2, 8, 8, 16, dtype=torch.bfloat16, device=DEV)
+    w = torch.randn(8, 16, 1, 3, 3, device=DEV)
+    y = ops.ConvFn.apply(x, w, None, False, False)
+    assert y.shape == (0, 2, 8, 8, 8)
+
+
+@pytest.mark.parametrize("C,slope,pool,shape", [(24, 0.2, (2, 2, 2), (2, 4, 8, 8)), (8, 0.01, (1, 2, 2), (3, 2, 7, 7)),
+                                                (64, 0.0, (1, 1, 1), (2, 2, 6, 10)), (128, 0.01, (2, 1, 1), (1, 4, 5, 9))])
+def test_bn_act_pool_forward_backward(C, slope, pool, shape):
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(N, C, D, H, W, generator=g) * 2 + 0.5)
+    bn = torch.nn.BatchNorm3d(C)
+    bn.weight.data.normal_(1.0, 0.2, generator=g)
+    bn.bias.data.normal_(0, 0.2, generator=g)
+    xr = x.bfloat16().float().requires_grad_(True)
+    full_r = F.leaky_relu(bn(xr), slope)
+    pool_r = F.avg_pool3d(full_r, pool)
+    gf, gp = torch.randn(full_r.shape, generator=g), torch.randn(pool_r.shape, generator=g)
+    (full_r * gf.bfloat16().float()).sum().backward(retain_graph=True)
+    (pool_r * gp.bfloat16().float()).sum().backward()
+
+    bn2 = torch.nn.BatchNorm3d(C).to(DEV)
+    bn2.load_state_dict({k: v for k, v in torch.nn.BatchNorm3d(C).state_dict().items()})
+    bn2.weight.data.copy_(bn.weight.data)
+    bn2.bias.data.copy_(bn.bias.data)
+    xc = ops.PackFn.apply(x.to(DEV), 0).requires_grad_(True)
+    from vfd_gan_b200.spatiotempconv import bn_apply
+    full, pooled = bn_apply(bn2, xc, slope, pool=pool, want_full=True, want_pool=True)
+    Cp = xc.shape[-1]
+    assert rel(full[..., :C].permute(0, 4, 1, 2, 3), full_r) < 3e-3
+    assert rel(pooled[..., :C].permute(0, 4, 1, 2, 3), pool_r) < 3e-3
+    assert float(full[..., C:].abs().max()) == 0.0 if Cp > C else True
+    torch.autograd.backward([full, pooled], [ops.PackFn.apply(gf.to(DEV), 0), ops.PackFn.apply(gp.to(DEV), 0)])
+    assert rel(xc.grad[..., :C].permute(0, 4, 1, 2, 3), xr.grad) < 5e-3
+    assert rel(bn2.weight.grad, bn.weight.grad) < 1e-3 and rel(bn2.bias.grad, bn.bias.grad) < 1e-3
+    assert rel(bn2.running_mean, bn.running_mean) < 1e-3 and rel(bn2.running_var, bn.running_var) < 1e-3
+    assert int(bn2.num_batches_tracked) == 1
+
+
+def test_bn_eval_mode_uses_running_stats():
+    C = 16
+    bn = torch.nn.BatchNorm3d(C)
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2)
+    bn.eval()
+    x = torch.randn(2, C, 2, 4, 4)
+    want = F.relu(bn(x.bfloat16().float()))
+    from vfd_gan_b200.spatiotempconv import bn_apply
+    bn2 = torch.nn.BatchNorm3d(C)
+    bn2.load_state_dict(bn.state_dict())
+    bn2 = bn2.to(DEV).eval()
+    full, _ = bn_apply(bn2, ops.PackFn.apply(x.to(DEV), 0), 0.0)
+    assert rel(full.permute(0, 4, 1, 2, 3), want) < 3e-3
+    assert int(bn2.num_batches_tracked) == 0
+
+
+def test_dropout_is_deterministic_scaled_and_unbiased():
+    C, p = 32, 0.25
+    y = torch.zeros(4, 4, 16, 16, C, dtype=torch.bfloat16, device=DEV)
+    one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    outs = []
+    for seed in (7, 7, 8):
+        o = torch.empty_like(y)
+        ops.bn_act_fwd(y, zero, one, 1.0, o, None, 1, 1, 1, p, seed)
+        outs.append(o.float())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    vals = outs[0].unique()
+    assert len(vals) == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1 / 0.75) < 1e-2
+    keep = float((outs[0] > 0).float().mean())
+    assert abs(keep - 0.75) < 5e-3
+    assert abs(float((outs[0] > 0).float().mean(dim=(0, 1, 2, 3)).std())) < 2e-2   # no per-channel structure
+
+
+@pytest.mark.parametrize("shape,C", [((2, 1, 2, 3), 16), ((1, 2, 7, 7), 256), ((2, 4, 8, 8), 64)])
+def test_upsample_concat_forward_backward(shape, C):
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(W)
+    x = torch.randn(N, C, D, H, W, generator=g)
+    skip = torch.randn(N, 8, 2 * D, 2 * H, 2 * W, generator=g)
+    xr = x.bfloat16().float().requires_grad_(True)
+    up_r = F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=True)
+    go = torch.randn(N, C + 8, 2 * D, 2 * H, 2 * W, generator=g)
+    (torch.cat([up_r, skip.bfloat16().float()], 1) * go.bfloat16().float()).sum().backward()
+    buf = torch.empty(N, 2 * D, 2 * H, 2 * W, C + 8, dtype=torch.bfloat16, device=DEV)
+    buf[..., C:] = ops.PackFn.apply(skip.to(DEV), 0)
+    xc = ops.PackFn.apply(x.to(DEV), 0).requires_grad_(True)
+    sk = buf[..., C:].detach().requires_grad_(True)
+    cat = ops.UpCatFn.apply(xc, sk, [buf])
+    assert rel(cat[..., :C].permute(0, 4, 1, 2, 3), up_r) < 3e-3
+    assert rel(cat[..., C:].permute(0, 4, 1, 2, 3), skip) < 3e-3
+    cat.backward(ops.PackFn.apply(go.to(DEV), 0))
+    assert rel(xc.grad.permute(0, 4, 1, 2, 3), xr.grad) < 3e-3
+    assert rel(sk.grad.permute(0, 4, 1, 2, 3), go[:, C:]) < 3e-3
+
+
+def test_losses_match_reference_fixture():
+    f = golden("losses.pt")
+    p, t = f["p"].to(DEV).requires_grad_(True), f["t"].to(DEV)
+    loss = V.weighted_bce(p, t)
+    assert abs(float(loss) - float(f["wbce"])) <= 1e-5 * abs(float(f["wbce"]))
+    assert abs(float(V.weighted_bce(p, t, 3)) - float(f["wbce_pw3"])) <= 1e-5 * abs(float(f["wbce_pw3"]))
+    loss.backward()
+    pr = f["p"].clone().requires_grad_(True)
+    O.weighted_bce(pr, f["t"]).backward()
+    assert rel(p.grad, pr.grad) < 1e-5
+    a, b = f["a"].to(DEV), f["b"].to(DEV)
+    got = ops.mse_cl(ops.PackFn.apply(a, 0), ops.PackFn.apply(b, 0), 5)
+    want = O.l2_loss(f["a"].bfloat16().float(), f["b"].bfloat16().float())
+    assert abs(float(got) - float(want)) <= 1e-5 * float(want)
+    assert abs(float(V.l2_loss(a, b)) - float(f["l2"])) <= 1e-5 * float(f["l2"])
+
+
+def test_spatiotemporal_conv_module_against_reference_fixture():
+    f = golden("st_conv_small.pt")
+    m = V.SpatioTemporalConv(8, 16, 3, padding=1)
+    m.load_state_dict(f["sd"])
+    m = m.to(DEV).train()
+    x = f["x"].to(DEV).requires_grad_(True)
+    y = m(x)
+    sd = {("m." + k): v.clone() for k, v in f["sd"].items()}
+    ym = O.st_conv(sd, "m", f["x"], (3, 3, 3), True, round_bf16=True)
+    assert rel(y, ym) < 1e-3                       # operand-matched oracle, fp32 epilogue
+    assert rel(y, f["y"]) < 1e-2                   # the reference's own fp32 output
+    y.backward(f["gy"].to(DEV))
+    assert rel(x.grad, f["gx"]) < 3e-2 and rel(m.temporal_conv.weight.grad, f["gw_temporal"]) < 1e-2
+    assert rel(m.temporal_conv.bias.grad, f["gb_temporal"]) < 1e-2
+    assert rel(m.spatial_conv.weight.grad, f["gw_spatial"]) < 3e-2
+    assert rel(m.bn.running_mean, f["sd_after"]["bn.running_mean"]) < 1e-2
+    assert rel(m.bn.running_var, f["sd_after"]["bn.running_var"]) < 1e-2
+
+
+def test_convlstm_cell_against_reference_fixture_and_unroll():
+    f = golden("convlstm_cell.pt")
+    cell = V.ConvLSTMCell((8, 8), 16, 32, (3, 3), True)
+    cell.load_state_dict(f["sd"])
+    cell = cell.to(DEV)
+    h, c = cell(f["x"].to(DEV), (f["h"].to(DEV), f["c"].to(DEV)))
+    assert rel(h, f["h_next"]) < 5e-3 and rel(c, f["c_next"]) < 5e-3
+    hm, cm = O.convlstm_cell(f["sd"], "", f["x"], f["h"], f["c"], round_bf16=True)
+    assert rel(h, hm) < 1e-3 and rel(c, cm) < 1e-3
+    torch.manual_seed(0)
+    lstm = V.ConvLSTM((8, 8), 16, 16, (3, 3), 1, batch_first=True, bias=False).to(DEV)
+    x = torch.randn(2, 3, 16, 8, 8)
+    out, (last,) = lstm(x.to(DEV))
+    want, _ = O.convlstm_unroll({k: v.cpu() for k, v in lstm.state_dict().items()}, "cell_list.0.", x, round_bf16=True)
+    assert out[0].shape == (2, 3, 16, 8, 8) and rel(out[0], want) < 3e-3
+
+
+def test_small_nets_against_reference_fixture():
+    f = golden("netg_netd_small.pt")
+    g, xg, sdisc, xs, tdisc, xt = build_small_nets()
+    g, sdisc, tdisc = g.to(DEV).train(), sdisc.to(DEV).train(), tdisc.to(DEV).train()
+    pred = g(xg.to(DEV))
+    assert pred.shape == f["predict"].shape and rel(pred, f["predict"]) < 2e-2
+    s_cls, s_feat = sdisc(xs.to(DEV))
+    t_cls, t_feat = tdisc(xt.to(DEV))
+    assert s_feat.shape == f["s_feat"].shape and t_feat.shape == f["t_feat"].shape
+    assert rel(s_cls, f["s_cls"]) < 1e-2 and rel(t_cls, f["t_cls"]) < 1e-2
+    assert rel(t_feat, f["t_feat"]) < 5e-2
+
+
+def _grad_envelope_check(net, res):
+    """CUDA gradients must sit inside the bf16 noise envelope: distance to the fp32 oracle no larger than
+    twice the distance of the operand-matched oracle to the fp32 oracle ('gradient fidelity')."""
+    for k, p in net.named_parameters():
+        gf, gm = res[False][k].grad, res[True][k].grad
+        if gf is None or (k.endswith(".bias") and ".bn." not in k and "linear" not in k):
+            continue
+        assert rel(p.grad, gf) <= max(2.0 * rel(gm, gf), 2e-2), k
+
+
+def test_netg_forward_backward_against_oracle():
+    B, D, S = 2, 16, 32
+    torch.manual_seed(0)
+    net = V.NetG()
+    net.apply(V.weights_init)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).train()
+    x = torch.rand(B, 3, D, S, S) * 2 - 1
+    gt = (torch.rand(B, 1, D, S, S) > 0.9).float()
+    pred = net(x.to(DEV))
+    V.weighted_bce(pred, gt.to(DEV)).backward()
+    shapes = [(B, 256, D // 16, S // 16, S // 16), (B, 256, D // 8, S // 8, S // 8), (B, 128, D // 4, S // 4, S // 4),
+              (B, 64, D // 2, S // 2, S // 2)]
+    masks = []
+    for seed, (N, C, d, h, w) in zip(net.last_dropout_seeds, shapes):       # recover the Philox masks
+        o = torch.empty(N, d, h, w, C, dtype=torch.bfloat16, device=DEV)
+        ops.bn_act_fwd(torch.zeros_like(o), torch.zeros(C, device=DEV), torch.ones(C, device=DEV), 1.0, o, None,
+                       1, 1, 1, 0.25, seed)
+        masks.append(o.float().permute(0, 4, 1, 2, 3).cpu().contiguous())
+    res, preds = {}, {}
+    for rb in (True, False):
+        sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        po = O.netg_forward(sdo, x, True, masks, round_bf16=rb)
+        O.weighted_bce(po, gt).backward()
+        res[rb], preds[rb] = sdo, po.detach()
+    assert rel(pred, preds[True]) < 1e-2 and rel(pred, preds[False]) < 1e-2
+    _grad_envelope_check(net, res)
+    for k in sd:
+        if "running" in k:
+            assert rel(net.state_dict()[k], res[False][k]) < 3e-2, k
+        if "num_batches" in k:
+            assert int(net.state_dict()[k]) == 1
+
+
+def test_netd_forward_backward_against_oracle():
+    B, D, S = 2, 16, 64
+    args = types.SimpleNamespace(nfr=D, isize=S)
+    torch.manual_seed(1)
+    net = V.NetD(args)
+    net.apply(V.weights_init)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).train()
+    x, y = torch.rand(B, 3, D, S, S), torch.rand(B, 3, D, S, S) * 2 - 1
+    outs = net(x.to(DEV), y.to(DEV))
+    (F.binary_cross_entropy(outs[0], torch.ones_like(outs[0])) +
+     F.binary_cross_entropy(outs[2], torch.ones_like(outs[2]))).backward()
+    res, fw = {}, {}
+    for rb in (True, False):
+        sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        o = O.netd_forward(sdo, x, y, True, rb)
+        (F.binary_cross_entropy(o[0], torch.ones_like(o[0])) + F.binary_cross_entropy(o[2], torch.ones_like(o[2]))).backward()
+        res[rb], fw[rb] = sdo, [t.detach() for t in o]
+    for i in range(4):
+        assert rel(outs[i], fw[False][i]) <= max(2.0 * rel(fw[True][i], fw[False][i]), 5e-3)
+    _grad_envelope_check(net, res)
+
+
+def test_train_trajectory_against_reference_fixture():
+    """10 train steps at BASELINE config 1 against the losses the reference's own modules produced."""
+    f = golden("step_traj_cfg1.pt")
+    netg, netd = build_cfg1_nets()
+    netg, netd = netg.to(DEV), netd.to(DEV)
+    tr = V.GanTrainStep(netg, netd)
+    cfg = f["config"]
+    for it, want in enumerate(f["traj"]):
+        batch = O.synthetic_batch(cfg["B"], cfg["D"], cfg["S"], seed=cfg["data_seed0"] + it)
+        tr.step(*(t.to(DEV) for t in batch))
+        got = tr.losses_dict()
+        for k in want:
+            assert abs(got[k] - want[k]) <= 1e-2 * abs(want[k]) + 1e-5, (it, k, got[k], want[k])
+
+
+def test_module_step_equals_fused_step():
+    """The drop-in path (reference-style optimize_params with autograd through the modules, including the
+    dead adversarial backward) and GanTrainStep produce the same losses."""
+    netg, netd = build_cfg1_nets()
+    netg2, netd2 = build_cfg1_nets()
+    netg, netd, netg2, netd2 = netg.to(DEV), netd.to(DEV), netg2.to(DEV), netd2.to(DEV)
+    fused = V.GanTrainStep(netg2, netd2)
+    og = torch.optim.Adam(netg.parameters(), lr=2e-5, betas=(0.5, 0.999))
+    od = torch.optim.Adam(netd.parameters(), lr=2e-5, betas=(0.5, 0.999))
+    bce = torch.nn.BCELoss()
+    for it in range(2):
+        inp, gt, gf, pf = (t.to(DEV) for t in O.synthetic_batch(2, 16, 64, seed=it))
+        netg.train(), netd.train()
+        predict = netg(inp)                                            # models/mygannet.py:275-286
+        s_pr, s_fr, t_pr, t_fr = netd(V.gray2rgb(gt), gf)
+        s_pf, s_ff, t_pf, t_ff = netd(V.gray2rgb(predict.detach()), pf)
+        og.zero_grad()
+        adv = V.l2_loss(s_fr, s_ff) + V.l2_loss(t_fr, t_ff)
+        con = V.weighted_bce(predict, gt)
+        err_g = adv * 1 + con * 10
+        err_g.backward(retain_graph=True)
+        og.step()
+        od.zero_grad()
+        ones, zeros = torch.ones(2, device=DEV), torch.zeros(2, device=DEV)
+        err_d = ((bce(s_pr, ones) + bce(t_pr, ones)) * 0.5 + (bce(s_pf, zeros) + bce(t_pf, zeros)) * 0.5) * 0.5
+        err_d.backward()
+        od.step()
+        fused.step(inp, gt, gf, pf)
+        got = fused.losses_dict()
+        assert abs(got["g/err_g"] - float(err_g)) <= 2e-3 * abs(float(err_g))
+        assert abs(got["d/err_d"] - float(err_d)) <= 2e-3 * abs(float(err_d))
