@@ -94,6 +94,14 @@ class KernelProfiler:
         b.record()
         self.records.append((kind, work, a, b))
 
+    def dump(self, path, steps):
+        """Per-call table (one step's worth): kind, work (FLOP or bytes), milliseconds."""
+        n = len(self.records) // steps
+        rows = [{"i": i, "kind": k, "work": w, "ms": a.elapsed_time(b)} for i, (k, w, a, b) in
+                enumerate(self.records[-n:])]
+        with open(path, "w") as f:
+            json.dump(rows, f)
+
     def summary(self, steps):
         out = {}
         for kind, work, a, b in self.records:
@@ -199,6 +207,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--dump-kernels", default="", help="write the per-call CUDA-event table of one step to this file")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -291,6 +300,8 @@ def main():
         torch.cuda.synchronize()
         ops.PROFILER = None
         kernels = prof.summary(psteps)
+        if args.dump_kernels and rank == 0:
+            prof.dump(args.dump_kernels, psteps)
         conv = {k: v for k, v in kernels.items() if k.startswith("conv")}
         dom = max(conv, key=lambda k: conv[k]["ms"])
         dd = conv[dom]

@@ -160,13 +160,27 @@ bn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   if (active) {
-    for (long long r = r0 + rl; r < r1; r += rows_per_iter) {
-      float v[8];
-      load8(x + r * ld + cg * 8, v);
+    for (long long r = r0 + rl; r < r1; r += 4 * rows_per_iter) {
+      uint4 raw[4];
+      bool ok[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += v[j];
-        ss[j] = fmaf(v[j], v[j], ss[j]);
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * rows_per_iter;
+        ok[u] = rr < r1;
+        if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(x + rr * ld + cg * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          s[2 * j] += f.x;
+          s[2 * j + 1] += f.y;
+          ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+          ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+        }
       }
     }
 #pragma unroll
@@ -229,109 +243,206 @@ struct ActGeom {
   int C;              // padded channel count (multiple of 8)
 };
 
+// The BN/activation kernels map one thread to (pool window, 8-channel group). A block owns a
+// contiguous range of windows; a thread keeps its channel group for the whole kernel (so the
+// per-channel constants live in registers) and strides over windows. All loads of an iteration are
+// issued before any arithmetic (U windows x NV voxels = 8 independent 128-bit loads per tensor).
+struct WinGeom {
+  int WD, WH, WW;   // windows per axis (ceil: partial windows still carry full-resolution voxels)
+  int QD, QH, QW;   // pooled extent (floor)
+  unsigned nwin;
+};
+template <int PD, int PH, int PW>
+__device__ __forceinline__ WinGeom win_geom(const ActGeom& g) {
+  WinGeom w;
+  w.WD = (g.D + PD - 1) / PD;
+  w.WH = (g.H + PH - 1) / PH;
+  w.WW = (g.W + PW - 1) / PW;
+  w.QD = g.D / PD;
+  w.QH = g.H / PH;
+  w.QW = g.W / PW;
+  w.nwin = (unsigned)g.N * w.WD * w.WH * w.WW;
+  return w;
+}
+__device__ __forceinline__ void decode_win(unsigned win, const WinGeom& wg, int& n, int& wd, int& wh,
+                                           int& ww) {
+  ww = win % wg.WW;
+  unsigned t = win / wg.WW;
+  wh = t % wg.WH;
+  t /= wg.WH;
+  wd = t % wg.WD;
+  n = t / wg.WD;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
 // out = dropout(act(y * scale + shift)); optionally also the average-pooled tensor.
-// One thread per (pool window, channel group).
-__global__ void __launch_bounds__(256)
+template <int PD, int PH, int PW, bool DROP>
+__global__ void __launch_bounds__(256, 2)
 bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                   const float* __restrict__ scale, const float* __restrict__ shift, float slope,
                   bf16* __restrict__ out_full, long long full_ld, bf16* __restrict__ out_pool,
                   long long pool_ld, float drop_p, unsigned long long seed) {
-  const int CG = g.C / 8;
-  const int WD = (g.D + g.pd - 1) / g.pd, WH = (g.H + g.ph - 1) / g.ph, WW = (g.W + g.pw - 1) / g.pw;
-  const int PD = g.D / g.pd, PH = g.H / g.ph, PW = g.W / g.pw;
-  const long long total = (long long)g.N * WD * WH * WW * CG;
-  const float inv_win = 1.0f / (float)(g.pd * g.ph * g.pw);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long t = i / CG;
-    const int ww = (int)(t % WW);
-    t /= WW;
-    const int wh = (int)(t % WH);
-    t /= WH;
-    const int wd = (int)(t % WD);
-    const int n = (int)(t / WD);
-    float sc[8], sf[8], acc[8];
+  constexpr int NV = PD * PH * PW;
+  constexpr int U = NV >= 8 ? 1 : 8 / NV;
+  const int CG = g.C >> 3;
+  const int rpi = 256 / CG;
+  const int tid = threadIdx.x;
+  if (tid >= rpi * CG) return;
+  const int cg = tid % CG, wl = tid / CG;
+  const WinGeom wg = win_geom<PD, PH, PW>(g);
+  const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+  const unsigned w_begin = blockIdx.x * per_block;
+  const unsigned w_end = min(wg.nwin, w_begin + per_block);
+  float sc[8], sf[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(scale + cg * 8 + j);
-      sf[j] = __ldg(shift + cg * 8 + j);
-      acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + cg * 8 + j);
+    sf[j] = __ldg(shift + cg * 8 + j);
+  }
+  const float inv_win = 1.0f / (float)NV;
+  for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+    uint4 raw[U][NV];
+    long long vox[U][NV];
+    bool ok[U][NV];
+    bool pool_ok[U];
+    long long pvox[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned win = wb + u * rpi;
+      const bool wv = win < w_end;
+      int n, wd, wh, ww;
+      decode_win(wv ? win : w_begin, wg, n, wd, wh, ww);
+      pool_ok[u] = wv && wd < wg.QD && wh < wg.QH && ww < wg.QW;
+      pvox[u] = (((long long)n * wg.QD + wd) * wg.QH + wh) * wg.QW + ww;
+#pragma unroll
+      for (int a = 0; a < PD; ++a)
+#pragma unroll
+        for (int b = 0; b < PH; ++b)
+#pragma unroll
+          for (int c = 0; c < PW; ++c) {
+            const int v = (a * PH + b) * PW + c;
+            const int d = wd * PD + a, h = wh * PH + b, w = ww * PW + c;
+            ok[u][v] = wv && d < g.D && h < g.H && w < g.W;
+            vox[u][v] = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+            if (ok[u][v]) raw[u][v] = ldg16(y + vox[u][v] * y_ld + cg * 8);
+          }
     }
-    for (int a = 0; a < g.pd; ++a)
-      for (int b = 0; b < g.ph; ++b)
-        for (int c = 0; c < g.pw; ++c) {
-          const int d = wd * g.pd + a, h = wh * g.ph + b, w = ww * g.pw + c;
-          if (d >= g.D || h >= g.H || w >= g.W) continue;
-          const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-          float v[8];
-          load8(y + vox * y_ld + cg * 8, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(v[j], sc[j], sf[j]);
-            v[j] = z > 0.f ? z : z * slope;
-          }
-          if (drop_p > 0.f) {
-            float m[8];
-            dropout8(seed, vox, cg, drop_p, m);
+    for (int u = 0; u < U; ++u) {
+      float acc[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= m[j];
-          }
-          if (out_full != nullptr) store8(out_full + vox * full_ld + cg * 8, v);
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int v = 0; v < NV; ++v) {
+        if (!ok[u][v]) continue;
+        float x[8];
+        unpack8(raw[u][v], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(x[j], sc[j], sf[j]);
+          x[j] = z > 0.f ? z : z * slope;
         }
-    if (out_pool != nullptr && wd < PD && wh < PH && ww < PW) {
+        if (DROP) {
+          float m[8];
+          dropout8(seed, vox[u][v], cg, drop_p, m);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= inv_win;
-      const long long pv = (((long long)n * PD + wd) * PH + wh) * PW + ww;
-      store8(out_pool + pv * pool_ld + cg * 8, acc);
+          for (int j = 0; j < 8; ++j) x[j] *= m[j];
+        }
+        if (out_full != nullptr) store8(out_full + vox[u][v] * full_ld + cg * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += x[j];
+      }
+      if (out_pool != nullptr && pool_ok[u]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv_win;
+        store8(out_pool + pvox[u] * pool_ld + cg * 8, acc);
+      }
     }
   }
 }
 
-// Upstream gradient of the activation output for 8 channels of voxel (n,d,h,w):
-// g_full (gradient of the full-resolution output) + g_pool / window (gradient of the pooled one),
-// times the dropout multiplier and the (leaky) ReLU slope.
-__device__ __forceinline__ void act_upstream(const bf16* __restrict__ y, long long y_ld,
-                                             const ActGeom& g, const float* sc, const float* sf,
-                                             float slope, const bf16* __restrict__ g_full,
-                                             long long gf_ld, const bf16* __restrict__ g_pool,
-                                             long long gp_ld, float drop_p, unsigned long long seed,
-                                             int n, int d, int h, int w, int cg, float* yv,
-                                             float* gv) {
-  const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-  load8(y + vox * y_ld + cg * 8, yv);
+// Shared front end of the two backward passes: loads y / g_full for the window's voxels and the
+// window's g_pool, and turns them into the gradient w.r.t. the BatchNorm output.
+template <int PD, int PH, int PW, bool DROP>
+struct BwdWindow {
+  static constexpr int NV = PD * PH * PW;
+  uint4 ry[NV], rg[NV], rp;
+  long long vox[NV];
+  bool ok[NV], pool_ok;
+
+  __device__ __forceinline__ void load(unsigned win, bool wv, unsigned w_begin, const WinGeom& wg,
+                                       const ActGeom& g, int cg, const bf16* __restrict__ y,
+                                       long long y_ld, const bf16* __restrict__ g_full, long long gf_ld,
+                                       const bf16* __restrict__ g_pool, long long gp_ld) {
+    int n, wd, wh, ww;
+    decode_win(wv ? win : w_begin, wg, n, wd, wh, ww);
+    pool_ok = wv && g_pool != nullptr && wd < wg.QD && wh < wg.QH && ww < wg.QW;
+    if (pool_ok) {
+      const long long pv = (((long long)n * wg.QD + wd) * wg.QH + wh) * wg.QW + ww;
+      rp = ldg16(g_pool + pv * gp_ld + cg * 8);
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gv[j] = 0.f;
-  if (g_full != nullptr) load8(g_full + vox * gf_ld + cg * 8, gv);
-  if (g_pool != nullptr) {
-    const int PD = g.D / g.pd, PH = g.H / g.ph, PW = g.W / g.pw;
-    const int qd = d / g.pd, qh = h / g.ph, qw = w / g.pw;
-    if (qd < PD && qh < PH && qw < PW) {
+    for (int a = 0; a < PD; ++a)
+#pragma unroll
+      for (int b = 0; b < PH; ++b)
+#pragma unroll
+        for (int c = 0; c < PW; ++c) {
+          const int v = (a * PH + b) * PW + c;
+          const int d = wd * PD + a, h = wh * PH + b, w = ww * PW + c;
+          ok[v] = wv && d < g.D && h < g.H && w < g.W;
+          vox[v] = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+          if (ok[v]) {
+            ry[v] = ldg16(y + vox[v] * y_ld + cg * 8);
+            if (g_full != nullptr) rg[v] = ldg16(g_full + vox[v] * gf_ld + cg * 8);
+          }
+        }
+  }
+  // gradient w.r.t. z = y*scale+shift for voxel v (yv receives the unpacked y)
+  __device__ __forceinline__ void grad(int v, bool has_full, const float* sc, const float* sf,
+                                       float slope, float drop_p, unsigned long long seed, int cg,
+                                       float* yv, float* gv) const {
+    unpack8(ry[v], yv);
+    if (has_full) {
+      unpack8(rg[v], gv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+    }
+    if (pool_ok) {
       float t[8];
-      const long long pv = (((long long)n * PD + qd) * PH + qh) * PW + qw;
-      load8(g_pool + pv * gp_ld + cg * 8, t);
-      const float inv_win = 1.0f / (float)(g.pd * g.ph * g.pw);
+      unpack8(rp, t);
+      const float inv_win = 1.0f / (float)NV;
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = fmaf(t[j], inv_win, gv[j]);
     }
-  }
-  if (drop_p > 0.f) {
-    float m[8];
-    dropout8(seed, vox, cg, drop_p, m);
+    if (DROP) {
+      float m[8];
+      dropout8(seed, vox[v], cg, drop_p, m);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gv[j] *= m[j];
-  }
+      for (int j = 0; j < 8; ++j) gv[j] *= m[j];
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float z = fmaf(yv[j], sc[j], sf[j]);
-    gv[j] = z > 0.f ? gv[j] : gv[j] * slope;
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(yv[j], sc[j], sf[j]);
+      gv[j] = z > 0.f ? gv[j] : gv[j] * slope;
+    }
   }
-}
+};
 
 // Pass 1 of BN backward: per-channel sum(g) and sum(g * xhat).
-__global__ void __launch_bounds__(256)
+template <int PD, int PH, int PW, bool DROP>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift,
@@ -339,20 +450,20 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                          unsigned long long seed, double* __restrict__ sums) {
   extern __shared__ float sh[];  // [2][C]
+  constexpr int NV = PD * PH * PW;
+  constexpr int U = NV >= 4 ? 1 : 4 / NV;
   const int C = g.C;
-  const int CG = C / 8;
-  const int rows_per_iter = 256 / CG;
+  const int CG = C >> 3;
+  const int rpi = 256 / CG;
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
   __syncthreads();
-  const long long V = (long long)g.N * g.D * g.H * g.W;
-  const bool active = tid < rows_per_iter * CG;
-  const int cg = tid % CG;
-  const int rl = tid / CG;
-  const long long per_block = (V + gridDim.x - 1) / gridDim.x;
-  const long long r0 = blockIdx.x * per_block;
-  const long long r1 = (r0 + per_block < V) ? (r0 + per_block) : V;
-  if (active) {
+  if (tid < rpi * CG) {
+    const int cg = tid % CG, wl = tid / CG;
+    const WinGeom wg = win_geom<PD, PH, PW>(g);
+    const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+    const unsigned w_begin = blockIdx.x * per_block;
+    const unsigned w_end = min(wg.nwin, w_begin + per_block);
     float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -362,22 +473,25 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
       is[j] = __ldg(invstd + cg * 8 + j);
       s1[j] = s2[j] = 0.f;
     }
-    for (long long r = r0 + rl; r < r1; r += rows_per_iter) {
-      long long t = r;
-      const int w = (int)(t % g.W);
-      t /= g.W;
-      const int h = (int)(t % g.H);
-      t /= g.H;
-      const int d = (int)(t % g.D);
-      const int n = (int)(t / g.D);
-      float yv[8], gv[8];
-      act_upstream(y, y_ld, g, sc, sf, slope, g_full, gf_ld, g_pool, gp_ld, drop_p, seed, n, d, h,
-                   w, cg, yv, gv);
+    const bool has_full = g_full != nullptr;
+    for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+      BwdWindow<PD, PH, PW, DROP> bw[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += gv[j];
-        s2[j] = fmaf(gv[j], (yv[j] - mu[j]) * is[j], s2[j]);
-      }
+      for (int u = 0; u < U; ++u)
+        bw[u].load(wb + u * rpi, wb + u * rpi < w_end, w_begin, wg, g, cg, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!bw[u].ok[v]) continue;
+          float yv[8], gv[8];
+          bw[u].grad(v, has_full, sc, sf, slope, drop_p, seed, cg, yv, gv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += gv[j];
+            s2[j] = fmaf(gv[j], (yv[j] - mu[j]) * is[j], s2[j]);
+          }
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -408,7 +522,8 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, int Cva
 }
 
 // Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2)
-__global__ void __launch_bounds__(256)
+template <int PD, int PH, int PW, bool DROP>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -416,36 +531,44 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                         const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                         unsigned long long seed, const float* __restrict__ c1,
                         const float* __restrict__ c2, bf16* __restrict__ dy, long long dy_ld) {
-  const int CG = g.C / 8;
-  const long long V = (long long)g.N * g.D * g.H * g.W;
-  const long long total = V * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const long long r = i / CG;
-    long long t = r;
-    const int w = (int)(t % g.W);
-    t /= g.W;
-    const int h = (int)(t % g.H);
-    t /= g.H;
-    const int d = (int)(t % g.D);
-    const int n = (int)(t / g.D);
-    float sc[8], sf[8];
+  constexpr int NV = PD * PH * PW;
+  constexpr int U = NV >= 4 ? 1 : 4 / NV;
+  const int CG = g.C >> 3;
+  const int rpi = 256 / CG;
+  const int tid = threadIdx.x;
+  if (tid >= rpi * CG) return;
+  const int cg = tid % CG, wl = tid / CG;
+  const WinGeom wg = win_geom<PD, PH, PW>(g);
+  const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+  const unsigned w_begin = blockIdx.x * per_block;
+  const unsigned w_end = min(wg.nwin, w_begin + per_block);
+  float sc[8], sf[8], mu[8], is[8], k1[8], k2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(scale + cg * 8 + j);
-      sf[j] = __ldg(shift + cg * 8 + j);
-    }
-    float yv[8], gv[8], o[8];
-    act_upstream(y, y_ld, g, sc, sf, slope, g_full, gf_ld, g_pool, gp_ld, drop_p, seed, n, d, h, w,
-                 cg, yv, gv);
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + cg * 8 + j);
+    sf[j] = __ldg(shift + cg * 8 + j);
+    mu[j] = __ldg(mean + cg * 8 + j);
+    is[j] = __ldg(invstd + cg * 8 + j);
+    k1[j] = __ldg(c1 + cg * 8 + j);
+    k2[j] = __ldg(c2 + cg * 8 + j);
+  }
+  const bool has_full = g_full != nullptr;
+  for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+    BwdWindow<PD, PH, PW, DROP> bw[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      const float xh = (yv[j] - __ldg(mean + c)) * __ldg(invstd + c);
-      o[j] = sc[j] * (gv[j] - __ldg(c1 + c) - xh * __ldg(c2 + c));
-    }
-    store8(dy + r * dy_ld + cg * 8, o);
+    for (int u = 0; u < U; ++u)
+      bw[u].load(wb + u * rpi, wb + u * rpi < w_end, w_begin, wg, g, cg, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!bw[u].ok[v]) continue;
+        float yv[8], gv[8], o[8];
+        bw[u].grad(v, has_full, sc, sf, slope, drop_p, seed, cg, yv, gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gv[j] - k1[j] - (yv[j] - mu[j]) * is[j] * k2[j]);
+        store8(dy + bw[u].vox[v] * dy_ld + cg * 8, o);
+      }
   }
 }
 
@@ -831,6 +954,28 @@ static int fill_act_geom(ActGeom& g, int N, int D, int H, int W, int C, int pd, 
   return 0;
 }
 
+static int win_grid(const ActGeom& g, int pd, int ph, int pw, int nv_per_iter) {
+  const long long nwin = (long long)g.N * ((g.D + pd - 1) / pd) * ((g.H + ph - 1) / ph) * ((g.W + pw - 1) / pw);
+  const int rpi = 256 / (g.C / 8);
+  long long b = (nwin + (long long)rpi * nv_per_iter * 4 - 1) / ((long long)rpi * nv_per_iter * 4);
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+#define VFD_POOL_DISPATCH(KERNEL, DROPFLAG, LAUNCH)                                               \
+  do {                                                                                            \
+    if (pd == 1 && ph == 1 && pw == 1) {                                                          \
+      if (DROPFLAG) { auto kfn = KERNEL<1, 1, 1, true>; LAUNCH; }                                 \
+      else { auto kfn = KERNEL<1, 1, 1, false>; LAUNCH; }                                         \
+    } else if (DROPFLAG) {                                                                        \
+      return set_error(VFD_ERR_ARG, "dropout is only fused into un-pooled BN+activation");        \
+    } else if (pd == 2 && ph == 2 && pw == 2) { auto kfn = KERNEL<2, 2, 2, false>; LAUNCH; }      \
+    else if (pd == 1 && ph == 2 && pw == 2) { auto kfn = KERNEL<1, 2, 2, false>; LAUNCH; }        \
+    else if (pd == 2 && ph == 1 && pw == 1) { auto kfn = KERNEL<2, 1, 1, false>; LAUNCH; }        \
+    else return set_error(VFD_ERR_ARG, "pool window must be (1,1,1), (2,2,2), (1,2,2) or (2,1,1)"); \
+  } while (0)
+
 VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, int W, int C,
                               const float* scale, const float* shift, float slope, void* out_full,
                               long long full_ld, void* out_pool, long long pool_ld, int pd, int ph,
@@ -840,11 +985,13 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
   if (out_pool && check_cl(out_pool, pool_ld, C, "bn_act_fwd: bad pooled output")) return VFD_ERR_ARG;
   ActGeom g;
   if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
-  const long long total = (long long)N * ((D + pd - 1) / pd) * ((H + ph - 1) / ph) * ((W + pw - 1) / pw) * (C / 8);
-  if (total == 0) return 0;
-  bn_act_fwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)y, y_ld, g, scale, shift, slope,
-                                                         (bf16*)out_full, full_ld, (bf16*)out_pool,
-                                                         pool_ld, drop_p, seed);
+  if ((long long)N * D * H * W >= (1LL << 31)) return set_error(VFD_ERR_ARG, "bn_act_fwd: more than 2^31 voxels");
+  if ((long long)N * D * H * W == 0) return 0;
+  const bool drop = drop_p > 0.f;
+  const int grid = win_grid(g, pd, ph, pw, 8 / (pd * ph * pw) > 0 ? 8 / (pd * ph * pw) : 1);
+  VFD_POOL_DISPATCH(bn_act_fwd_kernel, drop,
+                    (kfn<<<grid, 256, 0, STREAM>>>((const bf16*)y, y_ld, g, scale, shift, slope, (bf16*)out_full,
+                                                   full_ld, (bf16*)out_pool, pool_ld, drop_p, seed)));
   return check_launch("bn_act_fwd");
 }
 
@@ -861,16 +1008,22 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   ActGeom g;
   if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
   const long long V = (long long)N * D * H * W;
+  if (V >= (1LL << 31)) return set_error(VFD_ERR_ARG, "bn_act_bwd: more than 2^31 voxels");
   if (V == 0) return 0;
-  bn_act_bwd_reduce_kernel<<<stats_grid(V, C), 256, 2 * C * sizeof(float), STREAM>>>(
-      (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
-      (const bf16*)g_pool, gp_ld, drop_p, seed, sums);
+  const bool drop = drop_p > 0.f;
+  const int nvi = 4 / (pd * ph * pw) > 0 ? 4 / (pd * ph * pw) : 1;
+  const int grid = win_grid(g, pd, ph, pw, nvi);
+  VFD_POOL_DISPATCH(bn_act_bwd_reduce_kernel, drop,
+                    (kfn<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(
+                        (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
+                        (const bf16*)g_pool, gp_ld, drop_p, seed, sums)));
   if (int e = check_launch("bn_act_bwd_reduce")) return e;
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
   if (int e = check_launch("bn_bwd_finalize")) return e;
-  bn_act_bwd_apply_kernel<<<grid_for(V * (C / 8)), 256, 0, STREAM>>>(
-      (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
-      (const bf16*)g_pool, gp_ld, drop_p, seed, c1, c2, (bf16*)dy, dy_ld);
+  VFD_POOL_DISPATCH(bn_act_bwd_apply_kernel, drop,
+                    (kfn<<<grid, 256, 0, STREAM>>>((const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
+                                                   (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p,
+                                                   seed, c1, c2, (bf16*)dy, dy_ld)));
   return check_launch("bn_act_bwd_apply");
 }
 
