@@ -37,12 +37,15 @@ VFD_API int vfd_abi_version(void);
  *   bias     fp32 [w_rows] or NULL
  *   out      bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1) channels-last, row pitch out_ld;
  *            columns [0, out_cols) are written
+ *   stats    optional double [2][stats_ld] (zeroed): the epilogue adds the per-channel sum and sum of
+ *            squares of the stored bf16 values, i.e. the vfd_bn_stats result for the BatchNorm
+ *            that follows, without re-reading the tensor (bf16 output only)
  *   kc       channel block per MMA K-slab: 16, 32 or 64 (selects the 32/64/128-byte swizzle)
  * The input gradient (dgrad) is the same call on dy with mode-1 packed weights. */
 VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w_packed, int w_rows,
                            int cin_k, const float* bias, void* out, long long out_ld, int out_cols,
-                           int out_fp32, int N, int D, int H, int W, int kd, int kh, int kw, int kc,
-                           void* stream);
+                           int out_fp32, double* stats, int stats_ld, int N, int D, int H, int W, int kd,
+                           int kh, int kw, int kc, void* stream);
 
 /* Weight gradient of the same conv (autograd of nn.Conv3d, reached from err_g.backward() /
  * err_d.backward() at models/mygannet.py:311,344):

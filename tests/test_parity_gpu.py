@@ -70,7 +70,7 @@ def test_conv_dgrad_fp32_output_meets_1e3():
     pk = ops._packed(w)
     gyc = ops.PackFn.apply(gy, 0)
     out = torch.empty(2, 2, 16, 16, 64, dtype=torch.float32, device=DEV)
-    ops.conv3d_fwd(gyc, pk.dgrad, None, out, 1, 3, 3, pk.kc_d, 64, False)
+    ops.conv3d_fwd(gyc, pk.dgrad, None, out, None, 1, 3, 3, pk.kc_d, 64, False)
     assert rel(out.permute(0, 4, 1, 2, 3), xr.grad) < 1e-4
 
 

@@ -12,6 +12,8 @@
 //
 //   forward / dgrad : D[voxel][n]  = sum_{tap,c} X[voxel+tap][c] * Wp[n][tap][c]   (A,B K-major)
 //   wgrad           : dW[tap][co][ci] = sum_voxel dY[voxel][co] * X[voxel+tap][ci] (A,B MN-major)
+#include <cstdio>
+#include <cstdlib>
 #include "ptx.cuh"
 #include "vfd_internal.h"
 
@@ -30,18 +32,121 @@ struct ConvGeom {
   int8_t tap[27][4];  // (dd, dh, dw, unused): input offset of each tap relative to the output voxel
 };
 
+// Output side shared by the forward kernels.
+struct Epilogue {
+  int n_rows;        // rows in the packed weight matrix (valid bias entries)
+  int out_cols;      // columns to store (multiple of 8)
+  long long out_ld;  // elements between consecutive voxels in the output buffer
+  int out_fp32;
+  const float* bias;
+  void* out;
+  double* stats;     // optional [2][stats_ld]: per-channel sum / sum of squares of the stored bf16 values
+  int stats_ld;
+};
+
+// column sums of a 32-row x 32-column register tile spread over a warp (row = lane): after the
+// butterfly lane L holds the sum of column L. 31 shuffles.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// One accumulator tile (this warp's 32 TMEM lanes x block_n columns) -> bias, convert, store, and
+// optionally per-channel statistics into the CTA's shared accumulators. Warp-collective.
+__device__ __forceinline__ void epilogue_tile(const Epilogue& e, uint32_t tacc, int block_n, int col0,
+                                              bool valid, long long vox, int lane, float* s_sum,
+                                              float* s_sq) {
+  for (int c = 0; c < block_n; c += 32) {
+    float v[32];
+    if (c + 32 <= block_n) {
+      tmem_ld32(tacc + c, v);
+    } else {
+      tmem_ld16(tacc + c, v);
+#pragma unroll
+      for (int i = 16; i < 32; ++i) v[i] = 0.f;
+    }
+    const int col = col0 + c;
+    if (e.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col + i < e.n_rows) v[i] += __ldg(e.bias + col + i);
+    }
+    if (e.out_fp32) {
+      if (valid) {
+        float* o = reinterpret_cast<float*>(e.out) + vox * e.out_ld + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (c + i < block_n && col + i < e.out_cols)
+            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + vox * e.out_ld + col;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk;
+        const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]);
+        const __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+        const __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+        const __nv_bfloat162 t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+        pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<const uint32_t*>(&t2);
+        pk.w = *reinterpret_cast<const uint32_t*>(&t3);
+        if (valid && c + i < block_n && col + i < e.out_cols) *reinterpret_cast<uint4*>(o + i) = pk;
+        if (e.stats != nullptr) {  // statistics of exactly what is stored
+          const float2 f0 = __bfloat1622float2(t0), f1 = __bfloat1622float2(t1);
+          const float2 f2 = __bfloat1622float2(t2), f3 = __bfloat1622float2(t3);
+          v[i] = f0.x; v[i + 1] = f0.y; v[i + 2] = f1.x; v[i + 3] = f1.y;
+          v[i + 4] = f2.x; v[i + 5] = f2.y; v[i + 6] = f3.x; v[i + 7] = f3.y;
+        }
+      }
+    }
+    if (e.stats != nullptr) {
+      float sq[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = valid ? v[i] : 0.f;
+        sq[i] = v[i] * v[i];
+      }
+      const float cs = warp_colsum32(v, lane);
+      const float cq = warp_colsum32(sq, lane);
+      if (c + lane < block_n && col + lane < 1024) {
+        atomicAdd(&s_sum[col + lane], cs);
+        atomicAdd(&s_sq[col + lane], cq);
+      }
+    }
+  }
+}
+
+// After the last tile: the four epilogue warps publish the CTA's statistics.
+__device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_thread, const float* s_sum,
+                                                     const float* s_sq) {
+  if (e.stats == nullptr) return;
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+  for (int j = epi_thread; j < e.stats_ld && j < 1024; j += 128) {
+    if (s_sum[j] != 0.f || s_sq[j] != 0.f) {
+      atomicAdd(e.stats + j, (double)s_sum[j]);
+      atomicAdd(e.stats + e.stats_ld + j, (double)s_sq[j]);
+    }
+  }
+}
+
 struct FwdParams {
   ConvGeom g;
   int cblocks;    // channel blocks of KC per tap
   int n_tiles;    // tiles along the GEMM N (output channel) dimension
   int block_n;    // multiple of 16, <= 256
   int stages;
-  int n_rows;     // rows in the packed weight matrix (valid bias entries)
-  int out_cols;   // columns to store (multiple of 8)
-  long long out_ld;  // elements between consecutive voxels in the output buffer
-  int out_fp32;
-  const float* bias;
-  void* out;
+  Epilogue epi;
 };
 
 __device__ __forceinline__ void tile_origin(const ConvGeom& g, int mt, int& n0, int& d0, int& h0,
@@ -64,10 +169,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_sum[1024], s_sq[1024];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
+  if (p.epi.stats != nullptr)
+    for (int i = threadIdx.x; i < 1024; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.f;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -132,6 +240,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
+      const uint64_t d0 = sdesc_kmajor(smem_u32(smem), kRowBytes);  // A and B tiles share the layout
+      const uint32_t dlo0 = desc_lo(d0), dhi = desc_hi(d0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -143,13 +253,11 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t alo = dlo0 + ((static_cast<uint32_t>(s) * stage_bytes) >> 4);
+          const uint32_t blo = alo + (kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            umma_bf16(tacc, sdesc_kmajor(sa + k * 32, kRowBytes), sdesc_kmajor(sb + k * 32, kRowBytes),
-                      idesc, (ks | k) != 0);
-          }
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tacc, desc_join(alo + 2 * k, dhi), desc_join(blo + 2 * k, dhi), idesc, (ks | k) != 0);
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
@@ -188,42 +296,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c = 0; c < p.block_n; c += 16) {
-        float v[16];
-        tmem_ld16(tacc + c, v);  // warp-collective: every lane participates
-        const int col = col0 + c;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (col + i < p.n_rows) v[i] += __ldg(p.bias + col + i);
-        }
-        if (valid) {
-          if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + col;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              if (col + i < p.out_cols)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + col;
-#pragma unroll
-            for (int i = 0; i < 16; i += 8) {
-              if (col + i < p.out_cols) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(o + i) = pk;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -232,6 +305,195 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         aph ^= 1;
       }
     }
+    epilogue_flush_stats(p.epi, (warp - 2) * 32 + lane, s_sum, s_sq);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ resident-weight forward
+// Persistent forward/dgrad kernel for layers whose whole packed weight matrix fits in shared memory
+// (every "small-N" layer of the GAN: first/last convs, uconv1, temporal and 1x1x1 convs ...):
+//   * the weights are loaded ONCE per CTA and stay resident, so per tile only the input moves;
+//   * the input arrives as halo planes ((16+kh-1) x (8+kw-1) voxels per channel block and d-plane)
+//     through a ring of TMA slots; the kh*kw taps of a plane are row-shifted UMMA descriptors into
+//     the same slot (UMMA applies the swizzle to absolute smem address bits, so a descriptor may
+//     start at any row of the swizzle pattern; verified on B200);
+//   * up to four TMEM accumulator stages decouple the MMA issuer from the epilogue warps;
+//   * the epilogue optionally accumulates the per-channel sum / sum of squares of the bf16-rounded
+//     output for the BatchNorm that follows (saves one full read of the tensor).
+struct ResParams {
+  int N, D, H, W;
+  int tilesW, tilesH;
+  int kd, kh, kw;
+  int cblocks, block_n;
+  int a_slots, a_slot_bytes, b_tile_bytes;
+  int acc_stages, acc_stride;
+  Epilogue epi;
+};
+
+constexpr int kResMaxASlots = 16;
+
+template <int KC>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ ResParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[kResMaxASlots], a_empty[kResMaxASlots];
+  __shared__ uint64_t b_full, acc_full[4], acc_empty[4];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_sum[256], s_sq[256];  // block_n <= 256 and a single N tile in this kernel
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int kRowBytes = KC * 2;
+  const int ntaps = p.kd * p.kh * p.kw;
+  const int nbt = ntaps * p.cblocks;  // resident weight tiles
+  uint8_t* smem_a = smem + static_cast<size_t>(nbt) * p.b_tile_bytes;
+  const int PWc = 8 + p.kw - 1, PHc = 16 + p.kh - 1;
+  const int a_bytes = PWc * PHc * kRowBytes;
+  const int total_tiles = p.N * p.D * p.tilesH * p.tilesW;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_slots; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < p.acc_stages; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.f;
+  if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: one barrier, all tiles
+      mbar_expect_tx(&b_full, nbt * p.block_n * kRowBytes);
+      for (int t = 0; t < nbt; ++t)
+        tma_load_2d(&tmB, &b_full, smem + static_cast<size_t>(t) * p.b_tile_bytes, t * KC, 0);
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int w0 = (t % p.tilesW) * 8;
+        t /= p.tilesW;
+        const int h0 = (t % p.tilesH) * 16;
+        t /= p.tilesH;
+        const int d = t % p.D;
+        const int n = t / p.D;
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int a = 0; a < p.kd; ++a) {
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            mbar_expect_tx(&a_full[sa], a_bytes);
+            tma_load_5d(&tmA, &a_full[sa], smem_a + static_cast<size_t>(sa) * p.a_slot_bytes, cb * KC,
+                        w0 - p.kw / 2, h0 - p.kh / 2, d + a - p.kd / 2, n);
+            if (++sa == p.a_slots) {
+              sa = 0;
+              pha ^= 1;
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
+      const uint64_t da0 = sdesc_kmajor_ex(smem_u32(smem_a), kRowBytes, PWc * kRowBytes, 0);
+      const uint64_t db0 = sdesc_kmajor(smem_u32(smem), kRowBytes);
+      const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
+      const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_tile16 = p.b_tile_bytes >> 4;
+      const uint32_t row16 = kRowBytes >> 4;
+      const int khw = p.kh * p.kw;
+      int sa = 0, as = 0;
+      uint32_t pha = 0, aph = 0;
+      mbar_wait(&b_full, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * p.acc_stride;
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          uint32_t blo_plane = blo0 + static_cast<uint32_t>(cb) * b_tile16;  // tap 0 of this channel block
+          for (int a = 0; a < p.kd; ++a) {
+            mbar_wait(&a_full[sa], pha);
+            tc_fence_after();
+            const uint32_t alo = alo0 + static_cast<uint32_t>(sa) * a_slot16;
+            uint32_t blo = blo_plane;
+            uint32_t arow = alo;
+            for (int b = 0; b < p.kh; ++b) {
+              uint32_t at = arow;
+              for (int c = 0; c < p.kw; ++c) {
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  umma_bf16(tacc, desc_join(at + 2 * k, ahi), desc_join(blo + 2 * k, bhi), idesc, accumulate);
+                  accumulate = 1;
+                }
+                at += row16;                           // next tap in w: one halo row further
+                blo += p.cblocks * b_tile16;           // next tap's weight tile for this channel block
+              }
+              arow += PWc * row16;                     // next tap row in h
+            }
+            blo_plane += static_cast<uint32_t>(khw) * p.cblocks * b_tile16;
+            umma_commit(&a_empty[sa]);
+            if (++sa == p.a_slots) {
+              sa = 0;
+              pha ^= 1;
+            }
+          }
+        }
+        umma_commit(&acc_full[as]);
+        if (++as == p.acc_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int w = (t % p.tilesW) * 8 + (row & 7);
+      t /= p.tilesW;
+      const int h = (t % p.tilesH) * 16 + (row >> 3);
+      t /= p.tilesH;
+      const int d = t % p.D;
+      const int n = t / p.D;
+      const bool valid = (w < p.W) && (h < p.H);
+      const long long vox = ((static_cast<long long>(n) * p.D + d) * p.H + h) * p.W + w;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_tile(p.epi, tacc, p.block_n, 0, valid, vox, lane, s_sum, s_sq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == p.acc_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    epilogue_flush_stats(p.epi, (warp - 2) * 32 + lane, s_sum, s_sq);
   }
 
   tc_fence_before();
@@ -339,18 +601,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0 && has_work) {
       const uint32_t idesc = idesc_bf16_m128(p.block_n, true, true);
+      const uint64_t d0 = sdesc_mnmajor128(smem_u32(smem), kWgBoxBytes);
+      const uint32_t dlo0 = desc_lo(d0), dhi = desc_hi(d0);
       int s = 0;
       uint32_t ph = 0;
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t sb = sa + 2 * kWgBoxBytes;
+        const uint32_t alo = dlo0 + ((static_cast<uint32_t>(s) * stage_bytes) >> 4);
+        const uint32_t blo = alo + ((2 * kWgBoxBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 128 voxels per chunk = 8 x K16; 16 rows = 2048 B
-          umma_bf16(tmem_base, sdesc_mnmajor128(sa + k * 2048, kWgBoxBytes),
-                    sdesc_mnmajor128(sb + k * 2048, kWgBoxBytes), idesc, (c > c_begin) || (k != 0));
-        }
+        for (int k = 0; k < 8; ++k)  // 128 voxels per chunk = 8 x K16; 16 rows = 2048 B = 128 x 16 B
+          umma_bf16(tmem_base, desc_join(alo + 128 * k, dhi), desc_join(blo + 128 * k, dhi), idesc,
+                    (c > c_begin) || (k != 0));
         umma_commit(&empty_bar[s]);
         if (++s == p.stages) {
           s = 0;
@@ -395,6 +658,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
+  // cuTensorMapEncodeTiled is a driver call: the calling thread (e.g. an autograd worker that has
+  // not launched anything yet) must have the primary context bound, which a runtime no-op does.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* sym = nullptr;
@@ -430,7 +700,13 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, long long ld, int chan
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(boxC * 2),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(VFD_ERR_DRIVER, "cuTensorMapEncodeTiled(activation) failed");
+  if (r != CUDA_SUCCESS) {
+    char msg[384];
+    snprintf(msg, sizeof(msg),
+             "cuTensorMapEncodeTiled(activation) failed (%d): ptr %p ld %lld ch %d dims N%d D%d H%d W%d box C%d W%d H%d D%d N%d",
+             (int)r, ptr, ld, channels, N, D, H, W, boxC, TW, TH, TD, TN);
+    return set_error(VFD_ERR_DRIVER, msg);
+  }
   return 0;
 }
 
@@ -521,7 +797,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel<KC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_tc)");
     attr_set = true;
   }
@@ -532,15 +808,72 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   return check_launch("conv_fwd_tc");
 }
 
+constexpr int kResBudget = 221 * 1024;
+
+// Resident-weight kernel: returns 1 when the geometry does not qualify (caller falls back), 0 on
+// success, negative... error codes otherwise are returned through *err.
+template <int KC>
+static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_packed, int w_rows, int cin_k,
+                          ResParams& p, cudaStream_t stream, int* err) {
+  *err = 0;
+  const int PWc = 8 + p.kw - 1, PHc = 16 + p.kh - 1;
+  const int ntaps = p.kd * p.kh * p.kw;
+  p.b_tile_bytes = (p.block_n * KC * 2 + 1023) & ~1023;
+  p.a_slot_bytes = (PWc * PHc * KC * 2 + 1023) & ~1023;
+  const long long b_total = (long long)ntaps * p.cblocks * p.b_tile_bytes;
+  if (b_total + 3LL * p.a_slot_bytes > kResBudget) return 1;
+  if ((long long)ntaps * p.cblocks * p.block_n * KC * 2 >= (1 << 20)) return 1;  // mbarrier tx-count limit
+  int slots = (int)((kResBudget - b_total) / p.a_slot_bytes);
+  if (slots > kResMaxASlots) slots = kResMaxASlots;
+  p.a_slots = slots;
+  p.acc_stride = 32;
+  while (p.acc_stride < p.block_n) p.acc_stride *= 2;
+  p.acc_stages = 512 / p.acc_stride;
+  if (p.acc_stages > 4) p.acc_stages = 4;
+  CUtensorMap tmA, tmB;
+  if ((*err = make_act_map(&tmA, x, x_ld, cin, p.N, p.D, p.H, p.W, KC, PWc, PHc, 1, 1))) return 0;
+  if ((*err = make_weight_map(&tmB, w_packed, w_rows, (long long)ntaps * cin_k, KC, p.block_n))) return 0;
+  size_t smem = (size_t)b_total + (size_t)p.a_slots * p.a_slot_bytes + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         223 * 1024);
+    if (e != cudaSuccess) {
+      *err = set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_res)");
+      return 0;
+    }
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.N * p.D * p.tilesH * p.tilesW;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  conv_fwd_res_kernel<KC><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, p);
+  *err = check_launch("conv_fwd_res");
+  return 0;
+}
+
+// VFD_CONV_RES=0 disables the resident-weight kernel (debug / A-B timing)
+static bool res_enabled() {
+  static int mode = -1;
+  if (mode == -1) {
+    const char* e = getenv("VFD_CONV_RES");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 }  // namespace vfd
 
 using namespace vfd;
 
 VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w_packed,
                               int w_rows, int cin_k, const float* bias, void* out,
-                              long long out_ld, int out_cols, int out_fp32, int N, int D, int H,
-                              int W, int kd, int kh, int kw, int kc, void* stream_) {
+                              long long out_ld, int out_cols, int out_fp32, double* stats,
+                              int stats_ld, int N, int D, int H, int W, int kd, int kh, int kw, int kc,
+                              void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (stats != nullptr && (out_fp32 || stats_ld < out_cols || stats_ld > 1024))
+    return set_error(VFD_ERR_ARG, "conv3d_fwd: fused statistics need a bf16 output and out_cols <= stats_ld <= 1024");
   if (kc != 16 && kc != 32 && kc != 64) return set_error(VFD_ERR_ARG, "kc must be 16, 32 or 64");
   if (cin_k % kc || w_rows % 16 || out_cols % 8 || out_cols > w_rows + 8)
     return set_error(VFD_ERR_ARG, "conv3d_fwd: bad channel padding");
@@ -548,17 +881,42 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
       (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(VFD_ERR_ARG, "conv3d_fwd: output must be 16-byte aligned");
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;  // empty batch: nothing to do
+  Epilogue epi;
+  epi.n_rows = w_rows;
+  epi.out_cols = out_cols;
+  epi.out_ld = out_ld;
+  epi.out_fp32 = out_fp32;
+  epi.bias = bias;
+  epi.out = out;
+  epi.stats = stats;
+  epi.stats_ld = stats_ld;
+  if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
+    return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
+  if (res_enabled() && w_rows <= 256 && (stats == nullptr || stats_ld <= 256)) {
+    ResParams rp;
+    rp.N = N; rp.D = D; rp.H = H; rp.W = W;
+    rp.tilesW = (W + 7) / 8;
+    rp.tilesH = (H + 15) / 16;
+    rp.kd = kd; rp.kh = kh; rp.kw = kw;
+    rp.cblocks = cin_k / kc;
+    rp.block_n = w_rows;
+    rp.epi = epi;
+    // tiles are 8 x 16 voxels of one (n, d) plane: require a reasonable fill
+    const double fill = (double)W * H / ((double)rp.tilesW * 8 * rp.tilesH * 16);
+    if (fill >= 0.7) {
+      int err = 0, fb;
+      if (kc == 64) fb = try_launch_res<64>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
+      else if (kc == 32) fb = try_launch_res<32>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
+      else fb = try_launch_res<16>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
+      if (!fb) return err;
+    }
+  }
   FwdParams p;
   if (int e = fill_geom(p.g, N, D, H, W, kd, kh, kw)) return e;
   p.cblocks = cin_k / kc;
   p.n_tiles = (w_rows + 255) / 256;
   p.block_n = (((w_rows + p.n_tiles - 1) / p.n_tiles) + 15) & ~15;
-  p.n_rows = w_rows;
-  p.out_cols = out_cols;
-  p.out_ld = out_ld;
-  p.out_fp32 = out_fp32;
-  p.bias = bias;
-  p.out = out;
+  p.epi = epi;
   CUtensorMap tmA, tmB;
   if (int e = make_act_map(&tmA, x, x_ld, cin, N, D, H, W, kc, p.g.TW, p.g.TH, p.g.TD, p.g.TN))
     return e;

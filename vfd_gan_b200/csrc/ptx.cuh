@@ -138,6 +138,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1").
 //   start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 at [46,48),
 //   swizzle mode in [61,64): 2 = 128B, 4 = 64B, 6 = 32B.
@@ -153,6 +172,21 @@ __device__ __forceinline__ uint64_t sdesc_kmajor(uint32_t saddr, uint32_t row_by
   d |= mode << 61;
   return d;
 }
+// Same, for an operand whose 8-row groups are sbo_bytes apart and whose first row may sit at any
+// row of the swizzle pattern (row-shifted window into a larger "halo" tile). base_offset is the
+// descriptor's 3-bit pattern phase field (bits [49,52)).
+__device__ __forceinline__ uint64_t sdesc_kmajor_ex(uint32_t saddr, uint32_t row_bytes,
+                                                    uint32_t sbo_bytes, uint32_t base_offset) {
+  const uint64_t mode = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= mode << 61;
+  return d;
+}
 // MN-major operand, 128B swizzle: rows are K (one row = 64 MN-elements = 128 B), 8 K-rows per
 // 1024 B swizzle atom (SBO = 1024), consecutive 64-element MN blocks are lbo_bytes apart.
 __device__ __forceinline__ uint64_t sdesc_mnmajor128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -164,6 +198,17 @@ __device__ __forceinline__ uint64_t sdesc_mnmajor128(uint32_t saddr, uint32_t lb
   d |= 2ull << 61;
   return d;
 }
+// The MMA-issuing thread is a single lane: keep its per-instruction integer work minimal by splitting
+// descriptors into a constant high word and a low word that only receives 32-bit adds
+// (start address and LBO live in the low word, in 16-byte units).
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M=128.
 __device__ __host__ __forceinline__ uint32_t idesc_bf16_m128(uint32_t n, bool a_mn, bool b_mn) {
   uint32_t d = 0;

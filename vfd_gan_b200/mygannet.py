@@ -36,7 +36,7 @@ class NetgConv(nn.Module):
     def forward_cl(self, xc, **kw):
         if self.bn.training or self.bn.running_mean is None:
             y, tb = self.conv.forward_cl(xc, fold_bias=True)
-            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, **kw)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, stats_ready=True, **kw)
         return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):
@@ -130,7 +130,7 @@ class NetdConv(nn.Module):
     def forward_cl(self, xc, **kw):
         if self.bn.training or self.bn.running_mean is None:
             y, tb = self.conv.forward_cl(xc, fold_bias=True)
-            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, **kw)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, stats_ready=True, **kw)
         return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):

@@ -41,6 +41,9 @@ def round_up(x, m):
 def pick_kc(cin_p):
     """Channel block per MMA K-slab (16/32/64): the largest one whose padded K stays within 10 %
     of the tightest padding."""
+    import os
+    if os.environ.get("VFD_FORCE_KC64") and cin_p > 32:
+        return 64
     best = min(round_up(cin_p, k) for k in (16, 32, 64))
     for kc in (64, 32, 16):
         if round_up(cin_p, kc) <= 1.1 * best:
@@ -92,16 +95,20 @@ def as_cl_grad(g):
 # ------------------------------------------------------------------------------------------------
 # raw ops (mutating "out" style; registered with torch.library)
 # ------------------------------------------------------------------------------------------------
-def _conv3d_fwd(x, w_packed, bias, out, kd, kh, kw, kc, out_cols, direct):
+def _conv3d_fwd(x, w_packed, bias, out, stats, kd, kh, kw, kc, out_cols, direct):
     N, D, H, W, C, ld = _check_cl(x, "conv3d_fwd input")
     rows, taps, cin_k = w_packed.shape
     out_fp32 = 1 if out.dtype == torch.float32 else 0
-    args = [x.data_ptr(), ld, C, w_packed.data_ptr(), rows, cin_k, _ptr(bias), out.data_ptr(),
-            _ld(out), out_cols, out_fp32, N, D, H, W, kd, kh, kw]
+    head = [x.data_ptr(), ld, C, w_packed.data_ptr(), rows, cin_k, _ptr(bias), out.data_ptr(), _ld(out), out_cols,
+            out_fp32]
     if direct:
-        _lib.call("vfd_conv3d_fwd_direct", *args, _stream())
+        _lib.call("vfd_conv3d_fwd_direct", *head, N, D, H, W, kd, kh, kw, _stream())
+        if stats is not None:   # the CUDA-core cross-check path has no fused statistics
+            _lib.call("vfd_bn_stats", out.data_ptr(), _ld(out), out.shape[-1], N * D * H * W, stats.data_ptr(),
+                      _stream())
     else:
-        _lib.call("vfd_conv3d_fwd", *args, kc, _stream())
+        _lib.call("vfd_conv3d_fwd", *head, _ptr(stats), 0 if stats is None else stats.numel() // 2, N, D, H, W, kd,
+                  kh, kw, kc, _stream())
 
 
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct):
@@ -139,10 +146,10 @@ def _unpack_wgrad(acc, gw):
 
 
 def _bn_prepare(y, sums, cvalid, pre_bias, gamma, beta, running_mean, running_var, momentum, eps, train, mean,
-                invstd, scale, shift):
+                invstd, scale, shift, stats_ready):
     N, D, H, W, C, ld = _check_cl(y, "bn input")
     V = N * D * H * W
-    if train:
+    if train and not stats_ready:
         _lib.call("vfd_bn_stats", y.data_ptr(), ld, C, V, sums.data_ptr(), _stream())
     _lib.call("vfd_bn_finalize", sums.data_ptr(), C, cvalid, V, _ptr(pre_bias), gamma.data_ptr(), beta.data_ptr(),
               _ptr(running_mean), _ptr(running_var), momentum, eps, 1 if train else 0, mean.data_ptr(),
@@ -216,8 +223,8 @@ def _convlstm_cell_bwd(act, c_cur, c_next, dh, dc_in, dgates, dc_cur):
 
 
 conv3d_fwd = _define(
-    "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, int kd, int kh, int kw, int kc, "
-    "int out_cols, bool direct) -> ()", _conv3d_fwd)
+    "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
+    "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct) -> ()",
     _conv3d_wgrad)
@@ -229,7 +236,7 @@ bn_prepare = _define(
     "bn_prepare(Tensor y, Tensor(a!) sums, int cvalid, Tensor? pre_bias, Tensor gamma, Tensor beta, "
     "Tensor(b!)? running_mean, "
     "Tensor(c!)? running_var, float momentum, float eps, bool train, Tensor(d!) mean, Tensor(e!) invstd, "
-    "Tensor(f!) scale, Tensor(g!) shift) -> ()", _bn_prepare)
+    "Tensor(f!) scale, Tensor(g!) shift, bool stats_ready) -> ()", _bn_prepare)
 bn_act_fwd = _define(
     "bn_act_fwd(Tensor y, Tensor scale, Tensor shift, float slope, Tensor(a!)? out_full, Tensor(b!)? out_pool, "
     "int pd, int ph, int pw, float drop_p, int seed) -> ()", _bn_act_fwd)
@@ -398,7 +405,7 @@ class ConvFn(torch.autograd.Function):
     training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, out_fp32, bias_grad_exact_zero):
+    def forward(ctx, x, weight, bias, out_fp32, bias_grad_exact_zero, fuse_stats=False):
         N, D, H, W, Cin_p, _ = _check_cl(x, "conv input")
         cout, cin, kd, kh, kw = _wshape(weight)
         if round_up(cin, 8) != Cin_p:
@@ -411,7 +418,12 @@ class ConvFn(torch.autograd.Function):
             b = torch.zeros(pk.fwd.shape[0], dtype=torch.float32, device=x.device)
             b[:cout] = bias.detach()
         flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
-        _timed("conv_fwd", flops, lambda: conv3d_fwd(x, pk.fwd, b, out, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT))
+        # fuse_stats: the epilogue also accumulates the following BatchNorm's sum / sum-of-squares
+        # into the shared self-clearing scratch (the caller passes stats_ready=True to BnActFn)
+        st = bn_scratch(x.device, cout_p) if (fuse_stats and not out_fp32 and cout_p <= 1024) else None
+        ctx.stats_fused = st is not None
+        _timed("conv_fwd", flops,
+               lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT))
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_zero = bias_grad_exact_zero
@@ -429,7 +441,8 @@ class ConvFn(torch.autograd.Function):
             gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             _timed("conv_dgrad", flops,
-                   lambda: conv3d_fwd(g, pk.dgrad, None, gx, kd, kh, kw, pk.kc_d, x.shape[-1], CONV_IMPL_DIRECT))
+                   lambda: conv3d_fwd(g, pk.dgrad, None, gx, None, kd, kh, kw, pk.kc_d, x.shape[-1],
+                                      CONV_IMPL_DIRECT))
         if ctx.needs_input_grad[1]:
             taps = kd * kh * kw
             acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
@@ -444,7 +457,7 @@ class ConvFn(torch.autograd.Function):
                 s = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
                 channel_sum(g, s)
                 gb = s[:cout].clone()
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class BnActFn(torch.autograd.Function):
@@ -455,7 +468,7 @@ class BnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, gamma, beta, pre_bias, running_mean, running_var, train, momentum, eps, slope, pool, drop_p,
-                seed, want_full, want_pool, full_out_holder):
+                seed, want_full, want_pool, full_out_holder, stats_ready=False):
         N, D, H, W, C, _ = _check_cl(y, "bn input")
         cvalid = gamma.numel()
         dev = y.device
@@ -464,7 +477,7 @@ class BnActFn(torch.autograd.Function):
         pb = None if pre_bias is None else pre_bias.detach()
         _timed("bn_stats", 2.0 * y.numel(), lambda: bn_prepare(y, bn_scratch(dev, C), cvalid, pb, gamma.detach(), beta.detach(),
                                                    running_mean, running_var, momentum, eps, train, mean, invstd,
-                                                   scale, shift))
+                                                   scale, shift, bool(stats_ready and train)))
         pd, ph, pw = pool
         full = pooled = None
         if want_full:
@@ -495,7 +508,7 @@ class BnActFn(torch.autograd.Function):
                                   drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy))
         # a conv bias folded into training-mode BN has an identically zero gradient
         gpb = torch.zeros(cvalid, dtype=torch.float32, device=dev) if ctx.has_pre_bias else None
-        return (dy, dgamma, dbeta, gpb) + (None,) * 12
+        return (dy, dgamma, dbeta, gpb) + (None,) * 13
 
 
 class UpCatFn(torch.autograd.Function):

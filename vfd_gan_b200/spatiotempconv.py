@@ -23,7 +23,7 @@ def intermed_channels(in_channels, out_channels, kernel_size):
 
 
 def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None,
-             pre_bias=None):
+             pre_bias=None, stats_ready=False):
     """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16.
     ``pre_bias``: bias of the conv that produced ``y`` when it was left out of ``y`` (see
     ``SpatioTemporalConv.forward_cl``)."""
@@ -34,7 +34,8 @@ def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, w
         raise NotImplementedError("BatchNorm3d(affine=False) is not supported")
     full, pooled = ops.BnActFn.apply(y, bn.weight, bn.bias, pre_bias, bn.running_mean, bn.running_var, train,
                                      float(bn.momentum), float(bn.eps), float(slope), tuple(pool), float(drop_p),
-                                     int(seed), want_full, want_pool, None if full_out is None else [full_out])
+                                     int(seed), want_full, want_pool, None if full_out is None else [full_out],
+                                     stats_ready)
     if train and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return full, pooled
@@ -76,15 +77,16 @@ class SpatioTemporalConv(nn.Module):
                                       "only, got " + self._unsupported)
         bn_train = self.bn.training or self.bn.running_mean is None
         sb = self.spatial_conv.bias
-        if bn_train and sb is not None:
-            y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, None, False, False)
-            a1, _ = bn_apply(self.bn, y1, 0.0, pre_bias=sb)
+        if bn_train:
+            # bias folded into the BN (if any) and BN statistics accumulated by the conv epilogue
+            y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, None, False, False, True)
+            a1, _ = bn_apply(self.bn, y1, 0.0, pre_bias=sb, stats_ready=True)
         else:
             y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, sb, False, False)
             a1, _ = bn_apply(self.bn, y1, 0.0)
         tb = self.temporal_conv.bias
-        if fold_bias:
-            return ops.ConvFn.apply(a1, self.temporal_conv.weight, None, out_fp32, False), tb
+        if fold_bias:   # the caller's BatchNorm is in training mode: same treatment for temporal_conv
+            return ops.ConvFn.apply(a1, self.temporal_conv.weight, None, out_fp32, False, True), tb
         return ops.ConvFn.apply(a1, self.temporal_conv.weight, tb, out_fp32, False)
 
     def forward(self, x):
