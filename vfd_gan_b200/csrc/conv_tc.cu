@@ -651,6 +651,164 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------ wgrad v2
+// One CTA = (voxel range, 128 output channels, ci_n input channels, one d-plane of the filter). Per
+// 8x16-voxel chunk it loads the dY tile and ONE halo plane of X; each of the plane's kh*kw taps has its
+// own TMEM accumulator (kh*kw*ci_n <= 512 columns) fed from row-shifted MN-major descriptors into the
+// halo plane. dY and X are each read once per chunk instead of once per tap.
+struct Wg2Params {
+  int N, D, H, W;
+  int tilesW, tilesH;
+  int kd, kh, kw;
+  int cout, cin;
+  int co_tiles, ci_tiles, ci_n;
+  int nb;            // 64-channel X boxes per stage
+  int splits, stages, tmem_cols;
+  int plane_bytes, plane_stride, stage_bytes;  // plane_stride: plane_bytes rounded up to 1024
+  int co_pad, ci_pad;
+  float* acc;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ Wg2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ uint64_t acc_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  int wi = blockIdx.x;
+  const int a = wi % p.kd;
+  wi /= p.kd;
+  const int ct = wi % p.ci_tiles;
+  wi /= p.ci_tiles;
+  const int mt = wi % p.co_tiles;
+  const int split = wi / p.co_tiles;
+
+  const int khw = p.kh * p.kw;
+  const int PWc = 8 + p.kw - 1;
+  const int chunks = p.N * p.D * p.tilesH * p.tilesW;
+  const int per = (chunks + p.splits - 1) / p.splits;
+  const int c_begin = split * per;
+  const int c_end = min(chunks, c_begin + per);
+  const int co0 = mt * 128;
+  const int ci0 = ct * p.ci_n;
+  const int na = min(2, (p.cout - co0 + 63) / 64);
+  const int nbv = min(p.nb, (p.cin - ci0 + 63) / 64);   // X boxes that contain valid channels
+  const bool has_work = c_begin < c_end;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        int t = c;
+        const int w0 = (t % p.tilesW) * 8;
+        t /= p.tilesW;
+        const int h0 = (t % p.tilesH) * 16;
+        t /= p.tilesH;
+        const int d = t % p.D;
+        const int n = t / p.D;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + static_cast<size_t>(s) * p.stage_bytes;
+        uint8_t* sb = sa + 2 * kWgBoxBytes;
+        mbar_expect_tx(&full_bar[s], na * kWgBoxBytes + nbv * p.plane_bytes);
+        for (int i = 0; i < na; ++i)
+          tma_load_5d(&tmDY, &full_bar[s], sa + i * kWgBoxBytes, co0 + i * 64, w0, h0, d, n);
+        for (int i = 0; i < nbv; ++i)
+          tma_load_5d(&tmX, &full_bar[s], sb + static_cast<size_t>(i) * p.plane_stride, ci0 + i * 64,
+                      w0 - p.kw / 2, h0 - p.kh / 2, d + a - p.kd / 2, n);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
+      const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
+      const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * kWgBoxBytes, p.plane_stride, PWc * 128);
+      const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
+      const uint32_t stage16 = p.stage_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t alo = alo0 + static_cast<uint32_t>(s) * stage16;
+        const uint32_t blo = blo0 + static_cast<uint32_t>(s) * stage16;
+        const uint32_t accumulate = c > c_begin;
+        int tapidx = 0;
+        for (int b = 0; b < p.kh; ++b)
+          for (int cc = 0; cc < p.kw; ++cc, ++tapidx) {
+            const uint32_t tacc = tmem_base + tapidx * p.ci_n;
+            const uint32_t btap = blo + (b * PWc + cc) * 8;   // (b*PWc + cc) rows of 128 B, in 16-byte units
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // 8 x K16: dY advances 2 h-rows = 2048 B, X advances 2*PWc rows
+              umma_bf16(tacc, desc_join(alo + 128 * k, ahi), desc_join(btap + 16 * PWc * k, bhi), idesc,
+                        accumulate | (k != 0));
+          }
+        umma_commit(&empty_bar[s]);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int tapidx = 0; tapidx < khw; ++tapidx) {
+      const int tap = a * khw + tapidx;
+      for (int c = 0; c < p.ci_n; c += 16) {
+        float v[16];
+        tmem_ld16(tq + tapidx * p.ci_n + c, v);
+        if (co < p.cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci0 + c + i;
+            if (ci < p.cin) atomicAdd(p.acc + (static_cast<size_t>(tap) * p.ci_pad + ci) * p.co_pad + co, v[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -852,6 +1010,16 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   return 0;
 }
 
+// VFD_CONV_WGRAD2=0 disables the multi-tap halo wgrad kernel (debug / A-B timing)
+static bool wgrad2_enabled() {
+  static int mode = -1;
+  if (mode == -1) {
+    const char* e = getenv("VFD_CONV_WGRAD2");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 // VFD_CONV_RES=0 disables the resident-weight kernel (debug / A-B timing)
 static bool res_enabled() {
   static int mode = -1;
@@ -933,6 +1101,57 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
   if (co_pad < cout || ci_pad < cin) return set_error(VFD_ERR_ARG, "conv3d_wgrad: bad acc padding");
+  if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
+    return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
+  {
+    const int tilesW = (W + 7) / 8, tilesH = (H + 15) / 16;
+    const double fill = (double)W * H / ((double)tilesW * 8 * tilesH * 16);
+    if (wgrad2_enabled() && fill >= 0.7) {
+      Wg2Params q;
+      q.N = N; q.D = D; q.H = H; q.W = W; q.tilesW = tilesW; q.tilesH = tilesH;
+      q.kd = kd; q.kh = kh; q.kw = kw; q.cout = cout; q.cin = cin;
+      const int khw = kh * kw;
+      const int cin16 = (cin + 15) & ~15;
+      int max_n = (512 / khw) & ~15;            // TMEM: khw accumulators of ci_n columns
+      if (max_n > 256) max_n = 256;
+      q.ci_tiles = (cin16 + max_n - 1) / max_n;
+      q.ci_n = (((cin16 + q.ci_tiles - 1) / q.ci_tiles) + 15) & ~15;
+      q.co_tiles = (cout + 127) / 128;
+      q.nb = (q.ci_n + 63) / 64;
+      q.plane_bytes = (16 + kh - 1) * (8 + kw - 1) * 128;
+      q.plane_stride = (q.plane_bytes + 1023) & ~1023;
+      q.stage_bytes = 2 * kWgBoxBytes + q.nb * q.plane_stride;
+      int stages = kSmemBudget / q.stage_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      q.tmem_cols = 32;
+      while (q.tmem_cols < khw * q.ci_n) q.tmem_cols *= 2;
+      if (stages >= 2 && q.tmem_cols <= 512) {
+        q.stages = stages;
+        const long long chunks = (long long)N * D * tilesH * tilesW;
+        const long long base = (long long)kd * q.co_tiles * q.ci_tiles;
+        long long splits = (2LL * num_sms() + base - 1) / base;
+        if (splits > chunks) splits = chunks;
+        if (splits < 1) splits = 1;
+        q.splits = (int)splits;
+        q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc;
+        const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
+        CUtensorMap tmDY, tmX;
+        if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
+        if (int e = make_act_map(&tmX, x, x_ld, x_ch, N, D, H, W, 64, 8 + kw - 1, 16 + kh - 1, 1, 1)) return e;
+        static bool attr2 = false;
+        if (!attr2) {
+          cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               224 * 1024);
+          if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad2)");
+          attr2 = true;
+        }
+        size_t smem = (size_t)stages * q.stage_bytes + 1024;
+        if (q.tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM when it owns > half the TMEM
+        conv_wgrad2_kernel<<<(unsigned)(base * q.splits), kWgThreads, smem, stream>>>(tmDY, tmX, q);
+        return check_launch("conv_wgrad2");
+      }
+    }
+  }
   WgradParams p;
   if (int e = fill_geom(p.g, N, D, H, W, kd, kh, kw)) return e;
   p.cout = cout;

@@ -209,6 +209,19 @@ __device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
 __device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
 
+// MN-major, 128B swizzle, explicit stride between 8-K-row groups (row-shifted windows into a halo
+// plane whose 8-voxel runs are sbo_bytes apart).
+__device__ __forceinline__ uint64_t sdesc_mnmajor128_ex(uint32_t saddr, uint32_t lbo_bytes,
+                                                        uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M=128.
 __device__ __host__ __forceinline__ uint32_t idesc_bf16_m128(uint32_t n, bool a_mn, bool b_mn) {
   uint32_t d = 0;
