@@ -27,6 +27,10 @@
 
 VFD_API const char* vfd_last_error(void);
 VFD_API int vfd_abi_version(void);
+/* Diagnostics only (stage-isolation timing of the conv pipelines, tools/gpu_stage_probe.py): bit 0 skips
+ * the TMA loads, bit 1 the tcgen05.mma issue, bit 2 the epilogue arithmetic/stores. Results are garbage
+ * while any bit is set; 0 (the default) is the product path. */
+VFD_API int vfd_set_debug(int flags);
 
 /* ---- conv3d, stride 1, "same" zero padding, kernel extents in {1,3} ------------------------------
  * Replaces nn.Conv3d forward at models/spatiotempconv.py:49-50,59-60,63-64, conv_last at

@@ -237,11 +237,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
       const uint64_t d0 = sdesc_kmajor(smem_u32(smem), kRowBytes);  // A and B tiles share the layout
       const uint32_t dlo0 = desc_lo(d0), dhi = desc_hi(d0);
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -253,18 +255,20 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t alo = dlo0 + ((static_cast<uint32_t>(s) * stage_bytes) >> 4);
+          const uint32_t alo = dlo0 + static_cast<uint32_t>(s) * stage16;
           const uint32_t blo = alo + (kABytes >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            umma_bf16(tacc, desc_join(alo + 2 * k, dhi), desc_join(blo + 2 * k, dhi), idesc, (ks | k) != 0);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16(tacc, desc_join(alo + 2 * k, dhi), desc_join(blo + 2 * k, dhi), idesc, (ks | k) != 0);
+            umma_commit(&empty_bar[s]);
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&acc_full[as]);
+        if (leader) umma_commit(&acc_full[as]);
         if (++as == 2) {
           as = 0;
           aph ^= 1;
@@ -320,34 +324,59 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // Persistent forward/dgrad kernel for layers whose whole packed weight matrix fits in shared memory
 // (every "small-N" layer of the GAN: first/last convs, uconv1, temporal and 1x1x1 convs ...):
 //   * the weights are loaded ONCE per CTA and stay resident, so per tile only the input moves;
-//   * the input arrives as halo planes ((16+kh-1) x (8+kw-1) voxels per channel block and d-plane)
-//     through a ring of TMA slots; the kh*kw taps of a plane are row-shifted UMMA descriptors into
-//     the same slot (UMMA applies the swizzle to absolute smem address bits, so a descriptor may
-//     start at any row of the swizzle pattern; verified on B200);
-//   * up to four TMEM accumulator stages decouple the MMA issuer from the epilogue warps;
-//   * the epilogue optionally accumulates the per-channel sum / sum of squares of the bf16-rounded
-//     output for the BatchNorm that follows (saves one full read of the tensor).
-struct ResParams {
+//   * a tile is G consecutive d-planes of one 8 x 16 voxel window (G x 128 GEMM rows, G in {1,2,4}). The
+//     input arrives as ONE TMA box per channel block: (G + kd - 1) halo planes of (16+kh-1) x (8+kw-1)
+//     voxels. Every (sub-tile, tap) pair is a row-shifted UMMA descriptor into that box (UMMA applies the
+//     swizzle to absolute smem address bits, so a descriptor may start at any row of the pattern), which
+//     amortises the mbarrier / tcgen05.commit hand-shakes over G sub-tiles and re-uses the temporal halo;
+//   * the MMA warp runs warp-uniformly over a host-built table of descriptor offsets held in the kernel
+//     parameters (constant bank -> uniform registers), one elected lane issuing tcgen05.mma back to back;
+//   * eight epilogue warps (two per TMEM lane quarter, alternating sub-tiles) drain the accumulators:
+//     TMEM -> registers -> (bias) -> swizzled smem staging -> TMA store, which writes whole 64/128-byte
+//     rows and clips partial tiles. For a following BatchNorm they also accumulate the per-channel sum
+//     / sum of squares of the stored bf16 values: lane j sums column j of the staged 32 x 32 chunk into
+//     registers that live for the whole kernel, so the tensor is not read again for the statistics.
+constexpr int kRes2Threads = 320;   // warp0: TMA producer, warp1: MMA issuer, warps2-9: epilogue
+constexpr int kMaxTab = 108;        // G (<= 4) x taps (<= 27)
+constexpr int kResMaxASlots = 8;
+constexpr int kStageBytes = 4096;   // one epilogue staging buffer: 32 rows x 128 B (bf16 rows use 64 B)
+constexpr int kMaxChunks = 8;       // block_n <= 256
+
+struct Res2Params {
   int N, D, H, W;
-  int tilesW, tilesH;
+  int tilesW, tilesH, dgroups, G;
   int kd, kh, kw;
   int cblocks, block_n;
-  int a_slots, a_slot_bytes, b_tile_bytes;
-  int acc_stages, acc_stride;
-  Epilogue epi;
+  int a_slots, a_slot_bytes, a_box_bytes, b_tile_bytes;
+  int acc_stages, acc_stride;  // TMEM columns per sub-tile accumulator; one stage = G * acc_stride columns
+  int n_tab;                   // G * taps table entries
+  int nchunks;                 // 32-column output chunks
+  int stage_bufs;              // staging buffers per epilogue warp (1 or 2)
+  int out_fp32;
+  int n_rows;                  // valid bias entries
+  int dbg;
+  const float* bias;
+  double* stats;
+  int stats_ld;
+  uint32_t a_off[kMaxTab];     // 16-byte units, relative to the slot base
+  uint32_t b_off[kMaxTab];     // 16-byte units, relative to the weight tile of channel block 0 of tap 0
+  uint32_t meta[kMaxTab];      // bits 0-15: accumulator column within the stage, bit 16: first tap
 };
 
-constexpr int kResMaxASlots = 16;
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 template <int KC>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kRes2Threads, 1)
 conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ ResParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Res2Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[kResMaxASlots], a_empty[kResMaxASlots];
   __shared__ uint64_t b_full, acc_full[4], acc_empty[4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_sum[256], s_sq[256];  // block_n <= 256 and a single N tile in this kernel
+  __shared__ float s_sum[256], s_sq[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -356,10 +385,10 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int kRowBytes = KC * 2;
   const int ntaps = p.kd * p.kh * p.kw;
   const int nbt = ntaps * p.cblocks;  // resident weight tiles
-  uint8_t* smem_a = smem + static_cast<size_t>(nbt) * p.b_tile_bytes;
-  const int PWc = 8 + p.kw - 1, PHc = 16 + p.kh - 1;
-  const int a_bytes = PWc * PHc * kRowBytes;
-  const int total_tiles = p.N * p.D * p.tilesH * p.tilesW;
+  uint8_t* smem_stage = smem + static_cast<size_t>(nbt) * p.b_tile_bytes;
+  uint8_t* smem_a = smem_stage + 8 * p.stage_bufs * kStageBytes;
+  const int total_tiles = p.N * p.dgroups * p.tilesH * p.tilesW;
+  const int stage_cols = p.G * p.acc_stride;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_slots; ++s) {
@@ -369,15 +398,16 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(&b_full, 1);
     for (int s = 0; s < p.acc_stages; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], p.G == 1 ? 4 : 8);
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 256; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.f;
+  for (int i = threadIdx.x; i < 256; i += kRes2Threads) s_sum[i] = s_sq[i] = 0.f;
   if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   tc_fence_before();
   __syncthreads();
@@ -385,8 +415,8 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
+    // ------------------------------------------------ TMA producer
     if (lane == 0) {
-      // resident weights: one barrier, all tiles
       mbar_expect_tx(&b_full, nbt * p.block_n * kRowBytes);
       for (int t = 0; t < nbt; ++t)
         tma_load_2d(&tmB, &b_full, smem + static_cast<size_t>(t) * p.b_tile_bytes, t * KC, 0);
@@ -398,102 +428,202 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         t /= p.tilesW;
         const int h0 = (t % p.tilesH) * 16;
         t /= p.tilesH;
-        const int d = t % p.D;
-        const int n = t / p.D;
-        for (int cb = 0; cb < p.cblocks; ++cb)
-          for (int a = 0; a < p.kd; ++a) {
-            mbar_wait(&a_empty[sa], pha ^ 1);
-            mbar_expect_tx(&a_full[sa], a_bytes);
+        const int d0 = (t % p.dgroups) * p.G;
+        const int n = t / p.dgroups;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(&a_empty[sa], pha ^ 1);
+          if (p.dbg & 1) {
+            mbar_arrive(&a_full[sa]);
+          } else {
+            mbar_expect_tx(&a_full[sa], p.a_box_bytes);
             tma_load_5d(&tmA, &a_full[sa], smem_a + static_cast<size_t>(sa) * p.a_slot_bytes, cb * KC,
-                        w0 - p.kw / 2, h0 - p.kh / 2, d + a - p.kd / 2, n);
-            if (++sa == p.a_slots) {
-              sa = 0;
-              pha ^= 1;
-            }
+                        w0 - p.kw / 2, h0 - p.kh / 2, d0 - p.kd / 2, n);
           }
+          if (++sa == p.a_slots) {
+            sa = 0;
+            pha ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
-      const uint64_t da0 = sdesc_kmajor_ex(smem_u32(smem_a), kRowBytes, PWc * kRowBytes, 0);
-      const uint64_t db0 = sdesc_kmajor(smem_u32(smem), kRowBytes);
-      const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
-      const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_tile16 = p.b_tile_bytes >> 4;
-      const uint32_t row16 = kRowBytes >> 4;
-      const int khw = p.kh * p.kw;
-      int sa = 0, as = 0;
-      uint32_t pha = 0, aph = 0;
-      mbar_wait(&b_full, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[as], aph ^ 1);
+    // ------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
+    const int PWc = 8 + p.kw - 1;
+    const uint64_t da0 = sdesc_kmajor_ex(smem_u32(smem_a), kRowBytes, PWc * kRowBytes, 0);
+    const uint64_t db0 = sdesc_kmajor(smem_u32(smem), kRowBytes);
+    const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
+    const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_tile16 = p.b_tile_bytes >> 4;
+    const bool issue = leader && !(p.dbg & 2);
+    int sa = 0, as = 0;
+    uint32_t pha = 0, aph = 0;
+    mbar_wait(&b_full, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * stage_cols;
+      for (int cb = 0; cb < p.cblocks; ++cb) {
+        mbar_wait(&a_full[sa], pha);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * p.acc_stride;
-        uint32_t accumulate = 0;
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          uint32_t blo_plane = blo0 + static_cast<uint32_t>(cb) * b_tile16;  // tap 0 of this channel block
-          for (int a = 0; a < p.kd; ++a) {
-            mbar_wait(&a_full[sa], pha);
-            tc_fence_after();
-            const uint32_t alo = alo0 + static_cast<uint32_t>(sa) * a_slot16;
-            uint32_t blo = blo_plane;
-            uint32_t arow = alo;
-            for (int b = 0; b < p.kh; ++b) {
-              uint32_t at = arow;
-              for (int c = 0; c < p.kw; ++c) {
+        const uint32_t abase = alo0 + static_cast<uint32_t>(sa) * a_slot16;
+        const uint32_t bbase = blo0 + static_cast<uint32_t>(cb) * b_tile16;
+        const uint32_t later = cb != 0;
+#pragma unroll 2
+        for (int j = 0; j < p.n_tab; ++j) {
+          const uint32_t m = p.meta[j];
+          const uint32_t d = tacc + (m & 0xFFFFu);
+          const uint32_t a = abase + p.a_off[j];
+          const uint32_t b = bbase + p.b_off[j];
+          const uint32_t acc0 = later | ((m >> 16) ^ 1u);
+          if (issue) {
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16(tacc, desc_join(at + 2 * k, ahi), desc_join(blo + 2 * k, bhi), idesc, accumulate);
-                  accumulate = 1;
-                }
-                at += row16;                           // next tap in w: one halo row further
-                blo += p.cblocks * b_tile16;           // next tap's weight tile for this channel block
-              }
-              arow += PWc * row16;                     // next tap row in h
-            }
-            blo_plane += static_cast<uint32_t>(khw) * p.cblocks * b_tile16;
-            umma_commit(&a_empty[sa]);
-            if (++sa == p.a_slots) {
-              sa = 0;
-              pha ^= 1;
-            }
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16(d, desc_join(a + 2 * k, ahi), desc_join(b + 2 * k, bhi), idesc, k == 0 ? acc0 : 1u);
           }
         }
-        umma_commit(&acc_full[as]);
-        if (++as == p.acc_stages) {
-          as = 0;
-          aph ^= 1;
+        if (leader) umma_commit(&a_empty[sa]);
+        if (++sa == p.a_slots) {
+          sa = 0;
+          pha ^= 1;
         }
       }
-    }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    int as = 0;
-    uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int w = (t % p.tilesW) * 8 + (row & 7);
-      t /= p.tilesW;
-      const int h = (t % p.tilesH) * 16 + (row >> 3);
-      t /= p.tilesH;
-      const int d = t % p.D;
-      const int n = t / p.D;
-      const bool valid = (w < p.W) && (h < p.H);
-      const long long vox = ((static_cast<long long>(n) * p.D + d) * p.H + h) * p.W + w;
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile(p.epi, tacc, p.block_n, 0, valid, vox, lane, s_sum, s_sq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (leader) umma_commit(&acc_full[as]);
       if (++as == p.acc_stages) {
         as = 0;
         aph ^= 1;
       }
     }
-    epilogue_flush_stats(p.epi, (warp - 2) * 32 + lane, s_sum, s_sq);
+  } else {
+    // ------------------------------------------------ epilogue (8 warps: group e, TMEM lane quarter q)
+    const int ew = warp - 2;
+    const int e = ew >> 2;
+    const int q = warp & 3;
+    uint8_t* stg = smem_stage + static_cast<size_t>(ew) * p.stage_bufs * kStageBytes;
+    const bool do_stats = p.stats != nullptr;
+    float ssum[kMaxChunks], ssq[kMaxChunks];
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) ssum[i] = ssq[i] = 0.f;
+    // column-read offsets for the statistics (64-byte swizzle: chunk index ^ ((row >> 1) & 3))
+    uint32_t coff[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) coff[x] = ((((lane >> 3) ^ x) << 4) + ((lane & 7) << 1));
+    int as = 0, buf = 0;
+    uint32_t aph = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      int t = tile;
+      const int w0 = (t % p.tilesW) * 8;
+      t /= p.tilesW;
+      const int h0 = (t % p.tilesH) * 16;
+      t /= p.tilesH;
+      const int d0 = (t % p.dgroups) * p.G;
+      const int n = t / p.dgroups;
+      const bool mine = p.G > 1 || ((iter & 1) == e);
+      if (mine) {
+        mbar_wait(&acc_full[as], aph);
+        tc_fence_after();
+        const bool hw_ok = (w0 + (lane & 7) < p.W) && (h0 + 4 * q + (lane >> 3) < p.H);
+        for (int g = (p.G > 1 ? e : 0); g < p.G; g += 2) {
+          const int d = d0 + g;
+          if (d >= p.D || (p.dbg & 4)) continue;
+          const unsigned vmask = __ballot_sync(0xffffffffu, hw_ok);
+          const uint32_t tacc = tmem_base + as * stage_cols + g * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+          for (int ch = 0; ch < p.nchunks; ++ch) {
+            float v[32];
+            if (ch * 32 + 32 <= p.block_n) {
+              tmem_ld32(tacc + ch * 32, v);
+            } else {
+              tmem_ld16(tacc + ch * 32, v);
+#pragma unroll
+              for (int i = 16; i < 32; ++i) v[i] = 0.f;
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (ch * 32 + i < p.n_rows) v[i] += __ldg(p.bias + ch * 32 + i);
+            }
+            // the staging buffer may still be the source of an earlier TMA store
+            if (lane == 0) {
+              if (p.stage_bufs == 2) bulk_wait_group_read<1>();
+              else bulk_wait_group_read<0>();
+            }
+            __syncwarp();
+            uint8_t* sb = stg + buf * kStageBytes;
+            if (p.out_fp32) {
+              uint8_t* rowp = sb + lane * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(rowp + ((c ^ (lane & 7)) << 4)) =
+                    make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            } else {
+              uint8_t* rowp = sb + lane * 64;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+                pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+                pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+                *reinterpret_cast<uint4*>(rowp + ((c ^ ((lane >> 1) & 3)) << 4)) = pk;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_5d(&tmC, sb, ch * 32, w0, h0 + 4 * q, d, n);
+              bulk_commit_group();
+            }
+            if (do_stats) {
+              // lane j sums column j of the staged chunk over the warp's valid rows
+              float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+              const uint8_t* colp = sb;
+#pragma unroll
+              for (int r = 0; r < 32; r += 2) {
+                const uint32_t u0 = *reinterpret_cast<const uint16_t*>(colp + r * 64 + coff[(r >> 1) & 3]);
+                const uint32_t u1 = *reinterpret_cast<const uint16_t*>(colp + (r + 1) * 64 + coff[(r >> 1) & 3]);
+                const float f0 = ((vmask >> r) & 1u) ? __uint_as_float(u0 << 16) : 0.f;
+                const float f1 = ((vmask >> (r + 1)) & 1u) ? __uint_as_float(u1 << 16) : 0.f;
+                a0 += f0;
+                a1 += f1;
+                q0 = fmaf(f0, f0, q0);
+                q1 = fmaf(f1, f1, q1);
+              }
+#pragma unroll
+              for (int i = 0; i < kMaxChunks; ++i)
+                if (i == ch) {
+                  ssum[i] += a0 + a1;
+                  ssq[i] += q0 + q1;
+                }
+            }
+            if (p.stage_bufs == 2) buf ^= 1;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+      }
+      if (++as == p.acc_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+    if (do_stats) {
+#pragma unroll
+      for (int i = 0; i < kMaxChunks; ++i)
+        if (i < p.nchunks) {
+          atomicAdd(&s_sum[i * 32 + lane], ssum[i]);
+          atomicAdd(&s_sq[i * 32 + lane], ssq[i]);
+        }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+      const int j = ew * 32 + lane;
+      if (j < p.stats_ld && j < p.nchunks * 32 && (s_sum[j] != 0.f || s_sq[j] != 0.f)) {
+        atomicAdd(p.stats + j, (double)s_sum[j]);
+        atomicAdd(p.stats + p.stats_ld + j, (double)s_sq[j]);
+      }
+    }
   }
 
   tc_fence_before();
@@ -599,28 +729,33 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    {  // not guarded by has_work: an empty range simply runs no iterations, and the guard would make
+       // ptxas treat the loop as divergent (no uniform-datapath MMA issue)
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.block_n, true, true);
       const uint64_t d0 = sdesc_mnmajor128(smem_u32(smem), kWgBoxBytes);
       const uint32_t dlo0 = desc_lo(d0), dhi = desc_hi(d0);
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t alo = dlo0 + ((static_cast<uint32_t>(s) * stage_bytes) >> 4);
+        const uint32_t alo = dlo0 + static_cast<uint32_t>(s) * stage16;
         const uint32_t blo = alo + ((2 * kWgBoxBytes) >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // 128 voxels per chunk = 8 x K16; 16 rows = 2048 B = 128 x 16 B
-          umma_bf16(tmem_base, desc_join(alo + 128 * k, dhi), desc_join(blo + 128 * k, dhi), idesc,
-                    (c > c_begin) || (k != 0));
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < 8; ++k)  // 128 voxels per chunk = 8 x K16; 16 rows = 2048 B = 128 x 16 B
+            umma_bf16(tmem_base, desc_join(alo + 128 * k, dhi), desc_join(blo + 128 * k, dhi), idesc,
+                      (c > c_begin) || (k != 0));
+          umma_commit(&empty_bar[s]);
+        }
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
         }
       }
-      umma_commit(&acc_full);
+      if (leader) umma_commit(&acc_full);
     }
   } else if (has_work) {
     const int q = warp & 3;
@@ -666,7 +801,12 @@ struct Wg2Params {
   int splits, stages, tmem_cols;
   int plane_bytes, plane_stride, stage_bytes;  // plane_stride: plane_bytes rounded up to 1024
   int co_pad, ci_pad;
+  int dbg;
   float* acc;
+  int n_tab;                 // kh*kw taps x 8 K16-steps
+  uint32_t t_a[72];          // dY descriptor offset (16-byte units)
+  uint32_t t_b[72];          // X halo-plane descriptor offset
+  uint32_t t_meta[72];       // bits 0-15: accumulator column, bit 16: accumulate within the chunk
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -734,12 +874,16 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + static_cast<size_t>(s) * p.stage_bytes;
         uint8_t* sb = sa + 2 * kWgBoxBytes;
-        mbar_expect_tx(&full_bar[s], na * kWgBoxBytes + nbv * p.plane_bytes);
-        for (int i = 0; i < na; ++i)
-          tma_load_5d(&tmDY, &full_bar[s], sa + i * kWgBoxBytes, co0 + i * 64, w0, h0, d, n);
-        for (int i = 0; i < nbv; ++i)
-          tma_load_5d(&tmX, &full_bar[s], sb + static_cast<size_t>(i) * p.plane_stride, ci0 + i * 64,
-                      w0 - p.kw / 2, h0 - p.kh / 2, d + a - p.kd / 2, n);
+        if (p.dbg & 1) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_expect_tx(&full_bar[s], na * kWgBoxBytes + nbv * p.plane_bytes);
+          for (int i = 0; i < na; ++i)
+            tma_load_5d(&tmDY, &full_bar[s], sa + i * kWgBoxBytes, co0 + i * 64, w0, h0, d, n);
+          for (int i = 0; i < nbv; ++i)
+            tma_load_5d(&tmX, &full_bar[s], sb + static_cast<size_t>(i) * p.plane_stride, ci0 + i * 64,
+                        w0 - p.kw / 2, h0 - p.kh / 2, d + a - p.kd / 2, n);
+        }
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
@@ -747,7 +891,11 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    {  // not guarded by has_work: an empty range simply runs no iterations, and the guard would make
+       // ptxas treat the loop as divergent (no uniform-datapath MMA issue)
+      // warp-uniform loop over the host-built (tap, K16-step) table; one elected lane issues
+      const bool leader = elect_one();
+      const bool issue = leader && !(p.dbg & 2);
       const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
       const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
       const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * kWgBoxBytes, p.plane_stride, PWc * 128);
@@ -761,23 +909,22 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         const uint32_t alo = alo0 + static_cast<uint32_t>(s) * stage16;
         const uint32_t blo = blo0 + static_cast<uint32_t>(s) * stage16;
         const uint32_t accumulate = c > c_begin;
-        int tapidx = 0;
-        for (int b = 0; b < p.kh; ++b)
-          for (int cc = 0; cc < p.kw; ++cc, ++tapidx) {
-            const uint32_t tacc = tmem_base + tapidx * p.ci_n;
-            const uint32_t btap = blo + (b * PWc + cc) * 8;   // (b*PWc + cc) rows of 128 B, in 16-byte units
-#pragma unroll
-            for (int k = 0; k < 8; ++k)  // 8 x K16: dY advances 2 h-rows = 2048 B, X advances 2*PWc rows
-              umma_bf16(tacc, desc_join(alo + 128 * k, ahi), desc_join(btap + 16 * PWc * k, bhi), idesc,
-                        accumulate | (k != 0));
-          }
-        umma_commit(&empty_bar[s]);
+#pragma unroll 4
+        for (int j = 0; j < p.n_tab; ++j) {
+          const uint32_t m = p.t_meta[j];
+          const uint32_t d = tmem_base + (m & 0xFFFFu);
+          const uint64_t da = desc_join(alo + p.t_a[j], ahi);
+          const uint64_t db = desc_join(blo + p.t_b[j], bhi);
+          const uint32_t acc = accumulate | (m >> 16);
+          if (issue) umma_bf16(d, da, db, idesc, acc);
+        }
+        if (leader) umma_commit(&empty_bar[s]);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
         }
       }
-      umma_commit(&acc_full);
+      if (leader) umma_commit(&acc_full);
     }
   } else if (has_work) {
     const int q = warp & 3;
@@ -785,7 +932,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int tapidx = 0; tapidx < khw; ++tapidx) {
+    for (int tapidx = 0; tapidx < ((p.dbg & 4) ? 0 : khw); ++tapidx) {
       const int tap = a * khw + tapidx;
       for (int c = 0; c < p.ci_n; c += 16) {
         float v[16];
@@ -966,46 +1113,120 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   return check_launch("conv_fwd_tc");
 }
 
-constexpr int kResBudget = 221 * 1024;
+constexpr int kResBudget = 223 * 1024;
 
-// Resident-weight kernel: returns 1 when the geometry does not qualify (caller falls back), 0 on
-// success, negative... error codes otherwise are returned through *err.
+// 5-D map over the conv output for the epilogue's TMA stores: box = 32 channels x 8 (w) x 4 (h) voxels,
+// i.e. the 32 accumulator rows one epilogue warp owns.
+static int make_out_map(CUtensorMap* tm, const void* ptr, long long ld, int cols, int fp32, int N, int D, int H,
+                        int W) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(VFD_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t es = fp32 ? 4 : 2;
+  cuuint64_t dims[5] = {(cuuint64_t)cols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * W, (cuuint64_t)ld * es * W * H,
+                           (cuuint64_t)ld * es * W * H * D};
+  cuuint32_t box[5] = {32, 8, 4, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(output) failed (%d): ptr %p ld %lld cols %d fp32 %d", (int)r,
+             ptr, ld, cols, fp32);
+    return set_error(VFD_ERR_DRIVER, msg);
+  }
+  return 0;
+}
+
+static int g_dbg = 0;
+
+// Resident-weight kernel: returns 1 when the geometry does not qualify (caller falls back), 0 when it
+// launched or failed (status in *err).
 template <int KC>
 static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_packed, int w_rows, int cin_k,
-                          ResParams& p, cudaStream_t stream, int* err) {
+                          const Epilogue& epi, int N, int D, int H, int W, int kd, int kh, int kw,
+                          cudaStream_t stream, int* err) {
   *err = 0;
-  const int PWc = 8 + p.kw - 1, PHc = 16 + p.kh - 1;
-  const int ntaps = p.kd * p.kh * p.kw;
+  Res2Params p;
+  const int PWc = 8 + kw - 1, PHc = 16 + kh - 1;
+  const int ntaps = kd * kh * kw;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.tilesW = (W + 7) / 8;
+  p.tilesH = (H + 15) / 16;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  p.cblocks = cin_k / KC;
+  p.block_n = w_rows;
   p.b_tile_bytes = (p.block_n * KC * 2 + 1023) & ~1023;
-  p.a_slot_bytes = (PWc * PHc * KC * 2 + 1023) & ~1023;
   const long long b_total = (long long)ntaps * p.cblocks * p.b_tile_bytes;
-  if (b_total + 3LL * p.a_slot_bytes > kResBudget) return 1;
   if ((long long)ntaps * p.cblocks * p.block_n * KC * 2 >= (1 << 20)) return 1;  // mbarrier tx-count limit
-  int slots = (int)((kResBudget - b_total) / p.a_slot_bytes);
-  if (slots > kResMaxASlots) slots = kResMaxASlots;
-  p.a_slots = slots;
-  p.acc_stride = 32;
-  while (p.acc_stride < p.block_n) p.acc_stride *= 2;
-  p.acc_stages = 512 / p.acc_stride;
+  p.acc_stride = (p.block_n + 31) & ~31;
+  const int mmas_per_sub = ntaps * p.cblocks * (KC / 16);
+  int g0 = (kd == 3 || mmas_per_sub < 24) ? 4 : 1;
+  while (g0 > D) g0 >>= 1;
+  // pick (G, staging buffers): first choice with >= 3 input slots, else the first with >= 2
+  int bestG = 0, bestBufs = 0, bestSlots = 0;
+  for (int pass = 0; pass < 2 && !bestG; ++pass)
+    for (int G = g0; G >= 1 && !bestG; G >>= 1)
+      for (int bufs = 2; bufs >= 1 && !bestG; --bufs) {
+        if (G * p.acc_stride * 2 > 512) continue;
+        const long long box = (long long)(G + kd - 1) * PWc * PHc * KC * 2;
+        const long long slot = (box + 1023) & ~1023LL;
+        const long long avail = (long long)kResBudget - b_total - 8LL * bufs * kStageBytes;
+        if (avail <= 0 || box >= (1 << 20)) continue;
+        const int slots = (int)(avail / slot);
+        if (slots >= (pass == 0 ? 3 : 2)) {
+          bestG = G; bestBufs = bufs; bestSlots = slots;
+        }
+      }
+  if (!bestG) return 1;
+  p.G = bestG;
+  p.stage_bufs = bestBufs;
+  p.a_slots = bestSlots > kResMaxASlots ? kResMaxASlots : bestSlots;
+  p.a_box_bytes = (p.G + kd - 1) * PWc * PHc * KC * 2;
+  p.a_slot_bytes = (p.a_box_bytes + 1023) & ~1023;
+  p.dgroups = (D + p.G - 1) / p.G;
+  p.acc_stages = 512 / (p.G * p.acc_stride);
   if (p.acc_stages > 4) p.acc_stages = 4;
-  CUtensorMap tmA, tmB;
-  if ((*err = make_act_map(&tmA, x, x_ld, cin, p.N, p.D, p.H, p.W, KC, PWc, PHc, 1, 1))) return 0;
+  p.n_tab = p.G * ntaps;
+  p.nchunks = (p.block_n + 31) / 32;
+  p.out_fp32 = epi.out_fp32;
+  p.n_rows = epi.n_rows;
+  p.dbg = g_dbg;
+  p.bias = epi.bias;
+  p.stats = epi.stats;
+  p.stats_ld = epi.stats_ld;
+  const uint32_t row16 = KC * 2 / 16, b_tile16 = p.b_tile_bytes >> 4;
+  int j = 0;
+  for (int g = 0; g < p.G; ++g)
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < kh; ++b)
+        for (int c = 0; c < kw; ++c, ++j) {
+          const int tap = (a * kh + b) * kw + c;
+          p.a_off[j] = (uint32_t)(((g + a) * PHc * PWc + b * PWc + c) * row16);
+          p.b_off[j] = (uint32_t)tap * p.cblocks * b_tile16;
+          p.meta[j] = (uint32_t)(g * p.acc_stride) | (tap == 0 ? 1u << 16 : 0u);
+        }
+  CUtensorMap tmA, tmB, tmC;
+  if ((*err = make_act_map(&tmA, x, x_ld, cin, N, D, H, W, KC, PWc, PHc, p.G + kd - 1, 1))) return 0;
   if ((*err = make_weight_map(&tmB, w_packed, w_rows, (long long)ntaps * cin_k, KC, p.block_n))) return 0;
-  size_t smem = (size_t)b_total + (size_t)p.a_slots * p.a_slot_bytes + 1024;
-  if (smem < 120 * 1024) smem = 120 * 1024;
+  if ((*err = make_out_map(&tmC, epi.out, epi.out_ld, epi.out_cols, epi.out_fp32, N, D, H, W))) return 0;
+  size_t smem = (size_t)b_total + 8u * p.stage_bufs * kStageBytes + (size_t)p.a_slots * p.a_slot_bytes + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         223 * 1024);
+                                         224 * 1024);
     if (e != cudaSuccess) {
       *err = set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_res)");
       return 0;
     }
     attr_set = true;
   }
-  const long long tiles = (long long)p.N * p.D * p.tilesH * p.tilesW;
+  const long long tiles = (long long)N * p.dgroups * p.tilesH * p.tilesW;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_fwd_res_kernel<KC><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, p);
+  conv_fwd_res_kernel<KC><<<grid, kRes2Threads, smem, stream>>>(tmA, tmB, tmC, p);
   *err = check_launch("conv_fwd_res");
   return 0;
 }
@@ -1034,6 +1255,11 @@ static bool res_enabled() {
 
 using namespace vfd;
 
+VFD_API int vfd_set_debug(int flags) {
+  g_dbg = flags;
+  return 0;
+}
+
 VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w_packed,
                               int w_rows, int cin_k, const float* bias, void* out,
                               long long out_ld, int out_cols, int out_fp32, double* stats,
@@ -1061,21 +1287,13 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
   if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
     return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
   if (res_enabled() && w_rows <= 256 && (stats == nullptr || stats_ld <= 256)) {
-    ResParams rp;
-    rp.N = N; rp.D = D; rp.H = H; rp.W = W;
-    rp.tilesW = (W + 7) / 8;
-    rp.tilesH = (H + 15) / 16;
-    rp.kd = kd; rp.kh = kh; rp.kw = kw;
-    rp.cblocks = cin_k / kc;
-    rp.block_n = w_rows;
-    rp.epi = epi;
     // tiles are 8 x 16 voxels of one (n, d) plane: require a reasonable fill
-    const double fill = (double)W * H / ((double)rp.tilesW * 8 * rp.tilesH * 16);
+    const double fill = (double)W * H / ((double)((W + 7) / 8) * 8 * ((H + 15) / 16) * 16);
     if (fill >= 0.7) {
       int err = 0, fb;
-      if (kc == 64) fb = try_launch_res<64>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
-      else if (kc == 32) fb = try_launch_res<32>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
-      else fb = try_launch_res<16>(x, x_ld, cin, w_packed, w_rows, cin_k, rp, stream, &err);
+      if (kc == 64) fb = try_launch_res<64>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
+      else if (kc == 32) fb = try_launch_res<32>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
+      else fb = try_launch_res<16>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
       if (!fb) return err;
     }
   }
@@ -1133,7 +1351,19 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
         if (splits > chunks) splits = chunks;
         if (splits < 1) splits = 1;
         q.splits = (int)splits;
-        q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc;
+        q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+        {
+          const int PWc = 8 + kw - 1;
+          int j = 0;
+          for (int b = 0; b < kh; ++b)
+            for (int cc = 0; cc < kw; ++cc)
+              for (int k = 0; k < 8; ++k, ++j) {
+                q.t_a[j] = 128u * k;                                   // dY advances 2 h-rows = 2048 B per K16
+                q.t_b[j] = (uint32_t)((b * PWc + cc) * 8 + 16 * PWc * k);  // X: tap shift + 2*PWc rows per K16
+                q.t_meta[j] = (uint32_t)((b * kw + cc) * q.ci_n) | (k != 0 ? 1u << 16 : 0u);
+              }
+          q.n_tab = j;
+        }
         const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
         CUtensorMap tmDY, tmX;
         if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
