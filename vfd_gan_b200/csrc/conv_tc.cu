@@ -337,9 +337,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //     / sum of squares of the stored bf16 values: lane j sums column j of the staged 32 x 32 chunk into
 //     registers that live for the whole kernel, so the tensor is not read again for the statistics.
 constexpr int kRes2Threads = 320;   // warp0: TMA producer, warp1: MMA issuer, warps2-9: epilogue
-constexpr int kMaxTab = 108;        // G (<= 4) x taps (<= 27)
 constexpr int kResMaxASlots = 8;
-constexpr int kStageBytes = 4096;   // one epilogue staging buffer: 32 rows x 128 B (bf16 rows use 64 B)
 constexpr int kMaxChunks = 8;       // block_n <= 256
 
 struct Res2Params {
@@ -349,7 +347,6 @@ struct Res2Params {
   int cblocks, block_n;
   int a_slots, a_slot_bytes, a_box_bytes, b_tile_bytes;
   int acc_stages, acc_stride;  // TMEM columns per sub-tile accumulator; one stage = G * acc_stride columns
-  int n_tab;                   // G * taps table entries
   int nchunks;                 // 32-column output chunks
   int stage_bufs;              // staging buffers per epilogue warp (1 or 2)
   int out_fp32;
@@ -358,9 +355,7 @@ struct Res2Params {
   const float* bias;
   double* stats;
   int stats_ld;
-  uint32_t a_off[kMaxTab];     // 16-byte units, relative to the slot base
-  uint32_t b_off[kMaxTab];     // 16-byte units, relative to the weight tile of channel block 0 of tap 0
-  uint32_t meta[kMaxTab];      // bits 0-15: accumulator column within the stage, bit 16: first tap
+  int stage_bytes;             // bytes of one epilogue staging buffer (32 rows x 64 or 128 B)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -368,7 +363,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
-template <int KC>
+// KHW: spatial extent of the filter (kh == kw == KHW, 1 or 3); kd and G are run-time loops around the
+// fully unrolled (kh, kw, K16) issue sequence whose descriptor offsets are immediates.
+template <int KC, int KHW>
 __global__ void __launch_bounds__(kRes2Threads, 1)
 conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Res2Params p) {
@@ -386,7 +383,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int ntaps = p.kd * p.kh * p.kw;
   const int nbt = ntaps * p.cblocks;  // resident weight tiles
   uint8_t* smem_stage = smem + static_cast<size_t>(nbt) * p.b_tile_bytes;
-  uint8_t* smem_a = smem_stage + 8 * p.stage_bufs * kStageBytes;
+  uint8_t* smem_a = smem_stage + 8 * p.stage_bufs * p.stage_bytes;
   const int total_tiles = p.N * p.dgroups * p.tilesH * p.tilesW;
   const int stage_cols = p.G * p.acc_stride;
 
@@ -450,11 +447,14 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
     const bool leader = elect_one();
     const uint32_t idesc = idesc_bf16_m128(p.block_n, false, false);
-    const int PWc = 8 + p.kw - 1;
+    constexpr int PWc = 8 + KHW - 1, PHc = 16 + KHW - 1;
+    constexpr uint32_t row16 = kRowBytes >> 4;
+    constexpr uint32_t plane16 = PWc * PHc * row16;
     const uint64_t da0 = sdesc_kmajor_ex(smem_u32(smem_a), kRowBytes, PWc * kRowBytes, 0);
     const uint64_t db0 = sdesc_kmajor(smem_u32(smem), kRowBytes);
     const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
     const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_tile16 = p.b_tile_bytes >> 4;
+    const uint32_t tap16 = static_cast<uint32_t>(p.cblocks) * b_tile16;  // next tap's weight tile (same channel block)
     const bool issue = leader && !(p.dbg & 2);
     int sa = 0, as = 0;
     uint32_t pha = 0, aph = 0;
@@ -468,18 +468,24 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t abase = alo0 + static_cast<uint32_t>(sa) * a_slot16;
         const uint32_t bbase = blo0 + static_cast<uint32_t>(cb) * b_tile16;
-        const uint32_t later = cb != 0;
-#pragma unroll 2
-        for (int j = 0; j < p.n_tab; ++j) {
-          const uint32_t m = p.meta[j];
-          const uint32_t d = tacc + (m & 0xFFFFu);
-          const uint32_t a = abase + p.a_off[j];
-          const uint32_t b = bbase + p.b_off[j];
-          const uint32_t acc0 = later | ((m >> 16) ^ 1u);
-          if (issue) {
+        for (int g = 0; g < p.G; ++g) {
+          const uint32_t d = tacc + g * p.acc_stride;
+          uint32_t bt = bbase;
+          for (int a = 0; a < p.kd; ++a) {
+            const uint32_t ap = abase + static_cast<uint32_t>(g + a) * plane16;
+            const uint32_t first_acc = (cb | a) != 0;
+            if (issue) {
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              umma_bf16(d, desc_join(a + 2 * k, ahi), desc_join(b + 2 * k, bhi), idesc, k == 0 ? acc0 : 1u);
+              for (int b = 0; b < KHW; ++b)
+#pragma unroll
+                for (int c = 0; c < KHW; ++c)
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma_bf16(d, desc_join(ap + (b * PWc + c) * row16 + 2 * k, ahi),
+                              desc_join(bt + (b * KHW + c) * tap16 + 2 * k, bhi), idesc,
+                              (b | c | k) == 0 ? first_acc : 1u);
+            }
+            bt += KHW * KHW * tap16;
           }
         }
         if (leader) umma_commit(&a_empty[sa]);
@@ -499,7 +505,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int e = ew >> 2;
     const int q = warp & 3;
-    uint8_t* stg = smem_stage + static_cast<size_t>(ew) * p.stage_bufs * kStageBytes;
+    uint8_t* stg = smem_stage + static_cast<size_t>(ew) * p.stage_bufs * p.stage_bytes;
     const bool do_stats = p.stats != nullptr;
     float ssum[kMaxChunks], ssq[kMaxChunks];
 #pragma unroll
@@ -550,7 +556,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               else bulk_wait_group_read<0>();
             }
             __syncwarp();
-            uint8_t* sb = stg + buf * kStageBytes;
+            uint8_t* sb = stg + buf * p.stage_bytes;
             if (p.out_fp32) {
               uint8_t* rowp = sb + lane * 128;
 #pragma unroll
@@ -803,12 +809,9 @@ struct Wg2Params {
   int co_pad, ci_pad;
   int dbg;
   float* acc;
-  int n_tab;                 // kh*kw taps x 8 K16-steps
-  uint32_t t_a[72];          // dY descriptor offset (16-byte units)
-  uint32_t t_b[72];          // X halo-plane descriptor offset
-  uint32_t t_meta[72];       // bits 0-15: accumulator column, bit 16: accumulate within the chunk
 };
 
+template <int KHW>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ Wg2Params p) {
@@ -893,12 +896,14 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   } else if (warp == 1) {
     {  // not guarded by has_work: an empty range simply runs no iterations, and the guard would make
        // ptxas treat the loop as divergent (no uniform-datapath MMA issue)
-      // warp-uniform loop over the host-built (tap, K16-step) table; one elected lane issues
+      // warp-uniform; the (tap, K16-step) sequence is fully unrolled with immediate descriptor offsets and
+      // one elected lane issues
       const bool leader = elect_one();
       const bool issue = leader && !(p.dbg & 2);
+      constexpr int PWk = 8 + KHW - 1;
       const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
       const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
-      const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * kWgBoxBytes, p.plane_stride, PWc * 128);
+      const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * kWgBoxBytes, p.plane_stride, PWk * 128);
       const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
       const uint32_t stage16 = p.stage_bytes >> 4;
       int s = 0;
@@ -909,14 +914,17 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         const uint32_t alo = alo0 + static_cast<uint32_t>(s) * stage16;
         const uint32_t blo = blo0 + static_cast<uint32_t>(s) * stage16;
         const uint32_t accumulate = c > c_begin;
-#pragma unroll 4
-        for (int j = 0; j < p.n_tab; ++j) {
-          const uint32_t m = p.t_meta[j];
-          const uint32_t d = tmem_base + (m & 0xFFFFu);
-          const uint64_t da = desc_join(alo + p.t_a[j], ahi);
-          const uint64_t db = desc_join(blo + p.t_b[j], bhi);
-          const uint32_t acc = accumulate | (m >> 16);
-          if (issue) umma_bf16(d, da, db, idesc, acc);
+        if (issue) {
+#pragma unroll
+          for (int b = 0; b < KHW; ++b)
+#pragma unroll
+            for (int cc = 0; cc < KHW; ++cc) {
+              const uint32_t tacc = tmem_base + (b * KHW + cc) * p.ci_n;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)  // dY advances 2 h-rows = 2048 B per K16, X advances 2*PWk halo rows
+                umma_bf16(tacc, desc_join(alo + 128 * k, ahi),
+                          desc_join(blo + (b * PWk + cc) * 8 + 16 * PWk * k, bhi), idesc, k == 0 ? accumulate : 1u);
+            }
         }
         if (leader) umma_commit(&empty_bar[s]);
         if (++s == p.stages) {
@@ -1144,7 +1152,7 @@ static int g_dbg = 0;
 
 // Resident-weight kernel: returns 1 when the geometry does not qualify (caller falls back), 0 when it
 // launched or failed (status in *err).
-template <int KC>
+template <int KC, int KHW>
 static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_packed, int w_rows, int cin_k,
                           const Epilogue& epi, int N, int D, int H, int W, int kd, int kh, int kw,
                           cudaStream_t stream, int* err) {
@@ -1165,6 +1173,7 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   const int mmas_per_sub = ntaps * p.cblocks * (KC / 16);
   int g0 = (kd == 3 || mmas_per_sub < 24) ? 4 : 1;
   while (g0 > D) g0 >>= 1;
+  const int stage_bytes = epi.out_fp32 ? 4096 : 2048;  // 32 rows x 128 / 64 B
   // pick (G, staging buffers): first choice with >= 3 input slots, else the first with >= 2
   int bestG = 0, bestBufs = 0, bestSlots = 0;
   for (int pass = 0; pass < 2 && !bestG; ++pass)
@@ -1173,7 +1182,7 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
         if (G * p.acc_stride * 2 > 512) continue;
         const long long box = (long long)(G + kd - 1) * PWc * PHc * KC * 2;
         const long long slot = (box + 1023) & ~1023LL;
-        const long long avail = (long long)kResBudget - b_total - 8LL * bufs * kStageBytes;
+        const long long avail = (long long)kResBudget - b_total - 8LL * bufs * stage_bytes;
         if (avail <= 0 || box >= (1 << 20)) continue;
         const int slots = (int)(avail / slot);
         if (slots >= (pass == 0 ? 3 : 2)) {
@@ -1189,7 +1198,6 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   p.dgroups = (D + p.G - 1) / p.G;
   p.acc_stages = 512 / (p.G * p.acc_stride);
   if (p.acc_stages > 4) p.acc_stages = 4;
-  p.n_tab = p.G * ntaps;
   p.nchunks = (p.block_n + 31) / 32;
   p.out_fp32 = epi.out_fp32;
   p.n_rows = epi.n_rows;
@@ -1197,26 +1205,16 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   p.bias = epi.bias;
   p.stats = epi.stats;
   p.stats_ld = epi.stats_ld;
-  const uint32_t row16 = KC * 2 / 16, b_tile16 = p.b_tile_bytes >> 4;
-  int j = 0;
-  for (int g = 0; g < p.G; ++g)
-    for (int a = 0; a < kd; ++a)
-      for (int b = 0; b < kh; ++b)
-        for (int c = 0; c < kw; ++c, ++j) {
-          const int tap = (a * kh + b) * kw + c;
-          p.a_off[j] = (uint32_t)(((g + a) * PHc * PWc + b * PWc + c) * row16);
-          p.b_off[j] = (uint32_t)tap * p.cblocks * b_tile16;
-          p.meta[j] = (uint32_t)(g * p.acc_stride) | (tap == 0 ? 1u << 16 : 0u);
-        }
+  p.stage_bytes = stage_bytes;
   CUtensorMap tmA, tmB, tmC;
   if ((*err = make_act_map(&tmA, x, x_ld, cin, N, D, H, W, KC, PWc, PHc, p.G + kd - 1, 1))) return 0;
   if ((*err = make_weight_map(&tmB, w_packed, w_rows, (long long)ntaps * cin_k, KC, p.block_n))) return 0;
   if ((*err = make_out_map(&tmC, epi.out, epi.out_ld, epi.out_cols, epi.out_fp32, N, D, H, W))) return 0;
-  size_t smem = (size_t)b_total + 8u * p.stage_bufs * kStageBytes + (size_t)p.a_slots * p.a_slot_bytes + 1024;
+  size_t smem = (size_t)b_total + 8u * p.stage_bufs * stage_bytes + (size_t)p.a_slots * p.a_slot_bytes + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC, KHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          224 * 1024);
     if (e != cudaSuccess) {
       *err = set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_res)");
@@ -1226,7 +1224,7 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   }
   const long long tiles = (long long)N * p.dgroups * p.tilesH * p.tilesW;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_fwd_res_kernel<KC><<<grid, kRes2Threads, smem, stream>>>(tmA, tmB, tmC, p);
+  conv_fwd_res_kernel<KC, KHW><<<grid, kRes2Threads, smem, stream>>>(tmA, tmB, tmC, p);
   *err = check_launch("conv_fwd_res");
   return 0;
 }
@@ -1289,11 +1287,19 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
   if (res_enabled() && w_rows <= 256 && (stats == nullptr || stats_ld <= 256)) {
     // tiles are 8 x 16 voxels of one (n, d) plane: require a reasonable fill
     const double fill = (double)W * H / ((double)((W + 7) / 8) * 8 * ((H + 15) / 16) * 16);
-    if (fill >= 0.7) {
+    if (fill >= 0.7 && kh == kw) {
       int err = 0, fb;
-      if (kc == 64) fb = try_launch_res<64>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
-      else if (kc == 32) fb = try_launch_res<32>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
-      else fb = try_launch_res<16>(x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err);
+#define VFD_RES_ARGS x, x_ld, cin, w_packed, w_rows, cin_k, epi, N, D, H, W, kd, kh, kw, stream, &err
+      if (kh == 3) {
+        if (kc == 64) fb = try_launch_res<64, 3>(VFD_RES_ARGS);
+        else if (kc == 32) fb = try_launch_res<32, 3>(VFD_RES_ARGS);
+        else fb = try_launch_res<16, 3>(VFD_RES_ARGS);
+      } else {
+        if (kc == 64) fb = try_launch_res<64, 1>(VFD_RES_ARGS);
+        else if (kc == 32) fb = try_launch_res<32, 1>(VFD_RES_ARGS);
+        else fb = try_launch_res<16, 1>(VFD_RES_ARGS);
+      }
+#undef VFD_RES_ARGS
       if (!fb) return err;
     }
   }
@@ -1324,7 +1330,7 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   {
     const int tilesW = (W + 7) / 8, tilesH = (H + 15) / 16;
     const double fill = (double)W * H / ((double)tilesW * 8 * tilesH * 16);
-    if (wgrad2_enabled() && fill >= 0.7) {
+    if (wgrad2_enabled() && fill >= 0.7 && kh == kw) {
       Wg2Params q;
       q.N = N; q.D = D; q.H = H; q.W = W; q.tilesW = tilesW; q.tilesH = tilesH;
       q.kd = kd; q.kh = kh; q.kw = kw; q.cout = cout; q.cin = cin;
@@ -1347,37 +1353,27 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
         q.stages = stages;
         const long long chunks = (long long)N * D * tilesH * tilesW;
         const long long base = (long long)kd * q.co_tiles * q.ci_tiles;
-        long long splits = (2LL * num_sms() + base - 1) / base;
+        // one CTA per SM at a time: size the grid to whole waves (2 when the (co, ci, kd) tiling allows it)
+        long long splits = (2LL * num_sms()) / base;
+        if (splits < 1) splits = (base <= num_sms()) ? num_sms() / base : 1;
         if (splits > chunks) splits = chunks;
         if (splits < 1) splits = 1;
         q.splits = (int)splits;
         q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
-        {
-          const int PWc = 8 + kw - 1;
-          int j = 0;
-          for (int b = 0; b < kh; ++b)
-            for (int cc = 0; cc < kw; ++cc)
-              for (int k = 0; k < 8; ++k, ++j) {
-                q.t_a[j] = 128u * k;                                   // dY advances 2 h-rows = 2048 B per K16
-                q.t_b[j] = (uint32_t)((b * PWc + cc) * 8 + 16 * PWc * k);  // X: tap shift + 2*PWc rows per K16
-                q.t_meta[j] = (uint32_t)((b * kw + cc) * q.ci_n) | (k != 0 ? 1u << 16 : 0u);
-              }
-          q.n_tab = j;
-        }
         const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
         CUtensorMap tmDY, tmX;
         if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
         if (int e = make_act_map(&tmX, x, x_ld, x_ch, N, D, H, W, 64, 8 + kw - 1, 16 + kh - 1, 1, 1)) return e;
-        static bool attr2 = false;
-        if (!attr2) {
-          cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               224 * 1024);
+        auto kfn = kh == 3 ? conv_wgrad2_kernel<3> : conv_wgrad2_kernel<1>;
+        static bool attr2[2] = {false, false};
+        if (!attr2[kh == 3]) {
+          cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
           if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad2)");
-          attr2 = true;
+          attr2[kh == 3] = true;
         }
         size_t smem = (size_t)stages * q.stage_bytes + 1024;
-        if (q.tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM when it owns > half the TMEM
-        conv_wgrad2_kernel<<<(unsigned)(base * q.splits), kWgThreads, smem, stream>>>(tmDY, tmX, q);
+        if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM (TMEM and wave accounting below assume it)
+        kfn<<<(unsigned)(base * q.splits), kWgThreads, smem, stream>>>(tmDY, tmX, q);
         return check_launch("conv_wgrad2");
       }
     }
