@@ -237,56 +237,91 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int C, int Cvalid,
   sums[C + c] = 0.0;
 }
 
+// Division by a run-time constant without the integer divide sequence: q = (umulhi(n, m) + n) >> s,
+// exact for n < 2^31 (all voxel / window counts here are checked to be below that).
+struct FastDiv {
+  uint32_t m, s, d;
+};
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.m) + n) >> f.s; }
+
 struct ActGeom {
   int N, D, H, W;     // full-resolution voxel grid
   int pd, ph, pw;     // pooling window (1 or 2 per axis); floor semantics like nn.AvgPool3d
   int C;              // padded channel count (multiple of 8)
+  int WD, WH, WW;     // windows per axis (ceil: partial windows still carry full-resolution voxels)
+  int QD, QH, QW;     // pooled extent (floor)
+  unsigned nwin;
+  FastDiv fWW, fWH, fWD;
 };
 
 // The BN/activation kernels map one thread to (pool window, 8-channel group). A block owns a
 // contiguous range of windows; a thread keeps its channel group for the whole kernel (so the
 // per-channel constants live in registers) and strides over windows. All loads of an iteration are
-// issued before any arithmetic (U windows x NV voxels = 8 independent 128-bit loads per tensor).
-struct WinGeom {
-  int WD, WH, WW;   // windows per axis (ceil: partial windows still carry full-resolution voxels)
-  int QD, QH, QW;   // pooled extent (floor)
-  unsigned nwin;
-};
-template <int PD, int PH, int PW>
-__device__ __forceinline__ WinGeom win_geom(const ActGeom& g) {
-  WinGeom w;
-  w.WD = (g.D + PD - 1) / PD;
-  w.WH = (g.H + PH - 1) / PH;
-  w.WW = (g.W + PW - 1) / PW;
-  w.QD = g.D / PD;
-  w.QH = g.H / PH;
-  w.QW = g.W / PW;
-  w.nwin = (unsigned)g.N * w.WD * w.WH * w.WW;
-  return w;
-}
-__device__ __forceinline__ void decode_win(unsigned win, const WinGeom& wg, int& n, int& wd, int& wh,
-                                           int& ww) {
-  ww = win % wg.WW;
-  unsigned t = win / wg.WW;
-  wh = t % wg.WH;
-  t /= wg.WH;
-  wd = t % wg.WD;
-  n = t / wg.WD;
+// issued before any arithmetic (U windows x NV voxels independent 128-bit loads per tensor). These
+// kernels are instruction-issue bound before they are HBM bound, so the index math avoids integer
+// division (FastDiv; none at all for un-pooled tensors) and the per-element arithmetic is folded into
+// the fewest FFMA / FMNMX it takes.
+__device__ __forceinline__ void decode_win(unsigned win, const ActGeom& g, int& n, int& wd, int& wh, int& ww) {
+  const unsigned t = fdiv(win, g.fWW);
+  ww = win - t * g.WW;
+  const unsigned t2 = fdiv(t, g.fWH);
+  wh = t - t2 * g.WH;
+  const unsigned t3 = fdiv(t2, g.fWD);
+  wd = t2 - t3 * g.WD;
+  n = t3;
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
+  // bf16 -> fp32 is a 16-bit shift: low halves by shift, high halves by mask
+  v[0] = __uint_as_float(u.x << 16);
+  v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(u.y << 16);
+  v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  v[4] = __uint_as_float(u.z << 16);
+  v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  v[6] = __uint_as_float(u.w << 16);
+  v[7] = __uint_as_float(u.w & 0xFFFF0000u);
 }
 __device__ __forceinline__ uint4 ldg16(const bf16* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
+// Voxels of one window (template pool shape): indices, validity, pooled index.
+template <int PD, int PH, int PW>
+struct Window {
+  static constexpr int NV = PD * PH * PW;
+  unsigned vox[NV];
+  bool ok[NV];
+  bool pool_ok;
+  unsigned pvox;
+  __device__ __forceinline__ void locate(unsigned win, bool wv, const ActGeom& g) {
+    if (NV == 1) {
+      vox[0] = win;
+      ok[0] = wv;
+      pool_ok = wv;
+      pvox = win;
+      return;
+    }
+    int n, wd, wh, ww;
+    decode_win(wv ? win : 0u, g, n, wd, wh, ww);
+    pool_ok = wv && wd < g.QD && wh < g.QH && ww < g.QW;
+    pvox = ((n * g.QD + wd) * g.QH + wh) * g.QW + ww;
+    const unsigned base = ((n * g.D + wd * PD) * g.H + wh * PH) * g.W + ww * PW;
+#pragma unroll
+    for (int a = 0; a < PD; ++a)
+#pragma unroll
+      for (int b = 0; b < PH; ++b)
+#pragma unroll
+        for (int c = 0; c < PW; ++c) {
+          const int v = (a * PH + b) * PW + c;
+          ok[v] = wv && (PD == 1 || wd * PD + a < g.D) && (PH == 1 || wh * PH + b < g.H) &&
+                  (PW == 1 || ww * PW + c < g.W);
+          vox[v] = base + (a * g.H + b) * g.W + c;
+        }
+  }
+};
+
 // out = dropout(act(y * scale + shift)); optionally also the average-pooled tensor.
+// act(z) = max(z, slope * z) for 0 <= slope <= 1 (ReLU, LeakyReLU).
 template <int PD, int PH, int PW, bool DROP>
 __global__ void __launch_bounds__(256, 2)
 bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
@@ -300,43 +335,29 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   const int tid = threadIdx.x;
   if (tid >= rpi * CG) return;
   const int cg = tid % CG, wl = tid / CG;
-  const WinGeom wg = win_geom<PD, PH, PW>(g);
-  const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+  const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
   const unsigned w_begin = blockIdx.x * per_block;
-  const unsigned w_end = min(wg.nwin, w_begin + per_block);
+  const unsigned w_end = min(g.nwin, w_begin + per_block);
   float sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = __ldg(scale + cg * 8 + j);
     sf[j] = __ldg(shift + cg * 8 + j);
   }
+  y += cg * 8;
+  if (out_full != nullptr) out_full += cg * 8;
+  if (out_pool != nullptr) out_pool += cg * 8;
   const float inv_win = 1.0f / (float)NV;
   for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+    Window<PD, PH, PW> wn[U];
     uint4 raw[U][NV];
-    long long vox[U][NV];
-    bool ok[U][NV];
-    bool pool_ok[U];
-    long long pvox[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned win = wb + u * rpi;
-      const bool wv = win < w_end;
-      int n, wd, wh, ww;
-      decode_win(wv ? win : w_begin, wg, n, wd, wh, ww);
-      pool_ok[u] = wv && wd < wg.QD && wh < wg.QH && ww < wg.QW;
-      pvox[u] = (((long long)n * wg.QD + wd) * wg.QH + wh) * wg.QW + ww;
+      wn[u].locate(win, win < w_end, g);
 #pragma unroll
-      for (int a = 0; a < PD; ++a)
-#pragma unroll
-        for (int b = 0; b < PH; ++b)
-#pragma unroll
-          for (int c = 0; c < PW; ++c) {
-            const int v = (a * PH + b) * PW + c;
-            const int d = wd * PD + a, h = wh * PH + b, w = ww * PW + c;
-            ok[u][v] = wv && d < g.D && h < g.H && w < g.W;
-            vox[u][v] = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-            if (ok[u][v]) raw[u][v] = ldg16(y + vox[u][v] * y_ld + cg * 8);
-          }
+      for (int v = 0; v < NV; ++v)
+        if (wn[u].ok[v]) raw[u][v] = ldg16(y + (size_t)wn[u].vox[v] * y_ld);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -345,28 +366,28 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        if (!ok[u][v]) continue;
+        if (!wn[u].ok[v]) continue;
         float x[8];
         unpack8(raw[u][v], x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(x[j], sc[j], sf[j]);
-          x[j] = z > 0.f ? z : z * slope;
+          x[j] = fmaxf(z, z * slope);
         }
         if (DROP) {
           float m[8];
-          dropout8(seed, vox[u][v], cg, drop_p, m);
+          dropout8(seed, (long long)wn[u].vox[v], cg, drop_p, m);
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] *= m[j];
         }
-        if (out_full != nullptr) store8(out_full + vox[u][v] * full_ld + cg * 8, x);
+        if (out_full != nullptr) store8(out_full + (size_t)wn[u].vox[v] * full_ld, x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += x[j];
       }
-      if (out_pool != nullptr && pool_ok[u]) {
+      if (out_pool != nullptr && wn[u].pool_ok) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] *= inv_win;
-        store8(out_pool + pvox[u] * pool_ld + cg * 8, acc);
+        store8(out_pool + (size_t)wn[u].pvox * pool_ld, acc);
       }
     }
   }
@@ -377,36 +398,21 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
 template <int PD, int PH, int PW, bool DROP>
 struct BwdWindow {
   static constexpr int NV = PD * PH * PW;
+  Window<PD, PH, PW> w;
   uint4 ry[NV], rg[NV], rp;
-  long long vox[NV];
-  bool ok[NV], pool_ok;
 
-  __device__ __forceinline__ void load(unsigned win, bool wv, unsigned w_begin, const WinGeom& wg,
-                                       const ActGeom& g, int cg, const bf16* __restrict__ y,
+  __device__ __forceinline__ void load(unsigned win, bool wv, const ActGeom& g, const bf16* __restrict__ y,
                                        long long y_ld, const bf16* __restrict__ g_full, long long gf_ld,
                                        const bf16* __restrict__ g_pool, long long gp_ld) {
-    int n, wd, wh, ww;
-    decode_win(wv ? win : w_begin, wg, n, wd, wh, ww);
-    pool_ok = wv && g_pool != nullptr && wd < wg.QD && wh < wg.QH && ww < wg.QW;
-    if (pool_ok) {
-      const long long pv = (((long long)n * wg.QD + wd) * wg.QH + wh) * wg.QW + ww;
-      rp = ldg16(g_pool + pv * gp_ld + cg * 8);
-    }
+    w.locate(win, wv, g);
+    w.pool_ok = w.pool_ok && g_pool != nullptr;
+    if (w.pool_ok) rp = ldg16(g_pool + (size_t)w.pvox * gp_ld);
 #pragma unroll
-    for (int a = 0; a < PD; ++a)
-#pragma unroll
-      for (int b = 0; b < PH; ++b)
-#pragma unroll
-        for (int c = 0; c < PW; ++c) {
-          const int v = (a * PH + b) * PW + c;
-          const int d = wd * PD + a, h = wh * PH + b, w = ww * PW + c;
-          ok[v] = wv && d < g.D && h < g.H && w < g.W;
-          vox[v] = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-          if (ok[v]) {
-            ry[v] = ldg16(y + vox[v] * y_ld + cg * 8);
-            if (g_full != nullptr) rg[v] = ldg16(g_full + vox[v] * gf_ld + cg * 8);
-          }
-        }
+    for (int v = 0; v < NV; ++v)
+      if (w.ok[v]) {
+        ry[v] = ldg16(y + (size_t)w.vox[v] * y_ld);
+        if (g_full != nullptr) rg[v] = ldg16(g_full + (size_t)w.vox[v] * gf_ld);
+      }
   }
   // gradient w.r.t. z = y*scale+shift for voxel v (yv receives the unpacked y)
   __device__ __forceinline__ void grad(int v, bool has_full, const float* sc, const float* sf,
@@ -419,7 +425,7 @@ struct BwdWindow {
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = 0.f;
     }
-    if (pool_ok) {
+    if (w.pool_ok) {
       float t[8];
       unpack8(rp, t);
       const float inv_win = 1.0f / (float)NV;
@@ -428,7 +434,7 @@ struct BwdWindow {
     }
     if (DROP) {
       float m[8];
-      dropout8(seed, vox[v], cg, drop_p, m);
+      dropout8(seed, (long long)w.vox[v], cg, drop_p, m);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] *= m[j];
     }
@@ -460,36 +466,38 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   __syncthreads();
   if (tid < rpi * CG) {
     const int cg = tid % CG, wl = tid / CG;
-    const WinGeom wg = win_geom<PD, PH, PW>(g);
-    const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+    const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
     const unsigned w_begin = blockIdx.x * per_block;
-    const unsigned w_end = min(wg.nwin, w_begin + per_block);
-    float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
+    const unsigned w_end = min(g.nwin, w_begin + per_block);
+    float sc[8], sf[8], is[8], nm[8], s1[8], s2[8];   // xhat = y * is + nm, nm = -mean * invstd
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(scale + cg * 8 + j);
       sf[j] = __ldg(shift + cg * 8 + j);
-      mu[j] = __ldg(mean + cg * 8 + j);
       is[j] = __ldg(invstd + cg * 8 + j);
+      nm[j] = -__ldg(mean + cg * 8 + j) * is[j];
       s1[j] = s2[j] = 0.f;
     }
+    y += cg * 8;
+    if (g_full != nullptr) g_full += cg * 8;
+    if (g_pool != nullptr) g_pool += cg * 8;
     const bool has_full = g_full != nullptr;
     for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
       BwdWindow<PD, PH, PW, DROP> bw[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        bw[u].load(wb + u * rpi, wb + u * rpi < w_end, w_begin, wg, g, cg, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+        bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-          if (!bw[u].ok[v]) continue;
+          if (!bw[u].w.ok[v]) continue;
           float yv[8], gv[8];
           bw[u].grad(v, has_full, sc, sf, slope, drop_p, seed, cg, yv, gv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             s1[j] += gv[j];
-            s2[j] = fmaf(gv[j], (yv[j] - mu[j]) * is[j], s2[j]);
+            s2[j] = fmaf(gv[j], fmaf(yv[j], is[j], nm[j]), s2[j]);
           }
         }
     }
@@ -521,7 +529,7 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, int Cva
   sums[C + c] = 0.0;
 }
 
-// Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2)
+// Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2) = scale * g + (kb + kc * xhat)
 template <int PD, int PH, int PW, bool DROP>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
@@ -538,36 +546,40 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   const int tid = threadIdx.x;
   if (tid >= rpi * CG) return;
   const int cg = tid % CG, wl = tid / CG;
-  const WinGeom wg = win_geom<PD, PH, PW>(g);
-  const unsigned per_block = (wg.nwin + gridDim.x - 1) / gridDim.x;
+  const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
   const unsigned w_begin = blockIdx.x * per_block;
-  const unsigned w_end = min(wg.nwin, w_begin + per_block);
-  float sc[8], sf[8], mu[8], is[8], k1[8], k2[8];
+  const unsigned w_end = min(g.nwin, w_begin + per_block);
+  float sc[8], sf[8], is[8], nm[8], kb[8], kc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = __ldg(scale + cg * 8 + j);
     sf[j] = __ldg(shift + cg * 8 + j);
-    mu[j] = __ldg(mean + cg * 8 + j);
     is[j] = __ldg(invstd + cg * 8 + j);
-    k1[j] = __ldg(c1 + cg * 8 + j);
-    k2[j] = __ldg(c2 + cg * 8 + j);
+    nm[j] = -__ldg(mean + cg * 8 + j) * is[j];
+    kb[j] = -sc[j] * __ldg(c1 + cg * 8 + j);
+    kc[j] = -sc[j] * __ldg(c2 + cg * 8 + j);
   }
+  y += cg * 8;
+  dy += cg * 8;
+  if (g_full != nullptr) g_full += cg * 8;
+  if (g_pool != nullptr) g_pool += cg * 8;
   const bool has_full = g_full != nullptr;
   for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
     BwdWindow<PD, PH, PW, DROP> bw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      bw[u].load(wb + u * rpi, wb + u * rpi < w_end, w_begin, wg, g, cg, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+      bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        if (!bw[u].ok[v]) continue;
+        if (!bw[u].w.ok[v]) continue;
         float yv[8], gv[8], o[8];
         bw[u].grad(v, has_full, sc, sf, slope, drop_p, seed, cg, yv, gv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gv[j] - k1[j] - (yv[j] - mu[j]) * is[j] * k2[j]);
-        store8(dy + bw[u].vox[v] * dy_ld + cg * 8, o);
+        for (int j = 0; j < 8; ++j)
+          o[j] = fmaf(sc[j], gv[j], fmaf(kc[j], fmaf(yv[j], is[j], nm[j]), kb[j]));
+        store8(dy + (size_t)bw[u].w.vox[v] * dy_ld, o);
       }
   }
 }
@@ -618,28 +630,42 @@ __device__ __forceinline__ void src_index(int o, int in_size, int out_size, int&
   l0 = 1.f - l1;
 }
 
+struct UpGeom {
+  int N, D, H, W, CG;          // low-resolution grid, channel groups of 8
+  unsigned total;              // work items (voxels x channel groups) of the kernel's index space
+  FastDiv fCG, fX, fY, fZ;     // divisors: CG, then the W / H / D extents of the index space
+};
+
 __global__ void __launch_bounds__(256)
-upsample2x_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int N, int D, int H, int W,
-                      int C, bf16* __restrict__ out, long long out_ld) {
-  const int CG = C / 8;
+upsample2x_fwd_kernel(const bf16* __restrict__ x, long long x_ld, UpGeom g, bf16* __restrict__ out,
+                      long long out_ld) {
+  const int D = g.D, H = g.H, W = g.W;
   const int OD = 2 * D, OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)N * OD * OH * OW * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long t = i / CG;
-    const long long ov = t;
-    const int ow = (int)(t % OW);
-    t /= OW;
-    const int oh = (int)(t % OH);
-    t /= OH;
-    const int od = (int)(t % OD);
-    const int n = (int)(t / OD);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < g.total; i += gridDim.x * blockDim.x) {
+    const unsigned ov = fdiv(i, g.fCG);
+    const int cg = i - ov * g.CG;
+    unsigned t = fdiv(ov, g.fX);
+    const int ow = ov - t * OW;
+    unsigned t2 = fdiv(t, g.fY);
+    const int oh = t - t2 * OH;
+    const unsigned n = fdiv(t2, g.fZ);
+    const int od = t2 - n * OD;
     int d0, d1, h0, h1, w0, w1;
     float ld0, ld1, lh0, lh1, lw0, lw1;
     src_index(od, D, OD, d0, d1, ld0, ld1);
     src_index(oh, H, OH, h0, h1, lh0, lh1);
     src_index(ow, W, OW, w0, w1, lw0, lw1);
+    const bf16* xb = x + cg * 8;
+    uint4 raw[8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int d = a ? d1 : d0, h = b ? h1 : h0, w = c ? w1 : w0;
+          raw[(a * 2 + b) * 2 + c] = ldg16(xb + (size_t)(((n * D + d) * H + h) * W + w) * x_ld);
+        }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -649,14 +675,13 @@ upsample2x_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int N, int D, 
       for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int d = a ? d1 : d0, h = b ? h1 : h0, w = c ? w1 : w0;
           const float wt = (a ? ld1 : ld0) * (b ? lh1 : lh0) * (c ? lw1 : lw0);
           float v[8];
-          load8(x + ((((long long)n * D + d) * H + h) * W + w) * x_ld + cg * 8, v);
+          unpack8(raw[(a * 2 + b) * 2 + c], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
         }
-    store8(out + ov * out_ld + cg * 8, acc);
+    store8(out + (size_t)ov * out_ld + cg * 8, acc);
   }
 }
 
@@ -680,26 +705,24 @@ __device__ __forceinline__ void bwd_weights(int i, int in_size, float* wts) {
 
 // gradient of the x2 trilinear upsample w.r.t. its low-resolution input (gather form)
 __global__ void __launch_bounds__(256)
-upsample2x_bwd_kernel(const bf16* __restrict__ go, long long go_ld, int N, int D, int H, int W,
-                      int C, bf16* __restrict__ gx, long long gx_ld) {
-  const int CG = C / 8;
+upsample2x_bwd_kernel(const bf16* __restrict__ go, long long go_ld, UpGeom g, bf16* __restrict__ gx,
+                      long long gx_ld) {
+  const int D = g.D, H = g.H, W = g.W;
   const int OD = 2 * D, OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)N * D * H * W * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long t = i / CG;
-    const long long iv = t;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    t /= H;
-    const int d = (int)(t % D);
-    const int n = (int)(t / D);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < g.total; i += gridDim.x * blockDim.x) {
+    const unsigned iv = fdiv(i, g.fCG);
+    const int cg = i - iv * g.CG;
+    unsigned t = fdiv(iv, g.fX);
+    const int w = iv - t * W;
+    unsigned t2 = fdiv(t, g.fY);
+    const int h = t - t2 * H;
+    const unsigned n = fdiv(t2, g.fZ);
+    const int d = t2 - n * D;
     float wd[7], wh[7], ww[7];
     bwd_weights(d, D, wd);
     bwd_weights(h, H, wh);
     bwd_weights(w, W, ww);
+    const bf16* gb = go + cg * 8;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -709,18 +732,24 @@ upsample2x_bwd_kernel(const bf16* __restrict__ go, long long go_ld, int N, int D
       for (int b = 0; b < 7; ++b) {
         if (wh[b] == 0.f) continue;
         const int oh = 2 * h - 2 + b;
+        const unsigned rowv = ((n * OD + od) * OH + oh) * OW + (2 * w - 2);
+        // at most four of the seven w-taps are non-zero: issue their loads together
+        uint4 raw[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+          if (ww[c] != 0.f) raw[c] = ldg16(gb + (size_t)(rowv + c) * go_ld);
+#pragma unroll
         for (int c = 0; c < 7; ++c) {
           if (ww[c] == 0.f) continue;
-          const int ow = 2 * w - 2 + c;
           const float wt = wd[a] * wh[b] * ww[c];
           float v[8];
-          load8(go + ((((long long)n * OD + od) * OH + oh) * OW + ow) * go_ld + cg * 8, v);
+          unpack8(raw[c], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
         }
       }
     }
-    store8(gx + iv * gx_ld + cg * 8, acc);
+    store8(gx + (size_t)iv * gx_ld + cg * 8, acc);
   }
 }
 
@@ -947,10 +976,29 @@ VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const 
   return check_launch("bn_finalize");
 }
 
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) {
+    f.m = 0;
+    f.s = 0;
+  } else {
+    uint32_t sft = 0;
+    while ((1u << sft) < d) ++sft;  // ceil(log2 d)
+    f.m = (uint32_t)((((1ull << sft) - d) << 32) / d + 1);
+    f.s = sft;
+  }
+  return f;
+}
+
 static int fill_act_geom(ActGeom& g, int N, int D, int H, int W, int C, int pd, int ph, int pw) {
   if ((pd != 1 && pd != 2) || (ph != 1 && ph != 2) || (pw != 1 && pw != 2))
     return set_error(VFD_ERR_ARG, "pool window must be 1 or 2 per axis");
   g.N = N; g.D = D; g.H = H; g.W = W; g.C = C; g.pd = pd; g.ph = ph; g.pw = pw;
+  g.WD = (D + pd - 1) / pd; g.WH = (H + ph - 1) / ph; g.WW = (W + pw - 1) / pw;
+  g.QD = D / pd; g.QH = H / ph; g.QW = W / pw;
+  g.nwin = (unsigned)((long long)N * g.WD * g.WH * g.WW);
+  g.fWW = make_fastdiv(g.WW); g.fWH = make_fastdiv(g.WH); g.fWD = make_fastdiv(g.WD);
   return 0;
 }
 
@@ -987,6 +1035,7 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
   if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
   if ((long long)N * D * H * W >= (1LL << 31)) return set_error(VFD_ERR_ARG, "bn_act_fwd: more than 2^31 voxels");
   if ((long long)N * D * H * W == 0) return 0;
+  if (!(slope >= 0.f && slope <= 1.f)) return set_error(VFD_ERR_ARG, "bn_act_fwd: slope must be in [0, 1]");
   const bool drop = drop_p > 0.f;
   const int grid = win_grid(g, pd, ph, pw, 8 / (pd * ph * pw) > 0 ? 8 / (pd * ph * pw) : 1);
   VFD_POOL_DISPATCH(bn_act_fwd_kernel, drop,
@@ -1034,13 +1083,24 @@ VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, flo
   return check_launch("channel_sum");
 }
 
+static int fill_up_geom(UpGeom& g, int N, int D, int H, int W, int C, int scale, const char* what) {
+  const long long total = (long long)N * D * H * W * scale * scale * scale * (C / 8);
+  if (total >= (1LL << 31)) return set_error(VFD_ERR_ARG, what);
+  g.N = N; g.D = D; g.H = H; g.W = W; g.CG = C / 8;
+  g.total = (unsigned)total;
+  g.fCG = make_fastdiv(C / 8);
+  g.fX = make_fastdiv(W * scale); g.fY = make_fastdiv(H * scale); g.fZ = make_fastdiv(D * scale);
+  return 0;
+}
+
 VFD_API int vfd_upsample2x_fwd(const void* x, long long x_ld, int N, int D, int H, int W, int C,
                                   void* out, long long out_ld, void* stream_) {
   if (int e = check_cl(x, x_ld, C, "upsample2x_fwd: bad input")) return e;
   if (int e = check_cl(out, out_ld, C, "upsample2x_fwd: bad output")) return e;
-  const long long total = (long long)N * D * H * W * 8 * (C / 8);
-  if (total == 0) return 0;
-  upsample2x_fwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)x, x_ld, N, D, H, W, C, (bf16*)out, out_ld);
+  UpGeom g;
+  if (int e = fill_up_geom(g, N, D, H, W, C, 2, "upsample2x_fwd: more than 2^31 output vectors")) return e;
+  if (g.total == 0) return 0;
+  upsample2x_fwd_kernel<<<grid_for(g.total), 256, 0, STREAM>>>((const bf16*)x, x_ld, g, (bf16*)out, out_ld);
   return check_launch("upsample2x_fwd");
 }
 
@@ -1048,9 +1108,10 @@ VFD_API int vfd_upsample2x_bwd(const void* go, long long go_ld, int N, int D, in
                                   void* gx, long long gx_ld, void* stream_) {
   if (int e = check_cl(go, go_ld, C, "upsample2x_bwd: bad input")) return e;
   if (int e = check_cl(gx, gx_ld, C, "upsample2x_bwd: bad output")) return e;
-  const long long total = (long long)N * D * H * W * (C / 8);
-  if (total == 0) return 0;
-  upsample2x_bwd_kernel<<<grid_for(total), 256, 0, STREAM>>>((const bf16*)go, go_ld, N, D, H, W, C, (bf16*)gx, gx_ld);
+  UpGeom g;
+  if (int e = fill_up_geom(g, N, D, H, W, C, 1, "upsample2x_bwd: more than 2^31 vectors")) return e;
+  if (g.total == 0) return 0;
+  upsample2x_bwd_kernel<<<grid_for(g.total), 256, 0, STREAM>>>((const bf16*)go, go_ld, g, (bf16*)gx, gx_ld);
   return check_launch("upsample2x_bwd");
 }
 
