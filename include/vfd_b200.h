@@ -103,11 +103,14 @@ VFD_API int vfd_bn_finalize(double* sums, int C, int Cvalid, long long V, const 
                             float* shift, void* stream);
 /* out = dropout(act(y*scale + shift)), act(z) = z > 0 ? z : slope*z. out_full (full resolution)
  * and out_pool (average over pd x ph x pw windows, floor semantics) are optional (NULL to skip).
- * drop_p = 0 disables dropout; the mask is Philox4x32-10 keyed by (seed, voxel, channel group). */
+ * drop_p = 0 disables dropout; the mask is Philox4x32-10 keyed by (seed, voxel, channel group).
+ * seed_dev (optional device pointer) is added to seed inside the kernel, so a captured CUDA graph draws a
+ * fresh mask at every replay from a counter the graph itself advances. 0 <= slope <= 1. */
 VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, int W, int C,
                            const float* scale, const float* shift, float slope, void* out_full,
                            long long full_ld, void* out_pool, long long pool_ld, int pd, int ph, int pw,
-                           float drop_p, unsigned long long seed, void* stream);
+                           float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                           void* stream);
 /* Backward of the above through BatchNorm: given the gradients of out_full / out_pool (either may
  * be NULL) computes dy (bf16), dgamma and dbeta (fp32 [Cvalid]). sums: zeroed double [2*C] scratch,
  * c1 / c2: fp32 [C] scratch. */
@@ -115,8 +118,9 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
                            const float* mean, const float* invstd, const float* scale,
                            const float* shift, float slope, const void* g_full, long long gf_ld,
                            const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
-                           unsigned long long seed, int train, double* sums, float* c1, float* c2,
-                           float* dgamma, float* dbeta, void* dy, long long dy_ld, void* stream);
+                           unsigned long long seed, const unsigned long long* seed_dev, int train,
+                           double* sums, float* c1, float* c2, float* dgamma, float* dbeta, void* dy,
+                           long long dy_ld, void* stream);
 /* out[c] += sum_v x[v][c]  (conv bias gradient when no BatchNorm follows) */
 VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream);
 

@@ -25,9 +25,9 @@ SIGNATURES = {
     "vfd_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vfd_bn_stats": [_p, _ll, _i, _ll, _p, _p],
     "vfd_bn_finalize": [_p, _i, _i, _ll, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p],
-    "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p],
+    "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p, _p],
     "vfd_bn_act_bwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i,
-                       _f, _ull, _i, _p, _p, _p, _p, _p, _p, _ll, _p],
+                       _f, _ull, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p],
     "vfd_channel_sum": [_p, _ll, _i, _ll, _p, _p],
     "vfd_upsample2x_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
     "vfd_upsample2x_bwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
@@ -37,6 +37,7 @@ SIGNATURES = {
     "vfd_sqdiff": [_p, _ll, _p, _ll, _i, _ll, _p, _p],
     "vfd_convlstm_cell_fwd": [_p, _ll, _p, _i, _ll, _p, _p, _p, _p],
     "vfd_convlstm_cell_bwd": [_p, _p, _p, _p, _p, _i, _ll, _p, _ll, _p, _p],
+    "vfd_set_debug": [_i],
 }
 
 _lib = None

@@ -327,9 +327,11 @@ __global__ void __launch_bounds__(256, 2)
 bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                   const float* __restrict__ scale, const float* __restrict__ shift, float slope,
                   bf16* __restrict__ out_full, long long full_ld, bf16* __restrict__ out_pool,
-                  long long pool_ld, float drop_p, unsigned long long seed) {
+                  long long pool_ld, float drop_p, unsigned long long seed,
+                  const unsigned long long* __restrict__ seed_dev) {
   constexpr int NV = PD * PH * PW;
   constexpr int U = NV >= 8 ? 1 : 8 / NV;
+  if (DROP && seed_dev != nullptr) seed += *seed_dev;  // per-step offset kept on the device (CUDA-graph replay)
   const int CG = g.C >> 3;
   const int rpi = 256 / CG;
   const int tid = threadIdx.x;
@@ -454,10 +456,12 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          float slope, const bf16* __restrict__ g_full, long long gf_ld,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
-                         unsigned long long seed, double* __restrict__ sums) {
+                         unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                         double* __restrict__ sums) {
   extern __shared__ float sh[];  // [2][C]
   constexpr int NV = PD * PH * PW;
   constexpr int U = NV >= 4 ? 1 : 4 / NV;
+  if (DROP && seed_dev != nullptr) seed += *seed_dev;
   const int C = g.C;
   const int CG = C >> 3;
   const int rpi = 256 / CG;
@@ -537,10 +541,12 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         float slope, const bf16* __restrict__ g_full, long long gf_ld,
                         const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
-                        unsigned long long seed, const float* __restrict__ c1,
-                        const float* __restrict__ c2, bf16* __restrict__ dy, long long dy_ld) {
+                        unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                        const float* __restrict__ c1, const float* __restrict__ c2, bf16* __restrict__ dy,
+                        long long dy_ld) {
   constexpr int NV = PD * PH * PW;
   constexpr int U = NV >= 4 ? 1 : 4 / NV;
+  if (DROP && seed_dev != nullptr) seed += *seed_dev;
   const int CG = g.C >> 3;
   const int rpi = 256 / CG;
   const int tid = threadIdx.x;
@@ -1027,7 +1033,8 @@ static int win_grid(const ActGeom& g, int pd, int ph, int pw, int nv_per_iter) {
 VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, int W, int C,
                               const float* scale, const float* shift, float slope, void* out_full,
                               long long full_ld, void* out_pool, long long pool_ld, int pd, int ph,
-                              int pw, float drop_p, unsigned long long seed, void* stream_) {
+                              int pw, float drop_p, unsigned long long seed,
+                              const unsigned long long* seed_dev, void* stream_) {
   if (int e = check_cl(y, y_ld, C, "bn_act_fwd: bad input")) return e;
   if (out_full && check_cl(out_full, full_ld, C, "bn_act_fwd: bad full output")) return VFD_ERR_ARG;
   if (out_pool && check_cl(out_pool, pool_ld, C, "bn_act_fwd: bad pooled output")) return VFD_ERR_ARG;
@@ -1040,7 +1047,7 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
   const int grid = win_grid(g, pd, ph, pw, 8 / (pd * ph * pw) > 0 ? 8 / (pd * ph * pw) : 1);
   VFD_POOL_DISPATCH(bn_act_fwd_kernel, drop,
                     (kfn<<<grid, 256, 0, STREAM>>>((const bf16*)y, y_ld, g, scale, shift, slope, (bf16*)out_full,
-                                                   full_ld, (bf16*)out_pool, pool_ld, drop_p, seed)));
+                                                   full_ld, (bf16*)out_pool, pool_ld, drop_p, seed, seed_dev)));
   return check_launch("bn_act_fwd");
 }
 
@@ -1048,8 +1055,9 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
                               const float* mean, const float* invstd, const float* scale,
                               const float* shift, float slope, const void* g_full, long long gf_ld,
                               const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
-                              unsigned long long seed, int train, double* sums, float* c1, float* c2,
-                              float* dgamma, float* dbeta, void* dy, long long dy_ld, void* stream_) {
+                              unsigned long long seed, const unsigned long long* seed_dev, int train,
+                              double* sums, float* c1, float* c2, float* dgamma, float* dbeta, void* dy,
+                              long long dy_ld, void* stream_) {
   if (int e = check_cl(y, y_ld, C, "bn_act_bwd: bad input")) return e;
   if (int e = check_cl(dy, dy_ld, C, "bn_act_bwd: bad output")) return e;
   if (g_full && check_cl(g_full, gf_ld, C, "bn_act_bwd: bad full-resolution gradient")) return VFD_ERR_ARG;
@@ -1065,14 +1073,14 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   VFD_POOL_DISPATCH(bn_act_bwd_reduce_kernel, drop,
                     (kfn<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(
                         (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
-                        (const bf16*)g_pool, gp_ld, drop_p, seed, sums)));
+                        (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums)));
   if (int e = check_launch("bn_act_bwd_reduce")) return e;
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
   if (int e = check_launch("bn_bwd_finalize")) return e;
   VFD_POOL_DISPATCH(bn_act_bwd_apply_kernel, drop,
                     (kfn<<<grid, 256, 0, STREAM>>>((const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
                                                    (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p,
-                                                   seed, c1, c2, (bf16*)dy, dy_ld)));
+                                                   seed, seed_dev, c1, c2, (bf16*)dy, dy_ld)));
   return check_launch("bn_act_bwd_apply");
 }
 

@@ -73,8 +73,10 @@ class NetG(nn.Module):
         self.ngf = ngf
         self.last_dropout_seeds = None
 
-    def forward_cl(self, xc, dropout_seeds=None):
-        """channels-last bf16 clip -> (fp32 conv_last logits channels-last, latent_i channels-last)."""
+    def forward_cl(self, xc, dropout_seeds=None, seed_dev=None):
+        """channels-last bf16 clip -> (fp32 conv_last logits channels-last, latent_i channels-last).
+        ``seed_dev``: optional device int64 scalar added to every dropout seed inside the kernels (the
+        per-step counter of a CUDA-graph-captured train step)."""
         N, D, H, W, _ = xc.shape
         if D % 16 or H % 16 or W % 16:
             raise RuntimeError(f"NetG needs nfr and isize divisible by 16, got D={D} H={H} W={W}")
@@ -100,13 +102,13 @@ class NetG(nn.Module):
         else:
             seeds = [0, 0, 0, 0]
         self.last_dropout_seeds = seeds
-        x, _ = self.uconv5.forward_cl(latent, drop_p=p, seed=seeds[0])
+        x, _ = self.uconv5.forward_cl(latent, drop_p=p, seed=seeds[0], seed_dev=seed_dev)
         dec = [self.uconv4, self.uconv3, self.uconv2, self.uconv1]
         for i, blk in enumerate(dec):
             lvl = 3 - i
             cat = ops.UpCatFn.apply(x, skips[lvl], [bufs[lvl]])
             if i < 3:
-                x, _ = blk.forward_cl(cat, drop_p=p, seed=seeds[i + 1])
+                x, _ = blk.forward_cl(cat, drop_p=p, seed=seeds[i + 1], seed_dev=seed_dev)
             else:
                 x, _ = blk.forward_cl(cat)
         logits = ops.ConvFn.apply(x, self.conv_last.weight, None, True, False)

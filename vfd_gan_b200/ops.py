@@ -156,19 +156,19 @@ def _bn_prepare(y, sums, cvalid, pre_bias, gamma, beta, running_mean, running_va
               invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
 
 
-def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, seed):
+def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, seed, seed_dev=None):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_fwd input")
     _lib.call("vfd_bn_act_fwd", y.data_ptr(), ld, N, D, H, W, C, scale.data_ptr(), shift.data_ptr(), slope,
               _ptr(out_full), 0 if out_full is None else _ld(out_full), _ptr(out_pool),
-              0 if out_pool is None else _ld(out_pool), pd, ph, pw, drop_p, seed, _stream())
+              0 if out_pool is None else _ld(out_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev), _stream())
 
 
 def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd, ph, pw, drop_p, seed, train,
-                sums, c1, c2, dgamma, dbeta, dy):
+                sums, c1, c2, dgamma, dbeta, dy, seed_dev=None):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_bwd input")
     _lib.call("vfd_bn_act_bwd", y.data_ptr(), ld, N, D, H, W, C, cvalid, mean.data_ptr(), invstd.data_ptr(),
               scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
-              _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed,
+              _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev),
               1 if train else 0, sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
               dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
 
@@ -239,12 +239,12 @@ bn_prepare = _define(
     "Tensor(f!) scale, Tensor(g!) shift, bool stats_ready) -> ()", _bn_prepare)
 bn_act_fwd = _define(
     "bn_act_fwd(Tensor y, Tensor scale, Tensor shift, float slope, Tensor(a!)? out_full, Tensor(b!)? out_pool, "
-    "int pd, int ph, int pw, float drop_p, int seed) -> ()", _bn_act_fwd)
+    "int pd, int ph, int pw, float drop_p, int seed, Tensor? seed_dev=None) -> ()", _bn_act_fwd)
 bn_act_bwd = _define(
     "bn_act_bwd(Tensor y, int cvalid, Tensor mean, Tensor invstd, Tensor scale, Tensor shift, float slope, "
     "Tensor? g_full, Tensor? g_pool, int pd, int ph, int pw, float drop_p, int seed, bool train, "
-    "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy) -> ()",
-    _bn_act_bwd)
+    "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy, "
+    "Tensor? seed_dev=None) -> ()", _bn_act_bwd)
 channel_sum = _define("channel_sum(Tensor x, Tensor(a!) out) -> ()", _channel_sum)
 upsample2x_fwd = _define("upsample2x_fwd(Tensor x, Tensor(a!) out) -> ()", _upsample2x_fwd)
 upsample2x_bwd = _define("upsample2x_bwd(Tensor gout, Tensor(a!) gx) -> ()", _upsample2x_bwd)
@@ -468,7 +468,7 @@ class BnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, gamma, beta, pre_bias, running_mean, running_var, train, momentum, eps, slope, pool, drop_p,
-                seed, want_full, want_pool, full_out_holder, stats_ready=False):
+                seed, want_full, want_pool, full_out_holder, stats_ready=False, seed_dev=None):
         N, D, H, W, C, _ = _check_cl(y, "bn input")
         cvalid = gamma.numel()
         dev = y.device
@@ -485,9 +485,11 @@ class BnActFn(torch.autograd.Function):
         if want_pool:
             pooled = cl_empty(N, D // pd, H // ph, W // pw, C, dev)
         nbytes = 2.0 * y.numel() * (1 + (1 if want_full else 0)) + (2.0 * pooled.numel() if want_pool else 0)
-        _timed("bn_act_fwd", nbytes, lambda: bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed))
+        _timed("bn_act_fwd", nbytes,
+               lambda: bn_act_fwd(y, scale, shift, slope, full, pooled, pd, ph, pw, drop_p, seed, seed_dev))
         ctx.save_for_backward(y, stats)
         ctx.cfg = (cvalid, slope, pool, drop_p, seed, train)
+        ctx.seed_dev = seed_dev
         ctx.has_pre_bias = pre_bias is not None
         return full, pooled
 
@@ -505,10 +507,11 @@ class BnActFn(torch.autograd.Function):
         nbytes = 2.0 * y.numel() * 3 + 2.0 * 2 * sum(g.numel() for g in (g_full, g_pool) if g is not None)
         _timed("bn_act_bwd", nbytes,
                lambda: bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw,
-                                  drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy))
+                                  drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy,
+                                  ctx.seed_dev))
         # a conv bias folded into training-mode BN has an identically zero gradient
         gpb = torch.zeros(cvalid, dtype=torch.float32, device=dev) if ctx.has_pre_bias else None
-        return (dy, dgamma, dbeta, gpb) + (None,) * 13
+        return (dy, dgamma, dbeta, gpb) + (None,) * 14
 
 
 class UpCatFn(torch.autograd.Function):

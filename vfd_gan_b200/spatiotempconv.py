@@ -23,7 +23,7 @@ def intermed_channels(in_channels, out_channels, kernel_size):
 
 
 def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None,
-             pre_bias=None, stats_ready=False):
+             pre_bias=None, stats_ready=False, seed_dev=None):
     """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16.
     ``pre_bias``: bias of the conv that produced ``y`` when it was left out of ``y`` (see
     ``SpatioTemporalConv.forward_cl``)."""
@@ -35,7 +35,7 @@ def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, w
     full, pooled = ops.BnActFn.apply(y, bn.weight, bn.bias, pre_bias, bn.running_mean, bn.running_var, train,
                                      float(bn.momentum), float(bn.eps), float(slope), tuple(pool), float(drop_p),
                                      int(seed), want_full, want_pool, None if full_out is None else [full_out],
-                                     stats_ready)
+                                     stats_ready, seed_dev)
     if train and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return full, pooled

@@ -20,15 +20,23 @@ with two deliberate differences that do not change any result:
 Optical flow (``video_to_flow``, host cv2 Farneback, lib/utils.py:94-129) is an *input* here, as in
 SURVEY.md section 8d.
 
+CUDA graph: after two eager steps the whole step (both forward passes, both backward passes, the weight
+re-packing, the gradient all-reduces and the two fused-Adam updates -- about 1100 kernel launches) is
+captured once into a CUDA graph and replayed, which removes the Python / dispatcher launch overhead
+that otherwise bounds the step. Dropout masks stay fresh under replay because the kernels add a device
+resident step counter to their Philox seed. ``VFD_CUDA_GRAPH=0`` (or ``graph=False``) keeps the step eager.
+
 Data parallelism (one process per GPU): ``GradAllReducer`` averages gradients over ranks with NCCL
 in buckets, launched from post-accumulate-grad hooks on a side stream so the collectives overlap
 the rest of backward. BatchNorm statistics stay per rank (DataParallel semantics).
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 
 LOSS_KEYS = ("g/err_g", "g/err_g_adv", "g/err_g_adv_s", "g/err_g_adv_t", "g/err_g_con",
              "d/err_d_real_s", "d/err_d_real_t", "d/err_d_fake_s", "d/err_d_fake_t",
@@ -120,7 +128,7 @@ class GanTrainStep:
     """One ``optimize_params``-equivalent step; see the module docstring."""
 
     def __init__(self, netg, netd, lr=2e-5, beta1=0.5, w_adv=1, w_con=10, pos_weight=2, distributed=None,
-                 bucket_mb=16.0):
+                 bucket_mb=16.0, graph=None):
         self.netg, self.netd = netg, netd
         self.w_adv, self.w_con, self.pos_weight = w_adv, w_con, pos_weight
         if distributed is None:
@@ -129,21 +137,69 @@ class GanTrainStep:
         self.red_d = GradAllReducer(list(netd.parameters()), bucket_mb)
         dev = next(netg.parameters()).device
         fused = dev.type == "cuda"
-        # Same hyper-parameters as models/mygannet.py:270-273
-        self.optimizer_g = torch.optim.Adam(netg.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused)
-        self.optimizer_d = torch.optim.Adam(netd.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused)
+        if graph is None:
+            graph = fused and os.environ.get("VFD_CUDA_GRAPH", "1") != "0"
+        self.use_graph = bool(graph) and fused
+        # Same hyper-parameters as models/mygannet.py:270-273 (capturable: the step counters live on the device
+        # so the update can be replayed from a CUDA graph)
+        self.optimizer_g = torch.optim.Adam(netg.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused,
+                                            capturable=self.use_graph)
+        self.optimizer_d = torch.optim.Adam(netd.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused,
+                                            capturable=self.use_graph)
         self.losses = torch.zeros(len(LOSS_KEYS), dtype=torch.float32, device=dev)
         self.predict = None
+        self._graph, self._static_in, self._eager_steps = None, None, 0
+        self._step_counter = torch.zeros((), dtype=torch.int64, device=dev) if fused else None
+
+    GRAPH_WARMUP_STEPS = 2
 
     def step(self, inp, gt, gt_flow, pre_flow, dropout_seeds=None):
         """inp (B,3,D,H,W) in [-1,1]; gt (B,1,D,H,W) in {0,1}; flows (B,3,D,H,W). Returns the device
         tensor of the 12 logged scalars in LOSS_KEYS order (no host synchronisation)."""
+        args = (inp, gt, gt_flow, pre_flow)
+        if not self.use_graph or dropout_seeds is not None:
+            return self._step_impl(*args, dropout_seeds=dropout_seeds)
+        if self._graph is None:
+            if self._eager_steps < self.GRAPH_WARMUP_STEPS:
+                self._eager_steps += 1
+                return self._step_impl(*args, seed_dev=self._step_counter)
+            self._capture(args)
+        elif any(s.shape != t.shape for s, t in zip(self._static_in, args)):
+            return self._step_impl(*args, seed_dev=self._step_counter)   # other batch geometry: stay eager
+        for s, t in zip(self._static_in, args):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self._graph.replay()
+        _lib.LAUNCHES += self.graph_calls
+        _lib.KERNEL_LAUNCHES += self.graph_kernels          # kernels of ours the replay just launched
+        ops.invalidate_packed_weights()                     # the replay updated the fp32 masters
+        return self.losses
+
+    def _capture(self, args):
+        """Record one step into a CUDA graph. The caller's tensors become the graph's static inputs (later
+        calls with other tensors are copied into them)."""
+        self._static_in = [t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+                           for t in args]
+        self.netg.train()
+        self.netd.train()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        c0, k0 = _lib.LAUNCHES, _lib.KERNEL_LAUNCHES
+        with torch.cuda.graph(graph):
+            self._step_impl(*self._static_in, seed_dev=self._step_counter)
+        self.graph_calls, self.graph_kernels = _lib.LAUNCHES - c0, _lib.KERNEL_LAUNCHES - k0
+        _lib.LAUNCHES, _lib.KERNEL_LAUNCHES = c0, k0        # capture records, it does not launch
+        self._graph = graph
+
+    def _step_impl(self, inp, gt, gt_flow, pre_flow, dropout_seeds=None, seed_dev=None):
         netg, netd = self.netg, self.netd
         netg.train()
         netd.train()
+        if seed_dev is not None:
+            seed_dev += 1   # in-place on the device: captured, so every replay advances the dropout stream
 
         # forward_g
-        logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds)
+        logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds, seed_dev=seed_dev)
         predict = ops.SigmoidHeadFn.apply(logits)
         self.predict = predict.detach()
 
