@@ -16,6 +16,8 @@ LAYERS = {
     "T.dconv3.t": (54, 128, 3, 1, 1, 32, 4, 112, 112),
     "uconv2.s": (192, 172, 1, 3, 3, 32, 8, 56, 56),
 }
+import os
+FLAGS = [int(f) for f in os.environ.get("PROBE_FLAGS", "0,1,2,3,4,5,6,7").split(",")]
 names = sys.argv[1:] or list(LAYERS)
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -37,7 +39,8 @@ def timeit(fn, reps=3):
     return sorted(ts)[len(ts) // 2]
 
 
-print(f"{'layer':11s} {'kernel':10s} " + " ".join(f"dbg={d:<6d}" for d in range(8)) + "   (ms; 1=noTMA 2=noMMA 4=noEPI)")
+print(f"{'layer':11s} {'kernel':10s} " + " ".join(f"dbg={d:<6d}" for d in FLAGS) +
+      "   (ms; 1=noTMA 2=noMMA 4=noEPI 8=noTMAstore 16=nofence 32=noTMEMld)")
 for name in names:
     cin, cout, kd, kh, kw, N, D, H, W = LAYERS[name] if name in LAYERS else map(int, name.split(","))
     cin_p, cout_p = ops.round_up(cin, 8), ops.round_up(cout, 8)
@@ -59,7 +62,7 @@ for name in names:
     }
     for kname, fn in kernels.items():
         row = []
-        for dbg in range(8):
+        for dbg in FLAGS:
             L.vfd_set_debug(dbg)
             row.append(timeit(fn))
         L.vfd_set_debug(0)

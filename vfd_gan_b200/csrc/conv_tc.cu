@@ -538,7 +538,10 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
           for (int ch = 0; ch < p.nchunks; ++ch) {
             float v[32];
-            if (ch * 32 + 32 <= p.block_n) {
+            if (p.dbg & 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            } else if (ch * 32 + 32 <= p.block_n) {
               tmem_ld32(tacc + ch * 32, v);
             } else {
               tmem_ld16(tacc + ch * 32, v);
@@ -551,7 +554,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (ch * 32 + i < p.n_rows) v[i] += __ldg(p.bias + ch * 32 + i);
             }
             // the staging buffer may still be the source of an earlier TMA store
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & 8)) {
               if (p.stage_bufs == 2) bulk_wait_group_read<1>();
               else bulk_wait_group_read<0>();
             }
@@ -575,9 +578,9 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 *reinterpret_cast<uint4*>(rowp + ((c ^ ((lane >> 1) & 3)) << 4)) = pk;
               }
             }
-            fence_proxy_async_smem();
+            if (!(p.dbg & 16)) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & 8)) {
               tma_store_5d(&tmC, sb, ch * 32, w0, h0 + 4 * q, d, n);
               bulk_commit_group();
             }

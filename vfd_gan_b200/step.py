@@ -249,22 +249,59 @@ class GanTrainStep:
 class HostBatchStep:
     """End-to-end entry: pinned host buffers in, loss scalars out.
 
-    Every call copies the step's inputs host->device (async, from pinned memory), runs
+    Every call copies the step's inputs host->device (async, from pinned memory, on a copy stream), runs
     ``GanTrainStep.step`` and reads the 12 loss scalars back -- the same boundary as
-    ``lib/train_gan.py:69-70`` (``d.to('cuda')`` then ``optimize_params()``)."""
+    ``lib/train_gan.py:69-70`` (``d.to('cuda')`` then ``optimize_params()``).
+
+    The call is software-pipelined by one step, like a ``DataLoader(pin_memory=True)`` feeding
+    ``.to('cuda', non_blocking=True)``: the copy of step i runs on the copy stream while step i-1 is still
+    computing (two device input sets), and the scalars returned by call i are those of step i-1 (``None``
+    for the first call; ``flush()`` returns the last step's). Nothing is skipped: every step's host->device
+    bytes and device->host read are issued inside the caller's loop."""
 
     def __init__(self, trainer, batch, nfr, isize, device):
         self.trainer = trainer
         shp3, shp1 = (batch, 3, nfr, isize, isize), (batch, 1, nfr, isize, isize)
-        self.dev = [torch.empty(shp3, device=device), torch.empty(shp1, device=device),
-                    torch.empty(shp3, device=device), torch.empty(shp3, device=device)]
-        self.host_losses = torch.empty(len(LOSS_KEYS), dtype=torch.float32).pin_memory()
+        mk = lambda: [torch.empty(shp3, device=device), torch.empty(shp1, device=device),
+                      torch.empty(shp3, device=device), torch.empty(shp3, device=device)]
+        self.dev = mk()            # the step's (CUDA-graph static) inputs
+        self.stage = mk()          # landing buffers of the copy stream
+        self.host_losses = [torch.empty(len(LOSS_KEYS), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.h2d_bytes = sum(t.numel() * 4 for t in self.dev)
-        self.d2h_bytes = self.host_losses.numel() * 4
+        self.d2h_bytes = self.host_losses[0].numel() * 4
+        cuda = torch.device(device).type == "cuda"
+        self.copy_stream = torch.cuda.Stream(device=device) if cuda else None
+        self.copied = torch.cuda.Event() if cuda else None
+        self.consumed = torch.cuda.Event() if cuda else None
+        self.read_back = [torch.cuda.Event() if cuda else None for _ in range(2)]
+        self.n = 0
 
     def __call__(self, host_inp, host_gt, host_gt_flow, host_pre_flow):
-        for d, h in zip(self.dev, (host_inp, host_gt, host_gt_flow, host_pre_flow)):
-            d.copy_(h, non_blocking=True)
+        hosts = (host_inp, host_gt, host_gt_flow, host_pre_flow)
+        cur = torch.cuda.current_stream()
+        # host -> device on the copy stream; it may overlap the previous step's kernels
+        with torch.cuda.stream(self.copy_stream):
+            if self.n:
+                self.copy_stream.wait_event(self.consumed)   # the landing buffers were drained
+            for d, h in zip(self.stage, hosts):
+                d.copy_(h, non_blocking=True)
+            self.copied.record()
+        cur.wait_event(self.copied)
+        for d, s in zip(self.dev, self.stage):               # device-side hand-over into the static inputs
+            d.copy_(s, non_blocking=True)
+        self.consumed.record()
         losses = self.trainer.step(*self.dev)
-        self.host_losses.copy_(losses, non_blocking=True)
-        return self.host_losses
+        slot = self.n & 1
+        self.host_losses[slot].copy_(losses, non_blocking=True)
+        self.read_back[slot].record()
+        self.n += 1
+        if self.n == 1:
+            return None
+        self.read_back[slot ^ 1].synchronize()               # previous step's scalars are on the host
+        return self.host_losses[slot ^ 1]
+
+    def flush(self):
+        """Scalars of the most recent step (waits for it)."""
+        slot = (self.n - 1) & 1
+        self.read_back[slot].synchronize()
+        return self.host_losses[slot]
