@@ -121,6 +121,13 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
                            unsigned long long seed, const unsigned long long* seed_dev, int train,
                            double* sums, float* c1, float* c2, float* dgamma, float* dbeta, void* dy,
                            long long dy_ld, void* stream);
+/* Tap folding for the weight gradient of thin convs (autograd of nn.Conv3d, models/mygannet.py:311,344):
+ * dst[v][t*cs + c] = src[v + sign*offset(t)][c] for the kd*kh*kw taps t and c < cs (zero outside the volume,
+ * remaining columns zero; dst_cols = taps*cs rounded up to 8, <= 32). With taps folded into channels,
+ * vfd_conv3d_wgrad of a 1x1x1 kernel on (dy, dst) (sign +1, src = x) or on (dst, x) (sign -1, src = dy)
+ * yields every tap's gradient from dense MMAs. */
+VFD_API int vfd_tap_gather(const void* src, long long src_ld, int cs, void* dst, long long dst_ld, int dst_cols,
+                           int N, int D, int H, int W, int kd, int kh, int kw, int sign, void* stream);
 /* out[c] += sum_v x[v][c]  (conv bias gradient when no BatchNorm follows) */
 VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream);
 

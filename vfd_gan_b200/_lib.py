@@ -28,6 +28,7 @@ SIGNATURES = {
     "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p, _p],
     "vfd_bn_act_bwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i,
                        _f, _ull, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p],
+    "vfd_tap_gather": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_channel_sum": [_p, _ll, _i, _ll, _p, _p],
     "vfd_upsample2x_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
     "vfd_upsample2x_bwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],

@@ -902,6 +902,71 @@ __global__ void convlstm_cell_bwd_kernel(const float* __restrict__ act, const fl
   }
 }
 
+
+// ------------------------------------------------------------------------------ tap gather (im2col into channels)
+// dst[v][t*CS + c] = src[v + sign*off(t)][c] for the KD*KH*KW taps t (offsets centred, zero outside the
+// volume) and c < CS; the remaining destination columns are zero. Folding the taps of a thin conv into
+// the channel dimension turns its weight gradient into a 1x1x1 wgrad with a dense K = taps*CS (<= 32)
+// instead of taps x 8 nearly empty 128 x 16 x 16 MMAs per 128 voxels. One thread per voxel; lanes are
+// consecutive voxels, so the 16-byte source loads of a warp are contiguous.
+struct GatherGeom {
+  int N, D, H, W;
+  unsigned V;
+  FastDiv fW, fH, fD;
+};
+
+template <int KD, int KH, int KW, int CS>
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long dst_ld,
+                  GatherGeom g, int sign) {
+  constexpr int TAPS = KD * KH * KW;
+  constexpr int COLS = (TAPS * CS + 7) & ~7;
+  static_assert(COLS <= 32 && CS <= 4, "tap gather folds at most 32 columns");
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < g.V; v += gridDim.x * blockDim.x) {
+    unsigned t = fdiv(v, g.fW);
+    const int w = v - t * g.W;
+    unsigned t2 = fdiv(t, g.fH);
+    const int h = t - t2 * g.H;
+    const unsigned n = fdiv(t2, g.fD);
+    const int d = t2 - n * g.D;
+    uint32_t raw[TAPS][2];
+#pragma unroll
+    for (int a = 0; a < KD; ++a)
+#pragma unroll
+      for (int b = 0; b < KH; ++b)
+#pragma unroll
+        for (int c = 0; c < KW; ++c) {
+          const int tp = (a * KH + b) * KW + c;
+          const int dd = d + sign * (a - KD / 2), hh = h + sign * (b - KH / 2), ww = w + sign * (c - KW / 2);
+          const bool ok = dd >= 0 && dd < g.D && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
+          uint2 r = make_uint2(0u, 0u);
+          if (ok)
+            r = __ldg(reinterpret_cast<const uint2*>(src + (size_t)(((n * g.D + dd) * g.H + hh) * g.W + ww) * src_ld));
+          raw[tp][0] = r.x;
+          raw[tp][1] = r.y;
+        }
+    // element e of the destination row = channel (e % CS) of tap (e / CS)
+    uint32_t outw[COLS / 2];
+#pragma unroll
+    for (int e2 = 0; e2 < COLS / 2; ++e2) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int e = 2 * e2 + half;
+        if (e < TAPS * CS) {
+          const int tp = e / CS, ch = e % CS;
+          const uint32_t val = (raw[tp][ch >> 1] >> ((ch & 1) * 16)) & 0xFFFFu;
+          word |= val << (half * 16);
+        }
+      }
+      outw[e2] = word;
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)v * dst_ld);
+#pragma unroll
+    for (int i = 0; i < COLS / 8; ++i) o[i] = make_uint4(outw[4 * i], outw[4 * i + 1], outw[4 * i + 2], outw[4 * i + 3]);
+  }
+}
+
 static inline int grid_for(long long total, int block = 256, int max_blocks = 148 * 16) {
   long long b = (total + block - 1) / block;
   if (b < 1) b = 1;
@@ -1082,6 +1147,38 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
                                                    (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p,
                                                    seed, seed_dev, c1, c2, (bf16*)dy, dy_ld)));
   return check_launch("bn_act_bwd_apply");
+}
+
+VFD_API int vfd_tap_gather(const void* src, long long src_ld, int cs, void* dst, long long dst_ld, int dst_cols,
+                              int N, int D, int H, int W, int kd, int kh, int kw, int sign, void* stream_) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (src_ld % 8) || (reinterpret_cast<uintptr_t>(dst) & 15) || (dst_ld % 8))
+    return set_error(VFD_ERR_ARG, "tap_gather: tensors must be 16-byte aligned channels-last bf16");
+  const long long V = (long long)N * D * H * W;
+  if (V >= (1LL << 31)) return set_error(VFD_ERR_ARG, "tap_gather: more than 2^31 voxels");
+  if (V == 0) return 0;
+  if (sign != 1 && sign != -1) return set_error(VFD_ERR_ARG, "tap_gather: sign must be +1 or -1");
+  GatherGeom g;
+  g.N = N; g.D = D; g.H = H; g.W = W; g.V = (unsigned)V;
+  g.fW = make_fastdiv(W); g.fH = make_fastdiv(H); g.fD = make_fastdiv(D);
+  const int taps = kd * kh * kw;
+  if (dst_cols != ((taps * cs + 7) & ~7) || dst_ld < dst_cols)
+    return set_error(VFD_ERR_ARG, "tap_gather: dst_cols must be taps*cs rounded up to 8");
+#define VFD_GATHER(KD, KH, KW, CS)                                                                       \
+  if (kd == KD && kh == KH && kw == KW && cs == CS) {                                                    \
+    tap_gather_kernel<KD, KH, KW, CS><<<grid_for(V), 256, 0, STREAM>>>((const bf16*)src, src_ld, (bf16*)dst, \
+                                                                       dst_ld, g, sign);                \
+    return check_launch("tap_gather");                                                                   \
+  }
+  VFD_GATHER(3, 3, 3, 1)
+  VFD_GATHER(1, 3, 3, 3)
+  VFD_GATHER(1, 3, 3, 1)
+  VFD_GATHER(1, 3, 3, 2)
+  VFD_GATHER(3, 1, 1, 1)
+  VFD_GATHER(3, 1, 1, 2)
+  VFD_GATHER(3, 1, 1, 3)
+  VFD_GATHER(3, 1, 1, 4)
+#undef VFD_GATHER
+  return set_error(VFD_ERR_ARG, "tap_gather: unsupported (kernel, channels-per-tap) combination");
 }
 
 VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream_) {

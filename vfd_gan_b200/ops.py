@@ -8,6 +8,8 @@ exceed ``C`` (channel slice of a concat buffer). The ``nn.Module`` surface in ``
 Ops are registered in the ``vfd_b200`` torch.library namespace with CUDA implementations that call
 the C-ABI through ctypes (``_lib.call``); autograd is provided by the ``*Fn`` classes below.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -173,6 +175,12 @@ def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd
               dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
 
 
+def _tap_gather(src, cs, dst, kd, kh, kw, sign):
+    N, D, H, W, _, ld = _check_cl(src, "tap_gather source")
+    _lib.call("vfd_tap_gather", src.data_ptr(), ld, cs, dst.data_ptr(), _ld(dst), dst.shape[-1], N, D, H, W, kd, kh,
+              kw, sign, _stream())
+
+
 def _channel_sum(x, out):
     N, D, H, W, C, ld = _check_cl(x, "channel_sum input")
     _lib.call("vfd_channel_sum", x.data_ptr(), ld, C, N * D * H * W, out.data_ptr(), _stream())
@@ -245,6 +253,8 @@ bn_act_bwd = _define(
     "Tensor? g_full, Tensor? g_pool, int pd, int ph, int pw, float drop_p, int seed, bool train, "
     "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy, "
     "Tensor? seed_dev=None) -> ()", _bn_act_bwd)
+tap_gather = _define("tap_gather(Tensor src, int cs, Tensor(a!) dst, int kd, int kh, int kw, int sign) -> ()",
+                     _tap_gather)
 channel_sum = _define("channel_sum(Tensor x, Tensor(a!) out) -> ()", _channel_sum)
 upsample2x_fwd = _define("upsample2x_fwd(Tensor x, Tensor(a!) out) -> ()", _upsample2x_fwd)
 upsample2x_bwd = _define("upsample2x_bwd(Tensor gout, Tensor(a!) gx) -> ()", _upsample2x_bwd)
@@ -400,6 +410,48 @@ def _wshape(weight):
     return tuple(weight.shape)
 
 
+_FOLD_X = {(1, 3, 3, 3), (1, 3, 3, 1), (1, 3, 3, 2), (3, 1, 1, 1), (3, 1, 1, 2), (3, 1, 1, 3), (3, 1, 1, 4)}
+_FOLD_Y = {(3, 3, 3, 1), (1, 3, 3, 1), (1, 3, 3, 2), (1, 3, 3, 3), (3, 1, 1, 1), (3, 1, 1, 2), (3, 1, 1, 3),
+           (3, 1, 1, 4)}
+
+
+def wgrad_fold_mode(cin, cout, kd, kh, kw):
+    """Thin convs (taps * channels <= 32 on one side): fold the taps into that side's channel dimension
+    (vfd_tap_gather) and take the weight gradient as ONE 1x1x1 wgrad. "x": gather the input, "y": gather dy."""
+    if kd * kh * kw == 1 or os.environ.get("VFD_WGRAD_FOLD", "1") == "0":
+        return None
+    if (kd, kh, kw, cin) in _FOLD_X:
+        return "x"
+    if (kd, kh, kw, cout) in _FOLD_Y:
+        return "y"
+    return None
+
+
+def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
+    """-> fp32 weight gradient [cout, cin, taps]"""
+    taps = kd * kh * kw
+    N, D, H, W = g.shape[:4]
+    cs = cin if mode == "x" else cout
+    cols = round_up(taps * cs, 8)
+    folded = cl_empty(N, D, H, W, cols, g.device)
+
+    def run():
+        if mode == "x":     # X'[v][t*cin+ci] = x[v+off(t)][ci];  acc[0][t*cin+ci][co]
+            tap_gather(x, cs, folded, kd, kh, kw, 1)
+            conv3d_wgrad(g, cout, folded, taps * cin, acc, 1, 1, 1, False)
+        else:               # Y'[u][t*cout+co] = dy[u-off(t)][co]; acc[0][ci][t*cout+co]
+            tap_gather(g, cs, folded, kd, kh, kw, -1)
+            conv3d_wgrad(folded, taps * cout, x, cin, acc, 1, 1, 1, False)
+
+    if mode == "x":
+        acc = torch.zeros(1, cols, round_up(cout, 32), dtype=torch.float32, device=g.device)
+        _timed("conv_wgrad", flops, run)
+        return acc[0, :taps * cin, :cout].reshape(taps, cin, cout).permute(2, 1, 0).contiguous()
+    acc = torch.zeros(1, round_up(cin, 8), round_up(taps * cout, 32), dtype=torch.float32, device=g.device)
+    _timed("conv_wgrad", flops, run)
+    return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1).contiguous()
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
     training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
@@ -445,11 +497,15 @@ class ConvFn(torch.autograd.Function):
                                       CONV_IMPL_DIRECT))
         if ctx.needs_input_grad[1]:
             taps = kd * kh * kw
-            acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
-            _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
-            gw = torch.empty_like(weight, dtype=torch.float32)
-            unpack_wgrad(acc, gw)
+            fold = None if CONV_IMPL_DIRECT else wgrad_fold_mode(cin, cout, kd, kh, kw)
+            if fold is None:
+                acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+                _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
+                gw = torch.empty_like(weight, dtype=torch.float32)
+                unpack_wgrad(acc, gw)
+            else:
+                gw = _folded_wgrad(fold, g, x, cin, cout, kd, kh, kw, flops).reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             if ctx.bias_zero:
                 gb = torch.zeros(cout, dtype=torch.float32, device=g.device)
