@@ -507,13 +507,16 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     uint8_t* stg = smem_stage + static_cast<size_t>(ew) * p.stage_bufs * p.stage_bytes;
     const bool do_stats = p.stats != nullptr;
-    float ssum[kMaxChunks], ssq[kMaxChunks];
+    // statistics: lane = (column pair cp, row parity rh); it sums columns 2cp, 2cp+1 over rows rh, rh+2, ...
+    float ssum[kMaxChunks][2], ssq[kMaxChunks][2];
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) ssum[i] = ssq[i] = 0.f;
-    // column-read offsets for the statistics (64-byte swizzle: chunk index ^ ((row >> 1) & 3))
+    for (int i = 0; i < kMaxChunks; ++i) ssum[i][0] = ssum[i][1] = ssq[i][0] = ssq[i][1] = 0.f;
+    const int cp = lane & 15, rh = lane >> 4;
+    // byte offset of the pair inside a staged row for each swizzle phase (64-byte swizzle: 16-byte chunk
+    // index ^ ((row >> 1) & 3)); rows 2i + rh have phase i & 3
     uint32_t coff[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) coff[x] = ((((lane >> 3) ^ x) << 4) + ((lane & 7) << 1));
+    for (int x = 0; x < 4; ++x) coff[x] = rh * 64 + ((((cp >> 2) ^ x) << 4) + ((cp & 3) << 2));
     int as = 0, buf = 0;
     uint32_t aph = 0;
     int iter = 0;
@@ -585,25 +588,37 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               bulk_commit_group();
             }
             if (do_stats) {
-              // lane j sums column j of the staged chunk over the warp's valid rows
               float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
               const uint8_t* colp = sb;
+              if (vmask == 0xffffffffu) {
 #pragma unroll
-              for (int r = 0; r < 32; r += 2) {
-                const uint32_t u0 = *reinterpret_cast<const uint16_t*>(colp + r * 64 + coff[(r >> 1) & 3]);
-                const uint32_t u1 = *reinterpret_cast<const uint16_t*>(colp + (r + 1) * 64 + coff[(r >> 1) & 3]);
-                const float f0 = ((vmask >> r) & 1u) ? __uint_as_float(u0 << 16) : 0.f;
-                const float f1 = ((vmask >> (r + 1)) & 1u) ? __uint_as_float(u1 << 16) : 0.f;
-                a0 += f0;
-                a1 += f1;
-                q0 = fmaf(f0, f0, q0);
-                q1 = fmaf(f1, f1, q1);
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(colp + i * 128 + coff[i & 3]);
+                  const float f0 = __uint_as_float(u << 16), f1 = __uint_as_float(u & 0xFFFF0000u);
+                  a0 += f0;
+                  a1 += f1;
+                  q0 = fmaf(f0, f0, q0);
+                  q1 = fmaf(f1, f1, q1);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(colp + i * 128 + coff[i & 3]);
+                  const bool rv = (vmask >> (2 * i + rh)) & 1u;
+                  const float f0 = rv ? __uint_as_float(u << 16) : 0.f, f1 = rv ? __uint_as_float(u & 0xFFFF0000u) : 0.f;
+                  a0 += f0;
+                  a1 += f1;
+                  q0 = fmaf(f0, f0, q0);
+                  q1 = fmaf(f1, f1, q1);
+                }
               }
 #pragma unroll
               for (int i = 0; i < kMaxChunks; ++i)
                 if (i == ch) {
-                  ssum[i] += a0 + a1;
-                  ssq[i] += q0 + q1;
+                  ssum[i][0] += a0;
+                  ssum[i][1] += a1;
+                  ssq[i][0] += q0;
+                  ssq[i][1] += q1;
                 }
             }
             if (p.stage_bufs == 2) buf ^= 1;
@@ -623,8 +638,10 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int i = 0; i < kMaxChunks; ++i)
         if (i < p.nchunks) {
-          atomicAdd(&s_sum[i * 32 + lane], ssum[i]);
-          atomicAdd(&s_sq[i * 32 + lane], ssq[i]);
+          atomicAdd(&s_sum[i * 32 + 2 * cp], ssum[i][0]);
+          atomicAdd(&s_sum[i * 32 + 2 * cp + 1], ssum[i][1]);
+          atomicAdd(&s_sq[i * 32 + 2 * cp], ssq[i][0]);
+          atomicAdd(&s_sq[i * 32 + 2 * cp + 1], ssq[i][1]);
         }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       const int j = ew * 32 + lane;

@@ -395,10 +395,11 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   }
 }
 
+// ---- backward, 8-channel window-per-thread mapping (un-pooled and depth-only pooled tensors)
 // Shared front end of the two backward passes: loads y / g_full for the window's voxels and the
 // window's g_pool, and turns them into the gradient w.r.t. the BatchNorm output.
 template <int PD, int PH, int PW, bool DROP>
-struct BwdWindow {
+struct BwdWindow8 {
   static constexpr int NV = PD * PH * PW;
   Window<PD, PH, PW> w;
   uint4 ry[NV], rg[NV], rp;
@@ -451,7 +452,7 @@ struct BwdWindow {
 // Pass 1 of BN backward: per-channel sum(g) and sum(g * xhat).
 template <int PD, int PH, int PW, bool DROP>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
+bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          float slope, const bf16* __restrict__ g_full, long long gf_ld,
@@ -487,7 +488,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
     if (g_pool != nullptr) g_pool += cg * 8;
     const bool has_full = g_full != nullptr;
     for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
-      BwdWindow<PD, PH, PW, DROP> bw[U];
+      BwdWindow8<PD, PH, PW, DROP> bw[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
         bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
@@ -515,28 +516,10 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
 }
 
-// sums -> dgamma, dbeta and the two per-channel means used by pass 2; clears the accumulator.
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, int Cvalid, long long V,
-                                       int train, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ c1,
-                                       float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double sg = sums[c], sgx = sums[C + c];
-  if (c < Cvalid) {
-    dbeta[c] = (float)sg;
-    dgamma[c] = (float)sgx;
-  }
-  c1[c] = train ? (float)(sg / (double)V) : 0.f;
-  c2[c] = train ? (float)(sgx / (double)V) : 0.f;
-  sums[c] = 0.0;
-  sums[C + c] = 0.0;
-}
-
 // Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2) = scale * g + (kb + kc * xhat)
 template <int PD, int PH, int PW, bool DROP>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
+bn_act_bwd8_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         float slope, const bf16* __restrict__ g_full, long long gf_ld,
@@ -571,7 +554,7 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   if (g_pool != nullptr) g_pool += cg * 8;
   const bool has_full = g_full != nullptr;
   for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
-    BwdWindow<PD, PH, PW, DROP> bw[U];
+    BwdWindow8<PD, PH, PW, DROP> bw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
@@ -586,6 +569,253 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
         for (int j = 0; j < 8; ++j)
           o[j] = fmaf(sc[j], gv[j], fmaf(kc[j], fmaf(yv[j], is[j], nm[j]), kb[j]));
         store8(dy + (size_t)bw[u].w.vox[v] * dy_ld, o);
+      }
+  }
+}
+
+// ---- backward for spatially pooled tensors (ph = pw = 2). One thread = (plane window of PH x PW voxels of
+// one d-plane, 4-channel group): half the
+// per-channel state of the 8-channel forward mapping and at most four voxels per window, which keeps the
+// kernels under 85 registers without spills (24 resident warps per SM) -- they are latency bound, not issue bound. Depth
+// pooling (pd = 2) only changes which pooled-gradient element a plane reads.
+struct BwdGeom {
+  int N, D, H, W, C;
+  int WH, WW;        // windows per plane axis (ceil)
+  int QD, QH, QW;    // pooled extents (floor)
+  int pd;            // depth pooling factor (1 or 2)
+  unsigned nwin;     // N * D * WH * WW
+  FastDiv fWW, fWH, fD;
+  float inv_win;     // 1 / (pd * PH * PW)
+};
+
+__device__ __forceinline__ void unpack4(const uint2& u, float* v) {
+  v[0] = __uint_as_float(u.x << 16);
+  v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(u.y << 16);
+  v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint2 ldg8(const bf16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void store4(bf16* p, const float* v) {
+  uint2 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <int PH, int PW, bool DROP>
+struct BwdWindow {
+  static constexpr int NV = PH * PW;
+  unsigned vox[NV];
+  bool ok[NV], pool_ok;
+  uint2 ry[NV], rg[NV], rp;
+
+  __device__ __forceinline__ void load(unsigned win, bool wv, const BwdGeom& g, const bf16* __restrict__ y,
+                                       long long y_ld, const bf16* __restrict__ g_full, long long gf_ld,
+                                       const bf16* __restrict__ g_pool, long long gp_ld) {
+    unsigned pvox;
+    if (NV == 1 && g.pd == 1) {
+      vox[0] = win;
+      ok[0] = wv;
+      pool_ok = wv && g_pool != nullptr;
+      pvox = win;
+    } else {
+      const unsigned w0 = wv ? win : 0u;
+      const unsigned t = fdiv(w0, g.fWW);
+      const int ww = w0 - t * g.WW;
+      const unsigned t2 = fdiv(t, g.fWH);
+      const int wh = t - t2 * g.WH;
+      const unsigned n = fdiv(t2, g.fD);
+      const int d = t2 - n * g.D;
+      const int wd = g.pd == 2 ? (d >> 1) : d;
+      pool_ok = wv && g_pool != nullptr && wd < g.QD && wh < g.QH && ww < g.QW;
+      pvox = ((n * g.QD + wd) * g.QH + wh) * g.QW + ww;
+      const unsigned base = ((n * g.D + d) * g.H + wh * PH) * g.W + ww * PW;
+#pragma unroll
+      for (int b = 0; b < PH; ++b)
+#pragma unroll
+        for (int c = 0; c < PW; ++c) {
+          ok[b * PW + c] = wv && (PH == 1 || wh * PH + b < g.H) && (PW == 1 || ww * PW + c < g.W);
+          vox[b * PW + c] = base + b * g.W + c;
+        }
+    }
+    if (pool_ok) rp = ldg8(g_pool + (size_t)pvox * gp_ld);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (ok[v]) {
+        ry[v] = ldg8(y + (size_t)vox[v] * y_ld);
+        if (g_full != nullptr) rg[v] = ldg8(g_full + (size_t)vox[v] * gf_ld);
+      }
+  }
+  // gradient w.r.t. z = y*scale+shift for voxel v (yv receives the unpacked y)
+  __device__ __forceinline__ void grad(int v, bool has_full, const float* sc, const float* sf, float slope,
+                                       float inv_win, float drop_p, unsigned long long seed, int cg4, float* yv,
+                                       float* gv) const {
+    unpack4(ry[v], yv);
+    if (has_full) {
+      unpack4(rg[v], gv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gv[j] = 0.f;
+    }
+    if (pool_ok) {
+      float t[4];
+      unpack4(rp, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gv[j] = fmaf(t[j], inv_win, gv[j]);
+    }
+    if (DROP) {
+      float m[8];
+      dropout8(seed, (long long)vox[v], cg4 >> 1, drop_p, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gv[j] *= m[(cg4 & 1) * 4 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z = fmaf(yv[j], sc[j], sf[j]);
+      gv[j] = z > 0.f ? gv[j] : gv[j] * slope;
+    }
+  }
+};
+
+// Pass 1 of BN backward: per-channel sum(g) and sum(g * xhat). The loop accumulates sum(g) and sum(g * y);
+// sum(g * xhat) = invstd * (sum(g * y) - mean * sum(g)) is formed once per thread at the end.
+template <int PH, int PW, bool DROP>
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         float slope, const bf16* __restrict__ g_full, long long gf_ld,
+                         const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
+                         unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                         double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][C]
+  constexpr int NV = PH * PW;
+  constexpr int U = 8 / NV;
+  if (DROP && seed_dev != nullptr) seed += *seed_dev;
+  const int C = g.C;
+  const int CG = C >> 2;
+  const int rpi = 256 / CG;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  if (tid < rpi * CG) {
+    const int cg = tid % CG, wl = tid / CG;
+    const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
+    const unsigned w_begin = blockIdx.x * per_block;
+    const unsigned w_end = min(g.nwin, w_begin + per_block);
+    float sc[4], sf[4], s1[4], sy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = __ldg(scale + cg * 4 + j);
+      sf[j] = __ldg(shift + cg * 4 + j);
+      s1[j] = sy[j] = 0.f;
+    }
+    y += cg * 4;
+    if (g_full != nullptr) g_full += cg * 4;
+    if (g_pool != nullptr) g_pool += cg * 4;
+    const bool has_full = g_full != nullptr;
+    for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+      BwdWindow<PH, PW, DROP> bw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!bw[u].ok[v]) continue;
+          float yv[4], gv[4];
+          bw[u].grad(v, has_full, sc, sf, slope, g.inv_win, drop_p, seed, cg, yv, gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s1[j] += gv[j];
+            sy[j] = fmaf(gv[j], yv[j], sy[j]);
+          }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float is = __ldg(invstd + cg * 4 + j), mu = __ldg(mean + cg * 4 + j);
+      atomicAdd(&sh[cg * 4 + j], s1[j]);
+      atomicAdd(&sh[C + cg * 4 + j], is * (sy[j] - mu * s1[j]));
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+// sums -> dgamma, dbeta and the two per-channel means used by pass 2; clears the accumulator.
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, int Cvalid, long long V,
+                                       int train, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ c1,
+                                       float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sg = sums[c], sgx = sums[C + c];
+  if (c < Cvalid) {
+    dbeta[c] = (float)sg;
+    dgamma[c] = (float)sgx;
+  }
+  c1[c] = train ? (float)(sg / (double)V) : 0.f;
+  c2[c] = train ? (float)(sgx / (double)V) : 0.f;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+// Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2) = scale * g + a2 * y + b2 with
+// a2 = -scale * c2 * invstd, b2 = -scale * (c1 - c2 * mean * invstd).
+template <int PH, int PW, bool DROP>
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        float slope, const bf16* __restrict__ g_full, long long gf_ld,
+                        const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
+                        unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                        const float* __restrict__ c1, const float* __restrict__ c2, bf16* __restrict__ dy,
+                        long long dy_ld) {
+  constexpr int NV = PH * PW;
+  constexpr int U = 8 / NV;
+  if (DROP && seed_dev != nullptr) seed += *seed_dev;
+  const int CG = g.C >> 2;
+  const int rpi = 256 / CG;
+  const int tid = threadIdx.x;
+  if (tid >= rpi * CG) return;
+  const int cg = tid % CG, wl = tid / CG;
+  const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
+  const unsigned w_begin = blockIdx.x * per_block;
+  const unsigned w_end = min(g.nwin, w_begin + per_block);
+  float sc[4], sf[4], a2[4], b2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = __ldg(scale + cg * 4 + j);
+    sf[j] = __ldg(shift + cg * 4 + j);
+    const float is = __ldg(invstd + cg * 4 + j), mu = __ldg(mean + cg * 4 + j);
+    const float k1 = __ldg(c1 + cg * 4 + j), k2 = __ldg(c2 + cg * 4 + j);
+    a2[j] = -sc[j] * k2 * is;
+    b2[j] = -sc[j] * (k1 - k2 * mu * is);
+  }
+  y += cg * 4;
+  dy += cg * 4;
+  if (g_full != nullptr) g_full += cg * 4;
+  if (g_pool != nullptr) g_pool += cg * 4;
+  const bool has_full = g_full != nullptr;
+  for (unsigned wb = w_begin + wl; wb < w_end; wb += rpi * U) {
+    BwdWindow<PH, PW, DROP> bw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      bw[u].load(wb + u * rpi, wb + u * rpi < w_end, g, y, y_ld, g_full, gf_ld, g_pool, gp_ld);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!bw[u].ok[v]) continue;
+        float yv[4], gv[4], o[4];
+        bw[u].grad(v, has_full, sc, sf, slope, g.inv_win, drop_p, seed, cg, yv, gv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(a2[j], yv[j], b2[j]));
+        store4(dy + (size_t)bw[u].vox[v] * dy_ld, o);
       }
   }
 }
@@ -1127,25 +1357,73 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   if (int e = check_cl(dy, dy_ld, C, "bn_act_bwd: bad output")) return e;
   if (g_full && check_cl(g_full, gf_ld, C, "bn_act_bwd: bad full-resolution gradient")) return VFD_ERR_ARG;
   if (g_pool && check_cl(g_pool, gp_ld, C, "bn_act_bwd: bad pooled gradient")) return VFD_ERR_ARG;
-  ActGeom g;
-  if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
+  if ((pd != 1 && pd != 2) || (ph != 1 && ph != 2) || ph != pw)
+    return set_error(VFD_ERR_ARG, "bn_act_bwd: pool window must be (1,1,1), (2,2,2), (1,2,2) or (2,1,1)");
+  if (C > 1024) return set_error(VFD_ERR_ARG, "bn_act_bwd: at most 1024 channels");
   const long long V = (long long)N * D * H * W;
   if (V >= (1LL << 31)) return set_error(VFD_ERR_ARG, "bn_act_bwd: more than 2^31 voxels");
   if (V == 0) return 0;
   const bool drop = drop_p > 0.f;
-  const int nvi = 4 / (pd * ph * pw) > 0 ? 4 / (pd * ph * pw) : 1;
-  const int grid = win_grid(g, pd, ph, pw, nvi);
-  VFD_POOL_DISPATCH(bn_act_bwd_reduce_kernel, drop,
-                    (kfn<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(
-                        (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope, (const bf16*)g_full, gf_ld,
-                        (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums)));
-  if (int e = check_launch("bn_act_bwd_reduce")) return e;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
-  if (int e = check_launch("bn_bwd_finalize")) return e;
-  VFD_POOL_DISPATCH(bn_act_bwd_apply_kernel, drop,
-                    (kfn<<<grid, 256, 0, STREAM>>>((const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
-                                                   (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p,
-                                                   seed, seed_dev, c1, c2, (bf16*)dy, dy_ld)));
+  if (drop && (pd != 1 || ph != 1)) return set_error(VFD_ERR_ARG, "dropout is only fused into un-pooled BN+activation");
+  if (ph == 1) {
+    // un-pooled / depth-pooled: 8-channel window-per-thread kernels
+    ActGeom g;
+    if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
+    const int nvi = 4 / (pd * ph * pw) > 0 ? 4 / (pd * ph * pw) : 1;
+    const int grid = win_grid(g, pd, ph, pw, nvi);
+#define VFD_BWD8_LAUNCH(KERNEL, SMEM, ...)                                                             \
+    do {                                                                                                \
+      if (pd == 1) {                                                                                    \
+        if (drop) KERNEL<1, 1, 1, true><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                      \
+        else KERNEL<1, 1, 1, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                          \
+      } else {                                                                                          \
+        KERNEL<2, 1, 1, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                               \
+      }                                                                                                 \
+    } while (0)
+    VFD_BWD8_LAUNCH(bn_act_bwd8_reduce_kernel, 2 * C * sizeof(float), (const bf16*)y, y_ld, g, mean, invstd, scale,
+                    shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums);
+    if (int e = check_launch("bn_act_bwd_reduce")) return e;
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
+    if (int e = check_launch("bn_bwd_finalize")) return e;
+    VFD_BWD8_LAUNCH(bn_act_bwd8_apply_kernel, 0, (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
+                    (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, c1, c2, (bf16*)dy,
+                    dy_ld);
+#undef VFD_BWD8_LAUNCH
+    return check_launch("bn_act_bwd_apply");
+  }
+  BwdGeom g;
+  g.N = N; g.D = D; g.H = H; g.W = W; g.C = C; g.pd = pd;
+  g.WH = (H + ph - 1) / ph; g.WW = (W + pw - 1) / pw;
+  g.QD = D / pd; g.QH = H / ph; g.QW = W / pw;
+  g.nwin = (unsigned)((long long)N * D * g.WH * g.WW);
+  g.fWW = make_fastdiv(g.WW); g.fWH = make_fastdiv(g.WH); g.fD = make_fastdiv(D);
+  g.inv_win = 1.0f / (float)(pd * ph * pw);
+  {
+    const int rpi = 256 / (C / 4);
+    const int per_iter = rpi * (8 / (ph * pw));
+    long long b = ((long long)g.nwin + (long long)per_iter * 4 - 1) / ((long long)per_iter * 4);
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    const int grid = (int)b;
+#define VFD_BWD_LAUNCH(KERNEL, SMEM, ...)                                                              \
+    do {                                                                                                \
+      if (ph == 1) {                                                                                    \
+        if (drop) KERNEL<1, 1, true><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                         \
+        else KERNEL<1, 1, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                             \
+      } else {                                                                                          \
+        KERNEL<2, 2, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                                  \
+      }                                                                                                 \
+    } while (0)
+    VFD_BWD_LAUNCH(bn_act_bwd_reduce_kernel, 2 * C * sizeof(float), (const bf16*)y, y_ld, g, mean, invstd, scale,
+                   shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums);
+    if (int e = check_launch("bn_act_bwd_reduce")) return e;
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, dgamma, dbeta, c1, c2);
+    if (int e = check_launch("bn_bwd_finalize")) return e;
+    VFD_BWD_LAUNCH(bn_act_bwd_apply_kernel, 0, (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
+                   (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, c1, c2, (bf16*)dy,
+                   dy_ld);
+#undef VFD_BWD_LAUNCH
+  }
   return check_launch("bn_act_bwd_apply");
 }
 
