@@ -324,13 +324,31 @@ def main():
         achieved = dd["work"] / (dd["ms"] * 1e-3) / 1e12
         conv_ms = sum(v["ms_per_step"] for v in conv.values())
         conv_flops = sum(v["work"] for v in conv.values()) / psteps
-        roofline = {"bound": "tensor", "kernel": {"conv_fwd": "conv_fwd_tc_kernel (forward)", "conv_dgrad":
-                    "conv_fwd_tc_kernel (dgrad)", "conv_wgrad": "conv_wgrad_tc_kernel"}[dom],
-                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "launches_per_step": dd["launches_per_step"], "avg_launch_ms": dd["ms"] / dd["launches"],
+        kname = {"conv_fwd": "conv_fwd_res_kernel / conv_fwd_tc_kernel (forward)",
+                 "conv_dgrad": "conv_fwd_res_kernel / conv_fwd_tc_kernel (dgrad)",
+                 "conv_wgrad": "conv_wgrad2_kernel (+ tap_gather for folded thin layers)"}[dom]
+        # DRAM bytes per launch of the dominant kernel kind from the committed ncu pass (profiles/), if any
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom)
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                    "peak_source": peaks["source"], "launches_per_step": dd["launches_per_step"],
+                    "avg_launch_ms": dd["ms"] / dd["launches"],
+                    "note": "aggregate over all launches of the dominant conv kernel kind in one step: algorithmic "
+                            "FLOPs / CUDA-event time; most of these launches are thin HBM-bound layers",
                     "all_conv": {"tflops": conv_flops / (conv_ms * 1e-3) / 1e12, "ms_per_step": conv_ms,
                                  "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}}
+        bn = {k: v for k, v in kernels.items() if k in ("bn_act_fwd", "bn_act_bwd")}
+        if bn:
+            bn_bytes = sum(v["work"] for v in bn.values())
+            bn_ms = sum(v["ms"] for v in bn.values())
+            roofline["hbm_kernels"] = {"bound": "hbm", "kernel": "bn_act_fwd / bn_act_bwd_{reduce,apply}",
+                                       "achieved": bn_bytes / (bn_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                       "unit": "GB/s", "frac": bn_bytes / (bn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                       "ms_per_step": bn_ms / psteps}
         for k, v in kernels.items():
             if k.startswith("bn"):
                 v["gbs"] = v["work"] / (v["ms"] * 1e-3) / 1e9
