@@ -136,8 +136,10 @@ VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, flo
  * buffer (out_ld = total channels); backward gathers the gradient of the low-resolution input. */
 VFD_API int vfd_upsample2x_fwd(const void* x, long long x_ld, int N, int D, int H, int W, int C,
                                void* out, long long out_ld, void* stream);
+/* workspace (optional): N*2D*2H*W*C*2 + N*2D*H*W*C*2 bytes of device scratch enable the separable
+ * three-pass adjoint (W, H, D axes; bf16 temporaries); without it a direct gather kernel runs. */
 VFD_API int vfd_upsample2x_bwd(const void* gout, long long go_ld, int N, int D, int H, int W, int C,
-                               void* gx, long long gx_ld, void* stream);
+                               void* gx, long long gx_ld, void* workspace, long long ws_bytes, void* stream);
 
 /* ---- heads and losses ---------------------------------------------------------------------------
  * nn.Sigmoid after conv_last (models/mygannet.py:53,99): logits fp32 [V][ld] column 0 -> predict. */

@@ -31,7 +31,7 @@ SIGNATURES = {
     "vfd_tap_gather": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_channel_sum": [_p, _ll, _i, _ll, _p, _p],
     "vfd_upsample2x_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
-    "vfd_upsample2x_bwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
+    "vfd_upsample2x_bwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _p],
     "vfd_sigmoid_head_fwd": [_p, _ll, _ll, _p, _p],
     "vfd_sigmoid_head_bwd": [_p, _p, _ll, _p, _p],
     "vfd_weighted_bce": [_p, _p, _ll, _f, _f, _p, _p, _p],
@@ -44,7 +44,7 @@ SIGNATURES = {
 _lib = None
 LAUNCHES = 0         # C-ABI compute calls issued by this process
 KERNEL_LAUNCHES = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3}
+_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3}
 
 
 def build(force=False):

@@ -459,7 +459,7 @@ bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                          unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                          double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2][C]
+  __shared__ float part[16 * 256];  // [sum | sum*xhat][channel in group][thread]
   constexpr int NV = PD * PH * PW;
   constexpr int U = NV >= 4 ? 1 : 4 / NV;
   if (DROP && seed_dev != nullptr) seed += *seed_dev;
@@ -467,8 +467,6 @@ bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
   const int CG = C >> 3;
   const int rpi = 256 / CG;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
-  __syncthreads();
   if (tid < rpi * CG) {
     const int cg = tid % CG, wl = tid / CG;
     const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
@@ -506,14 +504,23 @@ bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
           }
         }
     }
+    // block reduction without shared-memory atomics (with few channel groups every thread of the block
+    // would hit the same handful of addresses): stage the partials, then one thread per channel sums them
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], s1[j]);
-      atomicAdd(&sh[C + cg * 8 + j], s2[j]);
+      part[j * 256 + tid] = s1[j];
+      part[(8 + j) * 256 + tid] = s2[j];
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = tid; i < 2 * C; i += 256) {
+    const int which = i >= C, c = which ? i - C : i;
+    const int cgi = c >> 3, j = c & 7;
+    const float* src = part + (which * 8 + j) * 256 + cgi;
+    float acc = 0.f;
+    for (int wl = 0; wl < rpi; ++wl) acc += src[wl * CG];
+    atomicAdd(&sums[i], (double)acc);
+  }
 }
 
 // Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2) = scale * g + (kb + kc * xhat)
@@ -689,7 +696,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                          unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                          double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2][C]
+  __shared__ float part[8 * 256];  // [sum | sum*xhat][channel in group][thread]
   constexpr int NV = PH * PW;
   constexpr int U = 8 / NV;
   if (DROP && seed_dev != nullptr) seed += *seed_dev;
@@ -697,8 +704,6 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
   const int CG = C >> 2;
   const int rpi = 256 / CG;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
-  __syncthreads();
   if (tid < rpi * CG) {
     const int cg = tid % CG, wl = tid / CG;
     const unsigned per_block = (g.nwin + gridDim.x - 1) / gridDim.x;
@@ -737,12 +742,19 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float is = __ldg(invstd + cg * 4 + j), mu = __ldg(mean + cg * 4 + j);
-      atomicAdd(&sh[cg * 4 + j], s1[j]);
-      atomicAdd(&sh[C + cg * 4 + j], is * (sy[j] - mu * s1[j]));
+      part[j * 256 + tid] = s1[j];
+      part[(4 + j) * 256 + tid] = is * (sy[j] - mu * s1[j]);
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = tid; i < 2 * C; i += 256) {
+    const int which = i >= C, c = which ? i - C : i;
+    const int cgi = c >> 2, j = c & 3;
+    const float* src = part + (which * 4 + j) * 256 + cgi;
+    float acc = 0.f;
+    for (int wl = 0; wl < rpi; ++wl) acc += src[wl * CG];
+    atomicAdd(&sums[i], (double)acc);
+  }
 }
 
 // sums -> dgamma, dbeta and the two per-channel means used by pass 2; clears the accumulator.
@@ -986,6 +998,50 @@ upsample2x_bwd_kernel(const bf16* __restrict__ go, long long go_ld, UpGeom g, bf
       }
     }
     store8(gx + (size_t)iv * gx_ld + cg * 8, acc);
+  }
+}
+
+
+// One axis of the adjoint of the separable x2 trilinear upsample: src [outer][2L][inner][C] -> dst [outer][L][inner][C],
+// dst[l] = sum_k wt_k(l) * src[2l - 2 + k]. Three such passes (W, H, D) read 1 + 1/2 + 1/4 of the gradient
+// tensor instead of gathering a 5 x 5 x 5 neighbourhood per low-resolution voxel.
+struct UpAxisGeom {
+  unsigned total;     // outer * L * inner * CG
+  int L, inner, CG;
+  FastDiv fCG, fInner, fL;
+};
+
+__global__ void __launch_bounds__(256)
+upsample_bwd_axis_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long dst_ld,
+                         UpAxisGeom g) {
+  const int L = g.L, OL = 2 * g.L;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < g.total; i += gridDim.x * blockDim.x) {
+    const unsigned r = fdiv(i, g.fCG);
+    const int cg = i - r * g.CG;
+    const unsigned r2 = fdiv(r, g.fInner);
+    const int in = r - r2 * g.inner;
+    const unsigned outer = fdiv(r2, g.fL);
+    const int l = r2 - outer * L;
+    float wts[7];
+    bwd_weights(l, L, wts);
+    uint4 raw[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int o = 2 * l - 2 + k;
+      if (wts[k] != 0.f) raw[k] = ldg16(src + (size_t)((outer * OL + o) * g.inner + in) * src_ld + cg * 8);
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      if (wts[k] == 0.f) continue;
+      float v[8];
+      unpack8(raw[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wts[k], v[j], acc[j]);
+    }
+    store8(dst + (size_t)r * dst_ld + cg * 8, acc);
   }
 }
 
@@ -1487,13 +1543,33 @@ VFD_API int vfd_upsample2x_fwd(const void* x, long long x_ld, int N, int D, int 
   return check_launch("upsample2x_fwd");
 }
 
+static int launch_up_axis(const bf16* src, long long src_ld, bf16* dst, long long dst_ld, long long outer, int L,
+                          long long inner, int C, cudaStream_t stream) {
+  const long long total = outer * L * inner * (C / 8);
+  if (total >= (1LL << 31) || inner >= (1LL << 31)) return set_error(VFD_ERR_ARG, "upsample2x_bwd: more than 2^31 vectors");
+  UpAxisGeom g;
+  g.total = (unsigned)total; g.L = L; g.inner = (int)inner; g.CG = C / 8;
+  g.fCG = make_fastdiv(C / 8); g.fInner = make_fastdiv((uint32_t)inner); g.fL = make_fastdiv(L);
+  upsample_bwd_axis_kernel<<<grid_for(total), 256, 0, stream>>>(src, src_ld, dst, dst_ld, g);
+  return check_launch("upsample2x_bwd_axis");
+}
+
 VFD_API int vfd_upsample2x_bwd(const void* go, long long go_ld, int N, int D, int H, int W, int C,
-                                  void* gx, long long gx_ld, void* stream_) {
+                                  void* gx, long long gx_ld, void* workspace, long long ws_bytes, void* stream_) {
   if (int e = check_cl(go, go_ld, C, "upsample2x_bwd: bad input")) return e;
   if (int e = check_cl(gx, gx_ld, C, "upsample2x_bwd: bad output")) return e;
+  if ((long long)N * D * H * W == 0) return 0;
+  // separable path: W, H, D adjoint passes through two bf16 temporaries in the workspace
+  const long long t1 = (long long)N * 2 * D * 2 * H * W * C * 2, t2 = (long long)N * 2 * D * H * W * C * 2;
+  if (workspace != nullptr && ws_bytes >= t1 + t2 && !(reinterpret_cast<uintptr_t>(workspace) & 15)) {
+    bf16* tmp1 = reinterpret_cast<bf16*>(workspace);
+    bf16* tmp2 = reinterpret_cast<bf16*>(reinterpret_cast<char*>(workspace) + t1);
+    if (int e = launch_up_axis((const bf16*)go, go_ld, tmp1, C, (long long)N * 2 * D * 2 * H, W, 1, C, STREAM)) return e;
+    if (int e = launch_up_axis(tmp1, C, tmp2, C, (long long)N * 2 * D, H, W, C, STREAM)) return e;
+    return launch_up_axis(tmp2, C, (bf16*)gx, gx_ld, N, D, (long long)H * W, C, STREAM);
+  }
   UpGeom g;
   if (int e = fill_up_geom(g, N, D, H, W, C, 1, "upsample2x_bwd: more than 2^31 vectors")) return e;
-  if (g.total == 0) return 0;
   upsample2x_bwd_kernel<<<grid_for(g.total), 256, 0, STREAM>>>((const bf16*)go, go_ld, g, (bf16*)gx, gx_ld);
   return check_launch("upsample2x_bwd");
 }

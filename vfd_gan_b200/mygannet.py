@@ -172,7 +172,7 @@ class SDisc(nn.Module):
         kd = self.gpool.kernel_size[0]
         if feat.shape[1] != kd:
             raise RuntimeError(f"SDisc built for nfr={kd}, got {feat.shape[1]} frames")
-        pooled = feat[..., :c].mean(dim=1, dtype=torch.float32)            # [N, h, w, C]
+        pooled = ops.MeanDimsFn.apply(feat, (1,), c)                         # [N, h, w, C]
         flat = pooled.permute(0, 3, 1, 2).reshape(pooled.shape[0], -1)      # (C, h, w) order like .view()
         cls = self.sigmoid(self.linear(flat))
         return cls.squeeze(1), feat
@@ -209,7 +209,7 @@ class TDisc(nn.Module):
         ks = self.gpool.kernel_size
         if feat.shape[2] != ks[1] or feat.shape[3] != ks[2]:
             raise RuntimeError(f"TDisc built for isize={ks[1]}, got {feat.shape[2]}x{feat.shape[3]}")
-        pooled = feat[..., :c].mean(dim=(2, 3), dtype=torch.float32)       # [N, d, C]
+        pooled = ops.MeanDimsFn.apply(feat, (2, 3), c)                       # [N, d, C]
         flat = pooled.permute(0, 2, 1).reshape(pooled.shape[0], -1)         # (C, d) order like .view()
         cls = self.sigmoid(self.linear(flat))
         return cls.squeeze(1), feat

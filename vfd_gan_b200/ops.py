@@ -193,7 +193,9 @@ def _upsample2x_fwd(x, out):
 
 def _upsample2x_bwd(gout, gx):
     N, D, H, W, C, ld = _check_cl(gx, "upsample2x_bwd output")
-    _lib.call("vfd_upsample2x_bwd", gout.data_ptr(), _ld(gout), N, D, H, W, C, gx.data_ptr(), ld, _stream())
+    ws = torch.empty(N * 2 * D * H * W * C * 2 * 3, dtype=torch.uint8, device=gx.device)   # two bf16 temporaries
+    _lib.call("vfd_upsample2x_bwd", gout.data_ptr(), _ld(gout), N, D, H, W, C, gx.data_ptr(), ld, ws.data_ptr(),
+              ws.numel(), _stream())
 
 
 def _sigmoid_head_fwd(logits, predict):
@@ -630,6 +632,30 @@ class WeightedBceFn(torch.autograd.Function):
     def backward(ctx, g):
         (gpred,) = ctx.saved_tensors
         return gpred * g, None, None
+
+
+class MeanDimsFn(torch.autograd.Function):
+    """fp32 mean of the first `c` channels of a channels-last bf16 tensor over voxel dims `dims` (the global
+    AvgPool3d heads of SDisc / TDisc, models/mygannet.py:133,175). Backward writes the (constant per pooled
+    element) gradient as one bf16 expand instead of autograd's fp32 expand + slice + cast chain."""
+
+    @staticmethod
+    def forward(ctx, feat, dims, c):
+        ctx.shape, ctx.dims, ctx.c = tuple(feat.shape), tuple(dims), c
+        return feat[..., :c].mean(dim=dims, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dims, c = ctx.shape, ctx.dims, ctx.c
+        count = 1
+        for d in dims:
+            count *= shape[d]
+        kept = [s for i, s in enumerate(shape[:-1]) if i not in dims]
+        gb = torch.zeros(*kept, shape[-1], dtype=torch.bfloat16, device=g.device)
+        gb[..., :c] = g / count
+        for d in sorted(dims):
+            gb = gb.unsqueeze(d)
+        return gb.expand(shape).contiguous(), None, None
 
 
 def mse_cl(a, b, valid_channels):
