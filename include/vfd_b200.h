@@ -54,11 +54,14 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
 /* Weight gradient of the same conv (autograd of nn.Conv3d, reached from err_g.backward() /
  * err_d.backward() at models/mygannet.py:311,344):
  *   acc[tap][ci][co] += sum_v dy[v][co] * x[v+tap][ci]     (fp32, red.add across voxel splits)
- * acc is [kd*kh*kw][ci_pad][co_pad] and must be zeroed by the caller; cout / cin are the valid
- * channel counts. */
+ * layout 0: acc is [kd*kh*kw][ci_pad][co_pad]; layout 1: acc is [kd*kh*kw][co_pad][ci_pad] (the kernel that
+ * puts the input channels on the GEMM M dimension; only where vfd_conv3d_wgrad_layout returns 1). acc must
+ * be zeroed by the caller; cout / cin are the valid channel counts. */
 VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
-                             int cin, float* acc, int co_pad, int ci_pad, int N, int D, int H, int W,
+                             int cin, float* acc, int co_pad, int ci_pad, int layout, int N, int D, int H, int W,
                              int kd, int kh, int kw, void* stream);
+/* Accumulator layout (0 or 1) the tcgen05 weight-gradient path wants for this geometry. */
+VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, int H, int W);
 
 /* CUDA-core versions on the same operands; used by the tests to cross-check the tcgen05 kernels. */
 VFD_API int vfd_conv3d_fwd_direct(const void* x, long long x_ld, int cin, const void* w_packed,

@@ -54,13 +54,18 @@ for name in names:
     gx = torch.empty_like(x)
     st = torch.zeros(2 * cout_p, dtype=torch.float64, device=dev)
     acc = torch.zeros(kd * kh * kw, cin_p, ops.round_up(cout, 32), dtype=torch.float32, device=dev)
+    lay = ops.wgrad_layout(cout, cin, kd, kh, kw, H, W)
+    acc3 = torch.zeros(kd * kh * kw, cout_p, ops.round_up(cin, 32), dtype=torch.float32, device=dev)
     kernels = {
         "fwd": lambda: ops.conv3d_fwd(x, pk.fwd, None, y, None, kd, kh, kw, pk.kc_f, cout_p, False),
         "fwd+stats": lambda: ops.conv3d_fwd(x, pk.fwd, None, y, st, kd, kh, kw, pk.kc_f, cout_p, False),
         "dgrad": lambda: ops.conv3d_fwd(gy, pk.dgrad, None, gx, None, kd, kh, kw, pk.kc_d, cin_p, False),
-        "wgrad": lambda: ops.conv3d_wgrad(gy, cout, x, cin, acc, kd, kh, kw, False),
+        "wgrad": lambda: ops.conv3d_wgrad(gy, cout, x, cin, acc, kd, kh, kw, False, 0),
+        "wgrad3": (lambda: ops.conv3d_wgrad(gy, cout, x, cin, acc3, kd, kh, kw, False, 1)) if lay else None,
     }
     for kname, fn in kernels.items():
+        if fn is None:
+            continue
         row = []
         for dbg in FLAGS:
             L.vfd_set_debug(dbg)

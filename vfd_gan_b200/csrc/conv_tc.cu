@@ -984,6 +984,183 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------ wgrad v3 (swapped)
+// Same data flow as wgrad v2 with the GEMM roles swapped: M = 128 INPUT channels (A = the X halo plane, row-
+// shifted per tap), N = co_n OUTPUT channels (B = dY), K = voxels. An SS-mode MMA re-reads its 128-row A tile
+// from shared memory for every K16 step (32 cycles) whatever N is, so the wide dimension belongs on N: with
+// N = cout (up to 256) instead of a TMEM-limited ci_n = 512 / 9 taps the same FLOPs take ~1.6-2.3x fewer MMA
+// cycles on the decoder's spatial convs. TMEM holds `tpc` taps x co_n columns; the 9 spatial taps are split
+// over `tgroups` CTAs. Accumulates into acc laid out [tap][co_pad][ci_pad] (lanes = consecutive ci).
+struct Wg3Params {
+  int N, D, H, W, tilesW, tilesH;
+  int kd;
+  int cout, cin;
+  int ci_tiles;        // tiles of 128 input channels (GEMM M)
+  int co_tiles, co_n;  // tiles of co_n output channels (GEMM N), co_n % 16 == 0, <= 256
+  int tpc, tgroups;    // spatial taps per CTA / number of tap groups
+  int nbY;             // 64-channel dY boxes per stage
+  int splits, stages, tmem_cols;
+  int plane_bytes, plane_stride, stage_bytes;
+  int co_pad, ci_pad;
+  int dbg;
+  float* acc;
+};
+
+template <int KHW>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ Wg3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ uint64_t acc_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  int wi = blockIdx.x;
+  const int tg = wi % p.tgroups;
+  wi /= p.tgroups;
+  const int a = wi % p.kd;
+  wi /= p.kd;
+  const int nt = wi % p.co_tiles;
+  wi /= p.co_tiles;
+  const int mt = wi % p.ci_tiles;
+  const int split = wi / p.ci_tiles;
+
+  constexpr int KT = KHW * KHW;
+  constexpr int PWk = 8 + KHW - 1;
+  const int t0 = tg * p.tpc;
+  const int ntaps = min(p.tpc, KT - t0);
+  const int chunks = p.N * p.D * p.tilesH * p.tilesW;
+  const int per = (chunks + p.splits - 1) / p.splits;
+  const int c_begin = split * per;
+  const int c_end = min(chunks, c_begin + per);
+  const int ci0 = mt * 128;
+  const int co0 = nt * p.co_n;
+  const int nx = min(2, (p.cin - ci0 + 63) / 64);                   // X boxes with valid channels
+  const int ny = min(p.nbY, (p.cout - co0 + 63) / 64);              // dY boxes with valid channels
+  const bool has_work = c_begin < c_end;
+  uint8_t* smem_y_off = nullptr;
+  (void)smem_y_off;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        int t = c;
+        const int w0 = (t % p.tilesW) * 8;
+        t /= p.tilesW;
+        const int h0 = (t % p.tilesH) * 16;
+        t /= p.tilesH;
+        const int d = t % p.D;
+        const int n = t / p.D;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sx = smem + static_cast<size_t>(s) * p.stage_bytes;
+        uint8_t* sy = sx + 2 * p.plane_stride;
+        if (p.dbg & 1) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_expect_tx(&full_bar[s], nx * p.plane_bytes + ny * kWgBoxBytes);
+          for (int i = 0; i < nx; ++i)
+            tma_load_5d(&tmX, &full_bar[s], sx + static_cast<size_t>(i) * p.plane_stride, ci0 + i * 64,
+                        w0 - KHW / 2, h0 - KHW / 2, d + a - p.kd / 2, n);
+          for (int i = 0; i < ny; ++i)
+            tma_load_5d(&tmDY, &full_bar[s], sy + i * kWgBoxBytes, co0 + i * 64, w0, h0, d, n);
+        }
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {  // warp-uniform MMA issue (see conv_wgrad2_kernel); not guarded by has_work
+      const bool leader = elect_one();
+      const bool issue = leader && !(p.dbg & 2);
+      const uint32_t idesc = idesc_bf16_m128(p.co_n, true, true);
+      const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), p.plane_stride, PWk * 128);
+      const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * p.plane_stride, kWgBoxBytes, 1024);
+      const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
+      const uint32_t stage16 = p.stage_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t alo = alo0 + static_cast<uint32_t>(s) * stage16;
+        const uint32_t blo = blo0 + static_cast<uint32_t>(s) * stage16;
+        const uint32_t accumulate = c > c_begin;
+        for (int t = 0; t < ntaps; ++t) {
+          const int tap = t0 + t;
+          const int b = tap / KHW, cc = tap - b * KHW;
+          const uint32_t at = alo + static_cast<uint32_t>((b * PWk + cc) * 8);  // tap shift: rows of 128 B
+          const uint32_t tacc = tmem_base + t * p.co_n;
+          if (issue) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // X advances 2*PWk halo rows per K16, dY advances 2 h-rows = 2048 B
+              umma_bf16(tacc, desc_join(at + 16 * PWk * k, ahi), desc_join(blo + 128 * k, bhi), idesc,
+                        k == 0 ? accumulate : 1u);
+          }
+        }
+        if (leader) umma_commit(&empty_bar[s]);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (leader) umma_commit(&acc_full);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const int ci = ci0 + q * 32 + lane;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int t = 0; t < ((p.dbg & 4) ? 0 : ntaps); ++t) {
+      const int tap = a * KT + t0 + t;
+      for (int c = 0; c < p.co_n; c += 16) {
+        float v[16];
+        tmem_ld16(tq + t * p.co_n + c, v);
+        if (ci < p.cin) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = co0 + c + i;
+            if (co < p.cout) atomicAdd(p.acc + (static_cast<size_t>(tap) * p.co_pad + co) * p.ci_pad + ci, v[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1249,6 +1426,37 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   return 0;
 }
 
+// MMA-cycle model of one (tap, K16 step) of the weight-gradient GEMM: tiles x (A re-read 32 + N/4 cycles).
+struct WgradPlan {
+  int swap;                 // 1: M = input channels (conv_wgrad3_kernel), acc is [tap][co][ci]
+  int ci_tiles, ci_n;       // v2: N tiling of the input channels
+  int co_tiles, co_n;       // v3: N tiling of the output channels
+  int tpc, tgroups;
+};
+static WgradPlan plan_wgrad(int cout, int cin, int kh) {
+  WgradPlan w;
+  const int khw = kh * kh;
+  const int cin16 = (cin + 15) & ~15, cout16 = (cout + 15) & ~15;
+  int max_n = (512 / khw) & ~15;
+  if (max_n > 256) max_n = 256;
+  w.ci_tiles = (cin16 + max_n - 1) / max_n;
+  w.ci_n = (((cin16 + w.ci_tiles - 1) / w.ci_tiles) + 15) & ~15;
+  const double cost2 = (double)((cout + 127) / 128) * w.ci_tiles * (32.0 + w.ci_n / 4.0);
+  w.co_tiles = (cout16 + 191) / 192;   // <= 3 dY boxes per stage, so two pipeline stages fit in shared memory
+  w.co_n = (((cout16 + w.co_tiles - 1) / w.co_tiles) + 15) & ~15;
+  w.tpc = 512 / w.co_n;
+  if (w.tpc > khw) w.tpc = khw;
+  w.tgroups = (khw + w.tpc - 1) / w.tpc;
+  const double cost3 = (double)((cin + 127) / 128) * w.co_tiles * (32.0 + w.co_n / 4.0);
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VFD_CONV_WGRAD3");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  w.swap = enabled && kh == 3 && cost3 < 0.85 * cost2;
+  return w;
+}
+
 // VFD_CONV_WGRAD2=0 disables the multi-tap halo wgrad kernel (debug / A-B timing)
 static bool wgrad2_enabled() {
   static int mode = -1;
@@ -1339,14 +1547,77 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
   return launch_fwd<16>(tmA, tmB, p, stream);
 }
 
+static bool wgrad_halo_ok(int H, int W, int kh, int kw) {
+  const int tilesW = (W + 7) / 8, tilesH = (H + 15) / 16;
+  const double fill = (double)W * H / ((double)tilesW * 8 * tilesH * 16);
+  return fill >= 0.7 && kh == kw;
+}
+
+VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, int H, int W) {
+  (void)kd;
+  if ((kh != 1 && kh != 3) || kh != kw || !wgrad2_enabled() || !wgrad_halo_ok(H, W, kh, kw)) return 0;
+  return plan_wgrad(cout, cin, kh).swap;
+}
+
+static int launch_wgrad3(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin,
+                         float* acc, int co_pad, int ci_pad, int N, int D, int H, int W, int kd, int kh,
+                         const WgradPlan& w, cudaStream_t stream) {
+  Wg3Params q;
+  q.N = N; q.D = D; q.H = H; q.W = W;
+  q.tilesW = (W + 7) / 8; q.tilesH = (H + 15) / 16;
+  q.kd = kd; q.cout = cout; q.cin = cin;
+  q.ci_tiles = (cin + 127) / 128;
+  q.co_tiles = w.co_tiles; q.co_n = w.co_n; q.tpc = w.tpc; q.tgroups = w.tgroups;
+  q.nbY = (w.co_n + 63) / 64;
+  q.plane_bytes = (16 + kh - 1) * (8 + kh - 1) * 128;
+  q.plane_stride = (q.plane_bytes + 1023) & ~1023;
+  q.stage_bytes = 2 * q.plane_stride + q.nbY * kWgBoxBytes;
+  int stages = kSmemBudget / q.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(VFD_ERR_ARG, "conv3d_wgrad: swapped tile does not fit in shared memory");
+  q.stages = stages;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < q.tpc * q.co_n) q.tmem_cols *= 2;
+  const long long chunks = (long long)N * D * q.tilesH * q.tilesW;
+  const long long base = (long long)kd * q.ci_tiles * q.co_tiles * q.tgroups;
+  long long splits = (2LL * num_sms()) / base;
+  if (splits < 1) splits = (base <= num_sms()) ? num_sms() / base : 1;
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  q.splits = (int)splits;
+  q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+  const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
+  CUtensorMap tmDY, tmX;
+  if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
+  if (int e = make_act_map(&tmX, x, x_ld, x_ch, N, D, H, W, 64, 8 + kh - 1, 16 + kh - 1, 1, 1)) return e;
+  auto kfn = conv_wgrad3_kernel<3>;
+  static bool attr3 = false;
+  if (!attr3) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad3)");
+    attr3 = true;
+  }
+  size_t smem = (size_t)stages * q.stage_bytes + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  kfn<<<(unsigned)(base * q.splits), kWgThreads, smem, stream>>>(tmDY, tmX, q);
+  return check_launch("conv_wgrad3");
+}
+
 VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const void* x,
-                                long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int N,
+                                long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int layout, int N,
                                 int D, int H, int W, int kd, int kh, int kw, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
   if (co_pad < cout || ci_pad < cin) return set_error(VFD_ERR_ARG, "conv3d_wgrad: bad acc padding");
   if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
     return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
+  if (layout == 1) {
+    if (!vfd_conv3d_wgrad_layout(cout, cin, kd, kh, kw, H, W))
+      return set_error(VFD_ERR_ARG, "conv3d_wgrad: layout 1 ([tap][co][ci]) only as reported by vfd_conv3d_wgrad_layout");
+    return launch_wgrad3(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, N, D, H, W, kd, kh,
+                         plan_wgrad(cout, cin, kh), stream);
+  }
+  if (layout != 0) return set_error(VFD_ERR_ARG, "conv3d_wgrad: layout must be 0 or 1");
   {
     const int tilesW = (W + 7) / 8, tilesH = (H + 15) / 16;
     const double fill = (double)W * H / ((double)tilesW * 8 * tilesH * 16);

@@ -113,12 +113,24 @@ def _conv3d_fwd(x, w_packed, bias, out, stats, kd, kh, kw, kc, out_cols, direct)
                   kh, kw, kc, _stream())
 
 
-def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct):
+def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
-    taps, ci_pad, co_pad = acc.shape
-    _lib.call("vfd_conv3d_wgrad_direct" if direct else "vfd_conv3d_wgrad", dy.data_ptr(), dy_ld, cout,
-              x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad, ci_pad, N, D, H, W, kd, kh, kw, _stream())
+    if layout == 1:
+        taps, co_pad, ci_pad = acc.shape
+    else:
+        taps, ci_pad, co_pad = acc.shape
+    if direct:
+        _lib.call("vfd_conv3d_wgrad_direct", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(),
+                  co_pad, ci_pad, N, D, H, W, kd, kh, kw, _stream())
+    else:
+        _lib.call("vfd_conv3d_wgrad", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
+                  ci_pad, layout, N, D, H, W, kd, kh, kw, _stream())
+
+
+def wgrad_layout(cout, cin, kd, kh, kw, H, W):
+    """Accumulator layout the tcgen05 wgrad wants: 0 = [tap][ci][co], 1 = [tap][co][ci] (swapped GEMM roles)."""
+    return int(_lib.lib().vfd_conv3d_wgrad_layout(cout, cin, kd, kh, kw, H, W))
 
 
 def _pack_ncdhw(src, dst, C, replicate):
@@ -236,8 +248,8 @@ conv3d_fwd = _define(
     "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
 conv3d_wgrad = _define(
-    "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct) -> ()",
-    _conv3d_wgrad)
+    "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
+    "int layout=0) -> ()", _conv3d_wgrad)
 pack_ncdhw = _define("pack_ncdhw(Tensor src, Tensor(a!) dst, int C, bool replicate) -> ()", _pack_ncdhw)
 unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack_ncdhw)
 pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
@@ -502,10 +514,16 @@ class ConvFn(torch.autograd.Function):
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             fold = None if CONV_IMPL_DIRECT else wgrad_fold_mode(cin, cout, kd, kh, kw)
             if fold is None:
-                acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
-                _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
-                gw = torch.empty_like(weight, dtype=torch.float32)
-                unpack_wgrad(acc, gw)
+                layout = 0 if CONV_IMPL_DIRECT else wgrad_layout(cout, cin, kd, kh, kw, H, W)
+                if layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
+                    acc = torch.zeros(taps, round_up(cout, 8), round_up(cin, 32), dtype=torch.float32, device=g.device)
+                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1))
+                    gw = acc[:, :cout, :cin].permute(1, 2, 0).contiguous().reshape(weight.shape)
+                else:
+                    acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
+                    gw = torch.empty_like(weight, dtype=torch.float32)
+                    unpack_wgrad(acc, gw)
             else:
                 gw = _folded_wgrad(fold, g, x, cin, cout, kd, kh, kw, flops).reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
