@@ -1161,6 +1161,196 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------ wgrad, temporal (3x1x1)
+// Weight gradient of the temporal convs: dW[a][co][ci] = sum_v dY[v][co] * X[v + (a-1)*H*W][ci]. A CTA walks
+// whole (n, h-tile, w-tile) columns along d and keeps a ring of pipeline stages; stage j of a column holds the
+// X tile of plane j and the dY tile of plane j-1. Output plane d = j-1 then finds X_{d-1}, X_d, X_{d+1} in the
+// stages j-2, j-1, j and dY_d in stage j, so every X and dY tile is loaded exactly once (the per-tap CTAs of
+// conv_wgrad2_kernel read each of them three times through L2). Three TMEM accumulators (one per tap).
+struct WgtParams {
+  int N, D, H, W, tilesW, tilesH;
+  int cout, cin;
+  int co_tiles, ci_tiles, ci_n;
+  int na, nb;            // 64-channel dY / X boxes per stage
+  int splits, stages, tmem_cols, stage_bytes;
+  int co_pad, ci_pad;
+  int dbg;
+  float* acc;            // [3][ci_pad][co_pad]
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                    const __grid_constant__ WgtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ uint64_t acc_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  int wi = blockIdx.x;
+  const int ct = wi % p.ci_tiles;
+  wi /= p.ci_tiles;
+  const int mt = wi % p.co_tiles;
+  const int split = wi / p.co_tiles;
+
+  const int columns = p.N * p.tilesH * p.tilesW;
+  const int per = (columns + p.splits - 1) / p.splits;
+  const int col_begin = split * per;
+  const int col_end = min(columns, col_begin + per);
+  const int co0 = mt * 128;
+  const int ci0 = ct * p.ci_n;
+  const int nay = min(p.na, (p.cout - co0 + 63) / 64);   // dY boxes with valid channels
+  const int nbx = min(p.nb, (p.cin - ci0 + 63) / 64);    // X boxes with valid channels
+  const bool has_work = col_begin < col_end;
+  const int D = p.D;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int col = col_begin; col < col_end; ++col) {
+        int t = col;
+        const int w0 = (t % p.tilesW) * 8;
+        t /= p.tilesW;
+        const int h0 = (t % p.tilesH) * 16;
+        const int n = t / p.tilesH;
+        for (int j = 0; j <= D; ++j) {       // stage j: X plane j (j < D) and dY plane j-1 (j >= 1)
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sy = smem + static_cast<size_t>(s) * p.stage_bytes;
+          uint8_t* sx = sy + p.na * kWgBoxBytes;
+          if (p.dbg & 1) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_expect_tx(&full_bar[s], ((j >= 1 ? nay : 0) + (j < D ? nbx : 0)) * kWgBoxBytes);
+            if (j >= 1)
+              for (int i = 0; i < nay; ++i)
+                tma_load_5d(&tmDY, &full_bar[s], sy + i * kWgBoxBytes, co0 + i * 64, w0, h0, j - 1, n);
+            if (j < D)
+              for (int i = 0; i < nbx; ++i)
+                tma_load_5d(&tmX, &full_bar[s], sx + i * kWgBoxBytes, ci0 + i * 64, w0, h0, j, n);
+          }
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {  // warp-uniform MMA issue; not guarded by has_work (see conv_wgrad2_kernel)
+      const bool leader = elect_one();
+      const bool issue = leader && !(p.dbg & 2);
+      const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
+      const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
+      const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + p.na * kWgBoxBytes, kWgBoxBytes, 1024);
+      const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
+      const uint32_t stage16 = p.stage_bytes >> 4;
+      int s = 0;            // ring index of the stage being consumed (stage j)
+      uint32_t ph = 0;
+      uint32_t started0 = 0, started1 = 0, started2 = 0;
+      for (int col = col_begin; col < col_end; ++col) {
+        for (int j = 0; j <= D; ++j) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const int s1 = s == 0 ? p.stages - 1 : s - 1;       // stage j-1
+          const int s2 = s1 == 0 ? p.stages - 1 : s1 - 1;     // stage j-2
+          if (j >= 1) {                                        // output plane d = j-1
+            const int d = j - 1;
+            const uint32_t alo = alo0 + static_cast<uint32_t>(s) * stage16;   // dY_d lives in stage j
+            const uint32_t b0 = blo0 + static_cast<uint32_t>(s2) * stage16;   // X_{d-1}
+            const uint32_t b1 = blo0 + static_cast<uint32_t>(s1) * stage16;   // X_d
+            const uint32_t b2 = blo0 + static_cast<uint32_t>(s) * stage16;    // X_{d+1}
+            const bool t0 = d >= 1, t2 = d + 1 < D;
+            if (issue) {
+              if (t0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  umma_bf16(tmem_base, desc_join(alo + 128 * k, ahi), desc_join(b0 + 128 * k, bhi), idesc,
+                            k == 0 ? started0 : 1u);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem_base + p.ci_n, desc_join(alo + 128 * k, ahi), desc_join(b1 + 128 * k, bhi), idesc,
+                          k == 0 ? started1 : 1u);
+              if (t2) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  umma_bf16(tmem_base + 2 * p.ci_n, desc_join(alo + 128 * k, ahi), desc_join(b2 + 128 * k, bhi),
+                            idesc, k == 0 ? started2 : 1u);
+              }
+            }
+            if (t0) started0 = 1;
+            started1 = 1;
+            if (t2) started2 = 1;
+          }
+          // releases: stage j-2 is no longer needed once plane j-1 has been issued; the last plane of a
+          // column also frees the two younger stages
+          if (leader) {
+            if (j >= 2) umma_commit(&empty_bar[s2]);
+            if (j == D) {
+              if (D >= 1) umma_commit(&empty_bar[s1]);
+              umma_commit(&empty_bar[s]);
+            }
+          }
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+      if (leader) umma_commit(&acc_full);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int a = 0; a < ((p.dbg & 4) ? 0 : 3); ++a) {
+      if (D == 1 && a != 1) continue;   // taps that never received a plane hold no data
+      for (int c = 0; c < p.ci_n; c += 16) {
+        float v[16];
+        tmem_ld16(tq + a * p.ci_n + c, v);
+        if (co < p.cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci0 + c + i;
+            if (ci < p.cin) atomicAdd(p.acc + (static_cast<size_t>(a) * p.ci_pad + ci) * p.co_pad + co, v[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1457,6 +1647,16 @@ static WgradPlan plan_wgrad(int cout, int cin, int kh) {
   return w;
 }
 
+// VFD_CONV_WGRADT=0 disables the temporal ring wgrad kernel (debug / A-B timing)
+static bool wgrad_t_enabled() {
+  static int mode = -1;
+  if (mode == -1) {
+    const char* e = getenv("VFD_CONV_WGRADT");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 // VFD_CONV_WGRAD2=0 disables the multi-tap halo wgrad kernel (debug / A-B timing)
 static bool wgrad2_enabled() {
   static int mode = -1;
@@ -1618,6 +1818,50 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
                          plan_wgrad(cout, cin, kh), stream);
   }
   if (layout != 0) return set_error(VFD_ERR_ARG, "conv3d_wgrad: layout must be 0 or 1");
+  if (kd == 3 && kh == 1 && kw == 1 && wgrad_t_enabled() && wgrad_halo_ok(H, W, 1, 1) && D >= 2) {
+    WgtParams q;
+    q.N = N; q.D = D; q.H = H; q.W = W;
+    q.tilesW = (W + 7) / 8; q.tilesH = (H + 15) / 16;
+    q.cout = cout; q.cin = cin;
+    const int cin16 = (cin + 15) & ~15;
+    const int max_n = 160;                                   // 3 taps x ci_n <= 512 TMEM columns
+    q.ci_tiles = (cin16 + max_n - 1) / max_n;
+    q.ci_n = (((cin16 + q.ci_tiles - 1) / q.ci_tiles) + 15) & ~15;
+    q.co_tiles = (cout + 127) / 128;
+    q.na = cout > 64 ? 2 : 1;
+    q.nb = (q.ci_n + 63) / 64;
+    q.stage_bytes = (q.na + q.nb) * kWgBoxBytes;
+    int stages = kSmemBudget / q.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages >= 4) {
+      q.stages = stages;
+      q.tmem_cols = 32;
+      while (q.tmem_cols < 3 * q.ci_n) q.tmem_cols *= 2;
+      const long long columns = (long long)N * q.tilesH * q.tilesW;
+      const long long base = (long long)q.co_tiles * q.ci_tiles;
+      long long splits = (2LL * num_sms()) / base;
+      if (splits < 1) splits = (base <= num_sms()) ? num_sms() / base : 1;
+      if (splits > columns) splits = columns;
+      if (splits < 1) splits = 1;
+      q.splits = (int)splits;
+      q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+      const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
+      CUtensorMap tmDY, tmX;
+      if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
+      if (int e = make_act_map(&tmX, x, x_ld, x_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
+      static bool attrt = false;
+      if (!attrt) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             224 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_t)");
+        attrt = true;
+      }
+      size_t smem = (size_t)stages * q.stage_bytes + 1024;
+      if (smem < 120 * 1024) smem = 120 * 1024;
+      conv_wgrad_t_kernel<<<(unsigned)(base * q.splits), kWgThreads, smem, stream>>>(tmDY, tmX, q);
+      return check_launch("conv_wgrad_t");
+    }
+  }
   {
     const int tilesW = (W + 7) / 8, tilesH = (H + 15) / 16;
     const double fill = (double)W * H / ((double)tilesW * 8 * tilesH * 16);
