@@ -87,24 +87,24 @@ class KernelProfiler:
     def __init__(self):
         self.records = []
 
-    def run(self, kind, work, thunk):
+    def run(self, kind, work, thunk, nbytes=0.0):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         thunk()
         b.record()
-        self.records.append((kind, work, a, b))
+        self.records.append((kind, work, a, b, nbytes))
 
     def dump(self, path, steps):
         """Per-call table (one step's worth): kind, work (FLOP or bytes), milliseconds."""
         n = len(self.records) // steps
-        rows = [{"i": i, "kind": k, "work": w, "ms": a.elapsed_time(b)} for i, (k, w, a, b) in
+        rows = [{"i": i, "kind": k, "work": w, "ms": a.elapsed_time(b), "bytes": nb} for i, (k, w, a, b, nb) in
                 enumerate(self.records[-n:])]
         with open(path, "w") as f:
             json.dump(rows, f)
 
     def summary(self, steps):
         out = {}
-        for kind, work, a, b in self.records:
+        for kind, work, a, b, _nb in self.records:
             d = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
             d["ms"] += a.elapsed_time(b)
             d["work"] += work

@@ -63,6 +63,12 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
 /* Accumulator layout (0 or 1) the tcgen05 weight-gradient path wants for this geometry. */
 VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, int H, int W);
 
+/* Thin 1x1x1 weight gradient (1 <= cin, cout <= 32; also the second half of the tap-folded gradients):
+ * acc[ci][co] += sum_v x[v][ci] * dy[v][co], acc fp32 [ci_pad][co_pad], zeroed by the caller. A streaming
+ * warp-level mma.sync kernel: these layers are HBM streams, not GEMMs. */
+VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
+                                  int cin, float* acc, int co_pad, int ci_pad, long long V, void* stream);
+
 /* CUDA-core versions on the same operands; used by the tests to cross-check the tcgen05 kernels. */
 VFD_API int vfd_conv3d_fwd_direct(const void* x, long long x_ld, int cin, const void* w_packed,
                                   int w_rows, int cin_k, const float* bias, void* out,

@@ -22,7 +22,7 @@ class P:
     def __init__(self):
         self.t = {}
 
-    def run(self, kind, work, thunk):
+    def run(self, kind, work, thunk, nbytes=0.0):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         thunk()

@@ -128,6 +128,14 @@ def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
                   ci_pad, layout, N, D, H, W, kd, kh, kw, _stream())
 
 
+def _conv3d_wgrad_thin(dy, cout, x, cin, acc):
+    N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad_thin dy")
+    _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad_thin x")
+    _, ci_pad, co_pad = acc.shape
+    _lib.call("vfd_conv3d_wgrad_thin", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
+              ci_pad, N * D * H * W, _stream())
+
+
 def wgrad_layout(cout, cin, kd, kh, kw, H, W):
     """Accumulator layout the tcgen05 wgrad wants: 0 = [tap][ci][co], 1 = [tap][co][ci] (swapped GEMM roles)."""
     return int(_lib.lib().vfd_conv3d_wgrad_layout(cout, cin, kd, kh, kw, H, W))
@@ -250,6 +258,8 @@ conv3d_fwd = _define(
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
+conv3d_wgrad_thin = _define("conv3d_wgrad_thin(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc) -> ()",
+                            _conv3d_wgrad_thin)
 pack_ncdhw = _define("pack_ncdhw(Tensor src, Tensor(a!) dst, int C, bool replicate) -> ()", _pack_ncdhw)
 unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack_ncdhw)
 pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
@@ -294,11 +304,13 @@ CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path agai
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
 
-def _timed(kind, work, thunk):
+def _timed(kind, work, thunk, nbytes=0.0):
+    """Run a kernel thunk; with a profiler installed (bench.py) it is bracketed by CUDA events and recorded
+    with its algorithmic work (FLOP for convs, bytes for the HBM-bound kernels) and algorithmic bytes."""
     if PROFILER is None:
         thunk()
     else:
-        PROFILER.run(kind, work, thunk)
+        PROFILER.run(kind, work, thunk, nbytes)
 
 _scratch = {}
 
@@ -441,6 +453,17 @@ def wgrad_fold_mode(cin, cout, kd, kh, kw):
     return None
 
 
+THIN_WGRAD = os.environ.get("VFD_WGRAD_THIN", "1") != "0"
+
+
+def _wgrad_1x1(dy, cout, x, cin, acc):
+    """1x1x1 weight gradient into acc[0][ci][co]: the streaming mma.sync kernel for thin layers, tcgen05 else."""
+    if THIN_WGRAD and cout <= 32 and cin <= 32:
+        conv3d_wgrad_thin(dy, cout, x, cin, acc)
+    else:
+        conv3d_wgrad(dy, cout, x, cin, acc, 1, 1, 1, False)
+
+
 def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     """-> fp32 weight gradient [cout, cin, taps]"""
     taps = kd * kh * kw
@@ -452,17 +475,17 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     def run():
         if mode == "x":     # X'[v][t*cin+ci] = x[v+off(t)][ci];  acc[0][t*cin+ci][co]
             tap_gather(x, cs, folded, kd, kh, kw, 1)
-            conv3d_wgrad(g, cout, folded, taps * cin, acc, 1, 1, 1, False)
+            _wgrad_1x1(g, cout, folded, taps * cin, acc)
         else:               # Y'[u][t*cout+co] = dy[u-off(t)][co]; acc[0][ci][t*cout+co]
             tap_gather(g, cs, folded, kd, kh, kw, -1)
-            conv3d_wgrad(folded, taps * cout, x, cin, acc, 1, 1, 1, False)
+            _wgrad_1x1(folded, taps * cout, x, cin, acc)
 
     if mode == "x":
         acc = torch.zeros(1, cols, round_up(cout, 32), dtype=torch.float32, device=g.device)
-        _timed("conv_wgrad", flops, run)
+        _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
         return acc[0, :taps * cin, :cout].reshape(taps, cin, cout).permute(2, 1, 0).contiguous()
     acc = torch.zeros(1, round_up(cin, 8), round_up(taps * cout, 32), dtype=torch.float32, device=g.device)
-    _timed("conv_wgrad", flops, run)
+    _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
     return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1).contiguous()
 
 
@@ -489,7 +512,8 @@ class ConvFn(torch.autograd.Function):
         st = bn_scratch(x.device, cout_p) if (fuse_stats and not out_fp32 and cout_p <= 1024) else None
         ctx.stats_fused = st is not None
         _timed("conv_fwd", flops,
-               lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT))
+               lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT),
+               2.0 * x.numel() + out.numel() * out.element_size())
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_zero = bias_grad_exact_zero
@@ -508,20 +532,28 @@ class ConvFn(torch.autograd.Function):
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             _timed("conv_dgrad", flops,
                    lambda: conv3d_fwd(g, pk.dgrad, None, gx, None, kd, kh, kw, pk.kc_d, x.shape[-1],
-                                      CONV_IMPL_DIRECT))
+                                      CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
         if ctx.needs_input_grad[1]:
             taps = kd * kh * kw
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             fold = None if CONV_IMPL_DIRECT else wgrad_fold_mode(cin, cout, kd, kh, kw)
             if fold is None:
                 layout = 0 if CONV_IMPL_DIRECT else wgrad_layout(cout, cin, kd, kh, kw, H, W)
-                if layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
+                if taps == 1 and cout <= 32 and cin <= 32 and THIN_WGRAD and not CONV_IMPL_DIRECT:
+                    acc = torch.zeros(1, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad_thin(g, cout, x, cin, acc),
+                           2.0 * (g.numel() + x.numel()))
+                    gw = torch.empty_like(weight, dtype=torch.float32)
+                    unpack_wgrad(acc, gw)
+                elif layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
                     acc = torch.zeros(taps, round_up(cout, 8), round_up(cin, 32), dtype=torch.float32, device=g.device)
-                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1))
+                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1),
+                           2.0 * (g.numel() + x.numel()))
                     gw = acc[:, :cout, :cin].permute(1, 2, 0).contiguous().reshape(weight.shape)
                 else:
                     acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
-                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT))
+                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT),
+                           2.0 * (g.numel() + x.numel()))
                     gw = torch.empty_like(weight, dtype=torch.float32)
                     unpack_wgrad(acc, gw)
             else:
