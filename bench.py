@@ -326,7 +326,7 @@ def main():
         conv_flops = sum(v["work"] for v in conv.values()) / psteps
         kname = {"conv_fwd": "conv_fwd_res_kernel / conv_fwd_tc_kernel (forward)",
                  "conv_dgrad": "conv_fwd_res_kernel / conv_fwd_tc_kernel (dgrad)",
-                 "conv_wgrad": "conv_wgrad2_kernel (+ tap_gather for folded thin layers)"}[dom]
+                 "conv_wgrad": "conv_wgrad{2,3,_t}_kernel / thin_wgrad_kernel (+ tap_gather for folded thin layers)"}[dom]
         # DRAM bytes per launch of the dominant kernel kind from the committed ncu pass (profiles/), if any
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")

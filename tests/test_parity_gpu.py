@@ -255,7 +255,9 @@ def test_graph_step_equals_eager_step():
             assert abs(a[k] - b[k]) <= tol * abs(a[k]) + 1e-6, (it, k, a[k], b[k])
     assert graph._graph is not None
     pa, pb = dict(ga.named_parameters()), dict(gb.named_parameters())
-    assert all(rel(pb[k], pa[k]) < 2e-3 for k in pa)
+    # Adam normalises gradients, so where a gradient is at noise level the two runs may step in different
+    # directions: bound the drift by a few learning-rate-sized steps instead of a relative error
+    assert all(float((pb[k] - pa[k]).abs().max()) <= 5 * 3 * 2e-5 for k in pa)
 
 
 def test_losses_match_reference_fixture():
