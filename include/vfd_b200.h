@@ -63,11 +63,15 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
 /* Accumulator layout (0 or 1) the tcgen05 weight-gradient path wants for this geometry. */
 VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, int H, int W);
 
-/* Thin 1x1x1 weight gradient (1 <= cin, cout <= 32; also the second half of the tap-folded gradients):
- * acc[ci][co] += sum_v x[v][ci] * dy[v][co], acc fp32 [ci_pad][co_pad], zeroed by the caller. A streaming
- * warp-level mma.sync kernel: these layers are HBM streams, not GEMMs. */
+/* Thin weight gradient (1 <= cin, cout <= 32): acc[ci][co] += sum_v x[v][ci] * dy[v][co], acc fp32
+ * [ci_pad][co_pad], zeroed by the caller. A streaming warp-level mma.sync kernel: these layers are HBM
+ * streams, not GEMMs. fold = 0: a plain 1x1x1 gradient (kd = kh = kw = 1). fold = 1 / 2: the x / dy side is
+ * tap-folded on the fly (as vfd_tap_gather would: the tensor holds cs channels per voxel and the folded
+ * channel count is kd*kh*kw*cs), so the gradient of a thin kd x kh x kw conv needs no im2col tensor.
+ * Supported folds: x (1,3,3) cs 3, x (3,1,1) cs 2, dy (3,3,3) cs 1. */
 VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
-                                  int cin, float* acc, int co_pad, int ci_pad, long long V, void* stream);
+                                  int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
+                                  int H, int W, int kd, int kh, int kw, void* stream);
 
 /* CUDA-core versions on the same operands; used by the tests to cross-check the tcgen05 kernels. */
 VFD_API int vfd_conv3d_fwd_direct(const void* x, long long x_ld, int cin, const void* w_packed,

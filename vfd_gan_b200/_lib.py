@@ -18,7 +18,7 @@ SIGNATURES = {
     "vfd_conv3d_fwd": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_layout": [_i, _i, _i, _i, _i, _i, _i],
-    "vfd_conv3d_wgrad_thin": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _ll, _p],
+    "vfd_conv3d_wgrad_thin": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_fwd_direct": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_direct": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_pack_ncdhw": [_p, _p, _i, _i, _ll, _i, _ll, _i, _i, _p],

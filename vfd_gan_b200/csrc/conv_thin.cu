@@ -32,12 +32,52 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// MT: 16-row tiles of input channels (1 or 2), NT: 8-column tiles of output channels (1..4)
-template <int MT, int NT>
+// Tap folding fused into the stream (see vfd_tap_gather): one side of the GEMM is not read as stored but
+// gathered on the fly, element e of the folded row = channel e % CS of the source voxel shifted by tap e / CS.
+struct FastDivT {
+  uint32_t m, s, d;
+};
+__device__ __forceinline__ uint32_t fdivt(uint32_t n, const FastDivT& f) { return (__umulhi(n, f.m) + n) >> f.s; }
+struct FoldGeom {
+  int D, H, W;
+  FastDivT fW, fH, fD;
+};
+struct NoFold {
+  static constexpr bool kFold = false;
+};
+template <int KD, int KH, int KW, int CS_>
+struct Fold {
+  static constexpr bool kFold = true;
+  static constexpr int TAPS = KD * KH * KW, CS = CS_;
+  // 16-byte chunk `chunk` of the folded row of voxel (n, d, h, w); sign = +1 gathers x, -1 gathers dy
+  static __device__ __forceinline__ uint4 chunk_of(const bf16* __restrict__ src, long long ld, const FoldGeom& g,
+                                                   unsigned n, int d, int h, int w, int chunk, int sign) {
+    uint32_t words[4] = {0u, 0u, 0u, 0u};
+    const unsigned short* s16 = reinterpret_cast<const unsigned short*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = chunk * 8 + j;
+      if (e < TAPS * CS) {
+        const int tap = e / CS, ch = e - tap * CS;
+        const int a = tap / (KH * KW), r = tap - a * (KH * KW), b = r / KW, c = r - b * KW;
+        const int dd = d + sign * (a - KD / 2), hh = h + sign * (b - KH / 2), ww = w + sign * (c - KW / 2);
+        if (dd >= 0 && dd < g.D && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) {
+          const uint32_t val = __ldg(s16 + (size_t)(((n * g.D + dd) * g.H + hh) * g.W + ww) * ld + ch);
+          words[j >> 1] |= val << ((j & 1) * 16);
+        }
+      }
+    }
+    return make_uint4(words[0], words[1], words[2], words[3]);
+  }
+};
+
+// MT: 16-row tiles of input channels (1 or 2), NT: 8-column tiles of output channels (1..4).
+// FX / FY: tap folding of the x / dy side (at most one of them).
+template <int MT, int NT, typename FX = NoFold, typename FY = NoFold>
 __global__ void __launch_bounds__(kThinThreads)
 thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const bf16* __restrict__ x,
-                  long long x_ld, int cin, float* __restrict__ acc, int co_pad, long long V) {
-  const int xchunks = (cin + 7) >> 3;   // 16-byte chunks that exist in a row of x (dy has exactly NT)
+                  long long x_ld, int cin, float* __restrict__ acc, int co_pad, long long V, FoldGeom fg) {
+  const int xchunks = (cin + 7) >> 3;   // 16-byte chunks that exist in a (folded) row of x (dy has exactly NT)
   __shared__ __align__(16) uint8_t tiles[kThinThreads / 32][2][16 * kThinRowBytes];
   __shared__ float red[32 * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,8 +114,25 @@ thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
       rx[i] = make_uint4(0u, 0u, 0u, 0u);
       ry[i] = make_uint4(0u, 0u, 0u, 0u);
       if (v < V) {
-        if (lchunk < xchunks) rx[i] = __ldg(reinterpret_cast<const uint4*>(x + v * x_ld) + lchunk);
-        if (lchunk < NT) ry[i] = __ldg(reinterpret_cast<const uint4*>(dy + v * dy_ld) + lchunk);
+        unsigned n = 0;
+        int d = 0, h = 0, w = 0;
+        if (FX::kFold || FY::kFold) {
+          const unsigned vv = static_cast<unsigned>(v);
+          const unsigned t1 = fdivt(vv, fg.fW);
+          w = vv - t1 * fg.W;
+          const unsigned t2 = fdivt(t1, fg.fH);
+          h = t1 - t2 * fg.H;
+          n = fdivt(t2, fg.fD);
+          d = t2 - n * fg.D;
+        }
+        if (lchunk < xchunks) {
+          if constexpr (FX::kFold) rx[i] = FX::chunk_of(x, x_ld, fg, n, d, h, w, lchunk, 1);
+          else rx[i] = __ldg(reinterpret_cast<const uint4*>(x + v * x_ld) + lchunk);
+        }
+        if (lchunk < NT) {
+          if constexpr (FY::kFold) ry[i] = FY::chunk_of(dy, dy_ld, fg, n, d, h, w, lchunk, -1);
+          else ry[i] = __ldg(reinterpret_cast<const uint4*>(dy + v * dy_ld) + lchunk);
+        }
       }
     }
     __syncwarp();   // the previous group's ldmatrix reads are done
@@ -123,26 +180,67 @@ thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
 
 using namespace vfd;
 
+static FastDivT make_fastdivt(uint32_t d) {
+  FastDivT f;
+  f.d = d;
+  if (d <= 1) {
+    f.m = 0;
+    f.s = 0;
+  } else {
+    uint32_t sft = 0;
+    while ((1u << sft) < d) ++sft;
+    f.m = (uint32_t)((((1ull << sft) - d) << 32) / d + 1);
+    f.s = sft;
+  }
+  return f;
+}
+
+// fold: 0 = none; 1 = x is folded on the fly (x holds cs channels per voxel, cin = taps * cs);
+//       2 = dy is folded on the fly (dy holds cs channels per voxel, cout = taps * cs)
 VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
-                                     int cin, float* acc, int co_pad, int ci_pad, long long V, void* stream_) {
+                                     int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
+                                     int H, int W, int kd, int kh, int kw, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long V = (long long)N * D * H * W;
   if (V <= 0) return 0;
+  if (V >= (1LL << 31)) return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: more than 2^31 voxels");
   if (cout < 1 || cout > 32 || cin < 1 || cin > 32 || co_pad < cout || ci_pad < cin)
     return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: needs 1 <= cin, cout <= 32 and a large enough accumulator");
+  const int x_need = fold == 1 ? ((cs + 7) & ~7) : ((cin + 7) & ~7), y_need = fold == 2 ? ((cs + 7) & ~7) : ((cout + 7) & ~7);
   if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (dy_ld % 8) || (x_ld % 8) ||
-      dy_ld < ((cout + 7) & ~7) || x_ld < ((cin + 7) & ~7))
+      dy_ld < y_need || x_ld < x_need)
     return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: tensors must be 16-byte aligned channels-last bf16");
+  const int taps = kd * kh * kw;
+  if ((fold == 1 && cin != taps * cs) || (fold == 2 && cout != taps * cs) || fold < 0 || fold > 2)
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: folded channel count must be taps * cs");
+  FoldGeom fg;
+  fg.D = D; fg.H = H; fg.W = W;
+  fg.fW = make_fastdivt(W); fg.fH = make_fastdivt(H); fg.fD = make_fastdivt(D);
   const int mt = (cin + 15) / 16, nt = (cout + 7) / 8;
-  // the staged tiles read whole 16-byte chunks: chunks beyond the tensor's padded width are not loaded
   const int grid = 148 * 4;
-#define VFD_THIN(MT, NT)                                                                                     \
-  if (mt == MT && nt == NT) {                                                                                \
-    thin_wgrad_kernel<MT, NT><<<grid, kThinThreads, 0, stream>>>((const bf16*)dy, dy_ld, cout, (const bf16*)x, \
-                                                                 x_ld, cin, acc, co_pad, V);                 \
-    return check_launch("thin_wgrad");                                                                       \
+#define VFD_THIN_ARGS (const bf16*)dy, dy_ld, cout, (const bf16*)x, x_ld, cin, acc, co_pad, V, fg
+#define VFD_THIN(MT, NT, FX, FY)                                                                  \
+  if (mt == MT && nt == NT) {                                                                     \
+    thin_wgrad_kernel<MT, NT, FX, FY><<<grid, kThinThreads, 0, stream>>>(VFD_THIN_ARGS);           \
+    return check_launch("thin_wgrad");                                                            \
   }
-  VFD_THIN(1, 1) VFD_THIN(1, 2) VFD_THIN(1, 3) VFD_THIN(1, 4)
-  VFD_THIN(2, 1) VFD_THIN(2, 2) VFD_THIN(2, 3) VFD_THIN(2, 4)
+#define VFD_THIN_NT(MT, FX, FY) VFD_THIN(MT, 1, FX, FY) VFD_THIN(MT, 2, FX, FY) VFD_THIN(MT, 3, FX, FY) VFD_THIN(MT, 4, FX, FY)
+  using F133_3 = Fold<1, 3, 3, 3>;
+  using F311_2 = Fold<3, 1, 1, 2>;
+  using F333_1 = Fold<3, 3, 3, 1>;
+  if (fold == 0) {
+    VFD_THIN_NT(1, NoFold, NoFold)
+    VFD_THIN_NT(2, NoFold, NoFold)
+  } else if (fold == 1 && kd == 1 && kh == 3 && kw == 3 && cs == 3) {
+    VFD_THIN_NT(2, F133_3, NoFold)
+  } else if (fold == 1 && kd == 3 && kh == 1 && kw == 1 && cs == 2) {
+    VFD_THIN_NT(1, F311_2, NoFold)
+  } else if (fold == 2 && kd == 3 && kh == 3 && kw == 3 && cs == 1) {
+    VFD_THIN(1, 4, NoFold, F333_1)
+    VFD_THIN(2, 4, NoFold, F333_1)
+  }
+#undef VFD_THIN_NT
 #undef VFD_THIN
-  return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: unsupported tile shape");
+#undef VFD_THIN_ARGS
+  return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: unsupported tile shape / fold combination");
 }

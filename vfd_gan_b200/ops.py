@@ -128,12 +128,12 @@ def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
                   ci_pad, layout, N, D, H, W, kd, kh, kw, _stream())
 
 
-def _conv3d_wgrad_thin(dy, cout, x, cin, acc):
+def _conv3d_wgrad_thin(dy, cout, x, cin, acc, fold=0, cs=0, kd=1, kh=1, kw=1):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad_thin dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad_thin x")
     _, ci_pad, co_pad = acc.shape
     _lib.call("vfd_conv3d_wgrad_thin", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
-              ci_pad, N * D * H * W, _stream())
+              ci_pad, fold, cs, N, D, H, W, kd, kh, kw, _stream())
 
 
 def wgrad_layout(cout, cin, kd, kh, kw, H, W):
@@ -258,8 +258,9 @@ conv3d_fwd = _define(
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
-conv3d_wgrad_thin = _define("conv3d_wgrad_thin(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc) -> ()",
-                            _conv3d_wgrad_thin)
+conv3d_wgrad_thin = _define(
+    "conv3d_wgrad_thin(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int fold=0, int cs=0, int kd=1, "
+    "int kh=1, int kw=1) -> ()", _conv3d_wgrad_thin)
 pack_ncdhw = _define("pack_ncdhw(Tensor src, Tensor(a!) dst, int C, bool replicate) -> ()", _pack_ncdhw)
 unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack_ncdhw)
 pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
@@ -464,21 +465,35 @@ def _wgrad_1x1(dy, cout, x, cin, acc):
         conv3d_wgrad(dy, cout, x, cin, acc, 1, 1, 1, False)
 
 
+# Gathers conv_thin.cu does in-stream. It also implements ("x", 1, 3, 3, 3) and ("y", 3, 3, 3, 1), but with 9 / 27
+# taps the per-element gather is instruction bound and measured slower on B200 than vfd_tap_gather + the plain
+# thin kernel (0.41 vs 0.30 ms for dconv1.spatial_conv), so only the 3-tap temporal fold is fused.
+_FUSED_FOLDS = {("x", 3, 1, 1, 2)}
+
+
 def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     """-> fp32 weight gradient [cout, cin, taps]"""
     taps = kd * kh * kw
     N, D, H, W = g.shape[:4]
     cs = cin if mode == "x" else cout
     cols = round_up(taps * cs, 8)
-    folded = cl_empty(N, D, H, W, cols, g.device)
+    other = cout if mode == "x" else cin
+    fused = THIN_WGRAD and other <= 32 and (mode, kd, kh, kw, cs) in _FUSED_FOLDS
+    folded = None if fused else cl_empty(N, D, H, W, cols, g.device)
 
     def run():
         if mode == "x":     # X'[v][t*cin+ci] = x[v+off(t)][ci];  acc[0][t*cin+ci][co]
-            tap_gather(x, cs, folded, kd, kh, kw, 1)
-            _wgrad_1x1(g, cout, folded, taps * cin, acc)
+            if fused:
+                conv3d_wgrad_thin(g, cout, x, taps * cin, acc, 1, cs, kd, kh, kw)
+            else:
+                tap_gather(x, cs, folded, kd, kh, kw, 1)
+                _wgrad_1x1(g, cout, folded, taps * cin, acc)
         else:               # Y'[u][t*cout+co] = dy[u-off(t)][co]; acc[0][ci][t*cout+co]
-            tap_gather(g, cs, folded, kd, kh, kw, -1)
-            _wgrad_1x1(folded, taps * cout, x, cin, acc)
+            if fused:
+                conv3d_wgrad_thin(g, taps * cout, x, cin, acc, 2, cs, kd, kh, kw)
+            else:
+                tap_gather(g, cs, folded, kd, kh, kw, -1)
+                _wgrad_1x1(folded, taps * cout, x, cin, acc)
 
     if mode == "x":
         acc = torch.zeros(1, cols, round_up(cout, 32), dtype=torch.float32, device=g.device)
