@@ -12,6 +12,7 @@
 // ConvLSTM cell update (models/convlstm.py:49-58).
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstdlib>
 #include "vfd_internal.h"
 
 namespace vfd {
@@ -1359,12 +1360,25 @@ static int fill_act_geom(ActGeom& g, int N, int D, int H, int W, int C, int pd, 
   return 0;
 }
 
-static int win_grid(const ActGeom& g, int pd, int ph, int pw, int nv_per_iter) {
+static int bn_waves() {
+  static int w = 0;
+  if (w == 0) {
+    const char* e = getenv("VFD_BN_WAVES");
+    w = e ? atoi(e) : 16;
+    if (w < 1) w = 16;
+  }
+  return w;
+}
+
+static int win_grid(const ActGeom& g, int pd, int ph, int pw, int nv_per_iter, int waves = 0) {
   const long long nwin = (long long)g.N * ((g.D + pd - 1) / pd) * ((g.H + ph - 1) / ph) * ((g.W + pw - 1) / pw);
   const int rpi = 256 / (g.C / 8);
   long long b = (nwin + (long long)rpi * nv_per_iter * 4 - 1) / ((long long)rpi * nv_per_iter * 4);
   if (b < 1) b = 1;
-  if (b > 148 * 16) b = 148 * 16;
+  // blocks per SM in the grid (2 are resident). Measured on B200: the forward kernels like many small
+  // blocks (16), the 8-channel backward kernels exactly one resident wave (2); VFD_BN_WAVES overrides both
+  const int cap = 148 * (getenv("VFD_BN_WAVES") ? bn_waves() : (waves ? waves : 16));
+  if (b > cap) b = cap;
   return (int)b;
 }
 
@@ -1426,7 +1440,7 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
     ActGeom g;
     if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
     const int nvi = 4 / (pd * ph * pw) > 0 ? 4 / (pd * ph * pw) : 1;
-    const int grid = win_grid(g, pd, ph, pw, nvi);
+    const int grid = win_grid(g, pd, ph, pw, nvi, 2);
 #define VFD_BWD8_LAUNCH(KERNEL, SMEM, ...)                                                             \
     do {                                                                                                \
       if (pd == 1) {                                                                                    \
@@ -1459,7 +1473,7 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
     const int per_iter = rpi * (8 / (ph * pw));
     long long b = ((long long)g.nwin + (long long)per_iter * 4 - 1) / ((long long)per_iter * 4);
     if (b < 1) b = 1;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > 148 * 6) b = 148 * 6;   // 3 resident blocks per SM, two waves
     const int grid = (int)b;
 #define VFD_BWD_LAUNCH(KERNEL, SMEM, ...)                                                              \
     do {                                                                                                \
