@@ -94,6 +94,10 @@ VFD_API int vfd_unpack_ncdhw(const void* src, int src_fp32, float* dst, int N, i
  * mode 0: forward (row = cout, col = cin); mode 1: dgrad (row = cin, col = cout, taps mirrored). */
 VFD_API int vfd_pack_weight(const float* w, void* w_packed, int Cout, int Cin, int taps, int rows,
                             int ck, int mode, void* stream);
+/* The same packing for many weights in one launch. jobs: device array of njobs records
+ *   { const float* w; void* dst; int cout, cin, taps, rows, ck, mode; long long begin; }   (48 bytes)
+ * where begin is the running sum of rows*taps*ck over the preceding jobs and total the overall sum. */
+VFD_API int vfd_pack_weights_batched(const void* jobs, int njobs, long long total, void* stream);
 /* wgrad accumulator [taps][ci_pad][co_pad] -> fp32 weight gradient [Cout][Cin][taps] */
 VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int co_pad,
                              int ci_pad, void* stream);

@@ -96,7 +96,15 @@ def test_conv_linearity_and_adjoint_at_full_size():
     ip_y = float((y.detach().double() * gy.double()).sum())
     tx = xg.grad.double() * x.double()
     tw = wp.grad.double() * w.bfloat16().double()
-    assert abs(float(tx.sum()) - ip_y) <= 4e-3 * float(tx.norm())      # dgrad is stored in bf16 (2^-9 per element)
+    # the autograd dgrad is STORED in bf16 (2^-9 per element; residuals of 0.1-3e-3 * norm were measured over
+    # seeds, tools/gpu_adjoint_check.py), so its bound is loose; the same kernel with the fp32 epilogue must
+    # satisfy the identity to accumulation-order precision
+    assert abs(float(tx.sum()) - ip_y) <= 1e-2 * float(tx.norm())
+    pk = ops._packed(wp)
+    gx32 = torch.empty(N, D, S, S, cin, dtype=torch.float32, device=DEV)
+    ops.conv3d_fwd(gy, pk.dgrad, None, gx32, None, 1, 3, 3, pk.kc_d, cin, False)
+    t32 = gx32.double() * x.double()
+    assert abs(float(t32.sum()) - ip_y) <= 1e-5 * float(t32.norm())
     assert abs(float(tw.sum()) - ip_y) <= 1e-4 * float(tw.norm()) * tw.numel() ** 0.5
 
 

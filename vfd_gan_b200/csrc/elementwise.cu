@@ -126,6 +126,39 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
   }
 }
 
+// All conv weights of a network in ONE launch: job j packs weight j into one of its two GEMM layouts
+// (see pack_weight_kernel). begin[] is the running element offset, so a thread finds its job by a short scan.
+struct PackJob {
+  const float* w;
+  bf16* dst;
+  int cout, cin, taps, rows, ck, mode;
+  long long begin;   // first flattened element of this job
+};
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;   // last job with begin <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackJob jb = jobs[lo];
+    const long long e = i - jb.begin;
+    const int c = (int)(e % jb.ck);
+    const long long t = e / jb.ck;
+    const int tap = (int)(t % jb.taps);
+    const int row = (int)(t / jb.taps);
+    float v = 0.f;
+    if (jb.mode == 0) {
+      if (row < jb.cout && c < jb.cin) v = jb.w[((long long)row * jb.cin + c) * jb.taps + tap];
+    } else {
+      if (row < jb.cin && c < jb.cout) v = jb.w[((long long)c * jb.cin + row) * jb.taps + (jb.taps - 1 - tap)];
+    }
+    jb.dst[e] = __float2bfloat16(v);
+  }
+}
+
 // wgrad accumulator [taps][ci_pad][co_pad] fp32 -> weight gradient [Cout][Cin][taps] fp32
 __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ gw, int Cout,
                                     int Cin, int taps, int co_pad, int ci_pad) {
@@ -1297,6 +1330,12 @@ VFD_API int vfd_pack_weight(const float* w, void* wp, int Cout, int Cin, int tap
   if (total == 0) return 0;
   pack_weight_kernel<<<grid_for(total), 256, 0, STREAM>>>(w, (bf16*)wp, Cout, Cin, taps, rows, ck, mode);
   return check_launch("pack_weight");
+}
+
+VFD_API int vfd_pack_weights_batched(const void* jobs, int njobs, long long total, void* stream_) {
+  if (njobs <= 0 || total <= 0) return 0;
+  pack_weights_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>((const PackJob*)jobs, njobs, total);
+  return check_launch("pack_weights_batched");
 }
 
 VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int co_pad,

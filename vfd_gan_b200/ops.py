@@ -339,29 +339,38 @@ _reg_post_hook(invalidate_packed_weights)
 
 
 class PackedWeights:
-    """bf16 GEMM operands of one conv weight, rebuilt when the fp32 master changes (Adam step)."""
+    """bf16 GEMM operands of one conv weight (forward and tap-mirrored dgrad layouts), rebuilt when the fp32
+    master changes (Adam step). The two buffers are allocated once and re-packed in place, so a
+    ``WeightPacker`` can refresh every weight of a network with one kernel launch."""
 
     def __init__(self):
-        self.version = None
         self.key = None
+        self.shape_key = None
         self.fwd = None
         self.dgrad = None
 
-    def get(self, weight):
+    def _allocate(self, weight):
         cout, cin = weight.shape[0], weight.shape[1]
         taps = weight[0, 0].numel()
-        key = (weight.data_ptr(), weight._version, weight.device, _weight_epoch[0])
+        cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
+        self.kc_f, self.kc_d = pick_kc(cin_p), pick_kc(cout_p)
+        self.fwd = torch.empty(round_up(cout, 16), taps, round_up(cin_p, self.kc_f), dtype=torch.bfloat16,
+                               device=weight.device)
+        self.dgrad = torch.empty(round_up(cin, 16), taps, round_up(cout_p, self.kc_d), dtype=torch.bfloat16,
+                                 device=weight.device)
+        self.shape_key = (tuple(weight.shape), weight.device)
+
+    def current_key(self, weight):
+        return (weight.data_ptr(), weight._version, weight.device, _weight_epoch[0])
+
+    def get(self, weight):
+        key = self.current_key(weight)
         if self.key != key:
-            cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
-            kc_f, kc_d = pick_kc(cin_p), pick_kc(cout_p)
+            if self.shape_key != (tuple(weight.shape), weight.device):
+                self._allocate(weight)
             w = weight.detach()
-            self.fwd = torch.empty(round_up(cout, 16), taps, round_up(cin_p, kc_f), dtype=torch.bfloat16,
-                                   device=weight.device)
-            self.dgrad = torch.empty(round_up(cin, 16), taps, round_up(cout_p, kc_d), dtype=torch.bfloat16,
-                                     device=weight.device)
             pack_weight(w, self.fwd, 0)
             pack_weight(w, self.dgrad, 1)
-            self.kc_f, self.kc_d = kc_f, kc_d
             self.key = key
         return self
 
@@ -372,6 +381,46 @@ def _packed(weight):
         pw = PackedWeights()
         weight._vfd_packed = pw
     return pw.get(weight)
+
+
+class WeightPacker:
+    """Re-packs all conv weights of a set of modules with ONE kernel launch (vfd_pack_weights_batched)."""
+
+    def __init__(self, modules):
+        import struct
+        self.weights = []
+        for m in modules:
+            for mod in m.modules():
+                if isinstance(mod, (torch.nn.Conv3d, torch.nn.Conv2d)):
+                    self.weights.append(mod.weight)
+        recs, begin = [], 0
+        self.entries = []
+        for w in self.weights:
+            pw = getattr(w, "_vfd_packed", None)
+            if pw is None:
+                pw = PackedWeights()
+                w._vfd_packed = pw
+            pw._allocate(w)
+            cout, cin = w.shape[0], w.shape[1]
+            taps = w[0, 0].numel()
+            for dst, mode in ((pw.fwd, 0), (pw.dgrad, 1)):
+                rows, _, ck = dst.shape
+                recs.append(struct.pack("<QQiiiiiiq", w.data_ptr(), dst.data_ptr(), cout, cin, taps, rows, ck, mode,
+                                        begin))
+                begin += dst.numel()
+            self.entries.append((w, pw))
+        self.total = begin
+        self.njobs = len(recs)
+        dev = self.weights[0].device
+        self.jobs = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        self.ptrs = [w.data_ptr() for w in self.weights]
+
+    def pack_all(self):
+        if [w.data_ptr() for w in self.weights] != self.ptrs:
+            raise RuntimeError("WeightPacker: a parameter was re-allocated; rebuild the packer")
+        _lib.call("vfd_pack_weights_batched", self.jobs.data_ptr(), self.njobs, self.total, _stream())
+        for w, pw in self.entries:
+            pw.key = pw.current_key(w)
 
 
 def cl_empty(N, D, H, W, C, device, dtype=torch.bfloat16):
@@ -530,6 +579,7 @@ class ConvFn(torch.autograd.Function):
                lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT),
                2.0 * x.numel() + out.numel() * out.element_size())
         ctx.save_for_backward(x, weight)
+        ctx.w_dgrad, ctx.kc_d = pk.dgrad, pk.kc_d     # the master cannot change between forward and backward
         ctx.has_bias = bias is not None
         ctx.bias_zero = bias_grad_exact_zero
         return out
@@ -541,12 +591,12 @@ class ConvFn(torch.autograd.Function):
         g = as_cl_grad(g)
         N, D, H, W, _, _ = _check_cl(g, "conv grad")
         gx = gw = gb = None
-        pk = _packed(weight)
+        w_dgrad, kc_d = ctx.w_dgrad, ctx.kc_d
         if ctx.needs_input_grad[0]:
             gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             _timed("conv_dgrad", flops,
-                   lambda: conv3d_fwd(g, pk.dgrad, None, gx, None, kd, kh, kw, pk.kc_d, x.shape[-1],
+                   lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
                                       CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
         if ctx.needs_input_grad[1]:
             taps = kd * kh * kw

@@ -22,6 +22,9 @@ def intermed_channels(in_channels, out_channels, kernel_size):
                           (kh * kw * in_channels + kt * out_channels)))
 
 
+DEFER_BN_COUNTERS = None   # list collecting num_batches_tracked tensors while GanTrainStep runs
+
+
 def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, want_pool=False, full_out=None,
              pre_bias=None, stats_ready=False, seed_dev=None):
     """nn.BatchNorm3d ``bn`` + (Leaky)ReLU(slope) [+ dropout] [+ average pool] on channels-last bf16.
@@ -37,7 +40,10 @@ def bn_apply(bn, y, slope, pool=(1, 1, 1), drop_p=0.0, seed=0, want_full=True, w
                                      int(seed), want_full, want_pool, None if full_out is None else [full_out],
                                      stats_ready, seed_dev)
     if train and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        if DEFER_BN_COUNTERS is not None:
+            DEFER_BN_COUNTERS.append(bn.num_batches_tracked)   # the fused train step adds them in one launch
+        else:
+            bn.num_batches_tracked += 1
     return full, pooled
 
 

@@ -36,7 +36,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import _lib, ops
+from . import _lib, ops, spatiotempconv
 
 LOSS_KEYS = ("g/err_g", "g/err_g_adv", "g/err_g_adv_s", "g/err_g_adv_t", "g/err_g_con",
              "d/err_d_real_s", "d/err_d_real_t", "d/err_d_fake_s", "d/err_d_fake_t",
@@ -148,6 +148,7 @@ class GanTrainStep:
                                             capturable=self.use_graph)
         self.losses = torch.zeros(len(LOSS_KEYS), dtype=torch.float32, device=dev)
         self.predict = None
+        self.packer = ops.WeightPacker([netg, netd]) if fused else None
         self._graph, self._static_in, self._eager_steps = None, None, 0
         self._step_counter = torch.zeros((), dtype=torch.int64, device=dev) if fused else None
 
@@ -197,6 +198,23 @@ class GanTrainStep:
         netd.train()
         if seed_dev is not None:
             seed_dev += 1   # in-place on the device: captured, so every replay advances the dropout stream
+        if self.packer is not None:
+            self.packer.pack_all()          # every conv weight's bf16 GEMM operands, one launch
+        spatiotempconv.DEFER_BN_COUNTERS = counters = []
+        try:
+            return self._step_body(inp, gt, gt_flow, pre_flow, dropout_seeds, seed_dev)
+        finally:
+            spatiotempconv.DEFER_BN_COUNTERS = None
+            if counters:   # num_batches_tracked of every BatchNorm call of the step (NetD runs twice)
+                seen = {}
+                for c in counters:
+                    ent = seen.setdefault(c.data_ptr(), [c, 0])
+                    ent[1] += 1
+                for n in sorted({e[1] for e in seen.values()}):
+                    torch._foreach_add_([e[0] for e in seen.values() if e[1] == n], n)
+
+    def _step_body(self, inp, gt, gt_flow, pre_flow, dropout_seeds, seed_dev):
+        netg, netd = self.netg, self.netd
 
         # forward_g
         logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds, seed_dev=seed_dev)
