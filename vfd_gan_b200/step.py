@@ -54,7 +54,10 @@ class GradAllReducer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
-        self.buckets = []
+        self.buckets, self.flat, self.pending, self.bucket_of = [], [], [], {}
+        self.comm_stream, self.handles, self.active = None, [], False
+        if self.world == 1:
+            return   # single rank: gradients stay ordinary per-parameter tensors (no flat copies, no adds)
         cap = int(bucket_mb * 1024 * 1024 / 4)
         cur, cur_n = [], 0
         for p in reversed(self.params):  # backward produces gradients roughly in reverse order
@@ -65,7 +68,6 @@ class GradAllReducer:
                 cur, cur_n = [], 0
         if cur:
             self.buckets.append(cur)
-        self.flat, self.pending, self.bucket_of = [], [], {}
         for bi, bucket in enumerate(self.buckets):
             n = sum(p.numel() for p in bucket)
             flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
@@ -76,14 +78,15 @@ class GradAllReducer:
                 self.bucket_of[p] = bi
             self.flat.append(flat)
             self.pending.append(0)
-        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and torch.cuda.is_available()) else None
-        self.handles = []
-        self.active = False
-        if self.world > 1:
-            for p in self.params:
-                p.register_post_accumulate_grad_hook(self._hook)
+        self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
 
     def zero(self):
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None          # autograd then hands the incoming gradient over without an add kernel
+            return
         for f in self.flat:
             f.zero_()
 
