@@ -1559,6 +1559,11 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   p.acc_stride = (p.block_n + 31) & ~31;
   const int mmas_per_sub = ntaps * p.cblocks * (KC / 16);
   int g0 = (kd == 3 || mmas_per_sub < 24) ? 4 : 1;
+  if (kd == 1 && mmas_per_sub < 24 && p.acc_stride <= 32) g0 = 8;   // thin N: amortise the hand-shakes further
+  if (const char* e = getenv("VFD_RES_G")) {   // diagnostics: force the sub-tile count
+    const int f = atoi(e);
+    if (f == 1 || f == 2 || f == 4 || f == 8) g0 = f;
+  }
   while (g0 > D) g0 >>= 1;
   const int stage_bytes = epi.out_fp32 ? 4096 : 2048;  // 32 rows x 128 / 64 B
   // pick (G, staging buffers): first choice with >= 3 input slots, else the first with >= 2
