@@ -511,6 +511,15 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float ssum[kMaxChunks][2], ssq[kMaxChunks][2];
 #pragma unroll
     for (int i = 0; i < kMaxChunks; ++i) ssum[i][0] = ssum[i][1] = ssq[i][0] = ssq[i][1] = 0.f;
+    // single-chunk layers (N <= 32, the thin HBM-bound ones) take their statistics from warp-level mma.sync
+    // instead: ones x tile gives the column sums, tile^T x tile (diagonal) the sums of squares; the fragments
+    // come from the staged chunk through ldmatrix.trans, rows outside the tensor are masked to zero
+    float msum[4][4], msq[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) msum[i][j] = msq[i][j] = 0.f;
+    const bool mma_stats = p.stats != nullptr && p.nchunks == 1 && !p.out_fp32;
     const int cp = lane & 15, rh = lane >> 4;
     // byte offset of the pair inside a staged row for each swizzle phase (64-byte swizzle: 16-byte chunk
     // index ^ ((row >> 1) & 3)); rows 2i + rh have phase i & 3
@@ -587,7 +596,36 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_store_5d(&tmC, sb, ch * 32, w0, h0 + 4 * q, d, n);
               bulk_commit_group();
             }
-            if (do_stats) {
+            if (mma_stats) {
+              const uint32_t sb_s = smem_u32(sb);
+              const int mat = lane >> 3, mr = lane & 7, t2 = (lane & 3) * 2;
+              constexpr uint32_t kOnes = 0x3F803F80u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t vb = vmask >> (16 * ks);
+                const uint32_t m_lo = (((vb >> t2) & 1u) ? 0xFFFFu : 0u) | (((vb >> (t2 + 1)) & 1u) ? 0xFFFF0000u : 0u);
+                const uint32_t m_hi = (((vb >> (t2 + 8)) & 1u) ? 0xFFFFu : 0u) | (((vb >> (t2 + 9)) & 1u) ? 0xFFFF0000u : 0u);
+                const int row = 16 * ks + (mat & 1) * 8 + mr;
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                  const int cidx = 2 * np + (mat >> 1);
+                  // b0/b1: voxel rows 0-7 / 8-15 of channel block 2np; b2/b3: the same rows of block 2np+1.
+                  // Read as an A fragment (channels on M, voxels on K) the same four registers are the
+                  // transposed tile, so tile^T x tile is the Gram matrix whose diagonal is the exact
+                  // (bf16 x bf16 products, fp32 accumulate) sum of squares.
+                  uint32_t b0, b1, b2, b3;
+                  ldmatrix_x4_trans(sb_s + row * 64 + ((cidx ^ ((row >> 1) & 3)) << 4), b0, b1, b2, b3);
+                  b0 &= m_lo;
+                  b2 &= m_lo;
+                  b1 &= m_hi;
+                  b3 &= m_hi;
+                  mma_bf16_16816(msum[2 * np], kOnes, kOnes, kOnes, kOnes, b0, b1);
+                  mma_bf16_16816(msum[2 * np + 1], kOnes, kOnes, kOnes, kOnes, b2, b3);
+                  mma_bf16_16816(msq[2 * np], b0, b2, b1, b3, b0, b1);
+                  mma_bf16_16816(msq[2 * np + 1], b0, b2, b1, b3, b2, b3);
+                }
+              }
+            } else if (do_stats) {
               float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
               const uint8_t* colp = sb;
               if (vmask == 0xffffffffu) {
@@ -635,14 +673,33 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (lane == 0) bulk_wait_group<0>();
     if (do_stats) {
+      if (mma_stats) {
+        if (lane < 4) {   // every accumulator row holds the same column sums: lanes 0-3 own columns 8n + 2t, +1
 #pragma unroll
-      for (int i = 0; i < kMaxChunks; ++i)
-        if (i < p.nchunks) {
-          atomicAdd(&s_sum[i * 32 + 2 * cp], ssum[i][0]);
-          atomicAdd(&s_sum[i * 32 + 2 * cp + 1], ssum[i][1]);
-          atomicAdd(&s_sq[i * 32 + 2 * cp], ssq[i][0]);
-          atomicAdd(&s_sq[i * 32 + 2 * cp + 1], ssq[i][1]);
+          for (int n = 0; n < 4; ++n) {
+            atomicAdd(&s_sum[8 * n + 2 * lane], msum[n][0]);
+            atomicAdd(&s_sum[8 * n + 2 * lane + 1], msum[n][1]);
+          }
         }
+        // Gram diagonals: accumulator element (row g [+8], column 2t + j) is on the diagonal when g == 2t + j
+        const int gq = lane >> 2, dj = gq - 2 * (lane & 3);
+        if (dj == 0 || dj == 1) {
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {
+            atomicAdd(&s_sq[16 * np + gq], dj ? msq[2 * np][1] : msq[2 * np][0]);
+            atomicAdd(&s_sq[16 * np + 8 + gq], dj ? msq[2 * np + 1][3] : msq[2 * np + 1][2]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i)
+          if (i < p.nchunks) {
+            atomicAdd(&s_sum[i * 32 + 2 * cp], ssum[i][0]);
+            atomicAdd(&s_sum[i * 32 + 2 * cp + 1], ssum[i][1]);
+            atomicAdd(&s_sq[i * 32 + 2 * cp], ssq[i][0]);
+            atomicAdd(&s_sq[i * 32 + 2 * cp + 1], ssq[i][1]);
+          }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       const int j = ew * 32 + lane;
       if (j < p.stats_ld && j < p.nchunks * 32 && (s_sum[j] != 0.f || s_sq[j] != 0.f)) {
