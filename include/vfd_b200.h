@@ -181,4 +181,43 @@ VFD_API int vfd_convlstm_cell_bwd(const float* act, const float* c_cur, const fl
                                   const float* dh, const float* dc_in, int hid, long long V,
                                   void* dgates, long long dg_ld, float* dc_cur, void* stream);
 
+/* ---- scoring: anomaly score, latent / contextual losses, evaluation (vfd_gan_b200/csrc/scoring.cu) ----
+ * per_clip[n] += sum over clip n of (a - b)^2; a, b channels-last bf16 latents [N * rows_per_clip][ld].
+ * Replaces torch.mean(torch.pow(latent_i - latent_o, 2), dim=1) (models/ganomaly.py:372) generalised to the
+ * 3-D latent (mean over every non-batch dim); the caller zeroes per_clip. The sum over all
+ * clips is the numerator of the latent L2 loss l_enc (models/ganomaly.py:439,477). */
+VFD_API int vfd_latent_score(const void* a, long long a_ld, const void* b, long long b_ld, int C,
+                             long long rows_per_clip, int N, double* per_clip, void* stream);
+/* gradient of scale * (*gscale) * sum((a-b)^2): ga = 2*scale*(*gscale)*(a-b), gb = -ga (bf16 channels-last;
+ * either may be NULL; gscale is an optional device scalar, the upstream autograd gradient) */
+VFD_API int vfd_sqdiff_bwd(const void* a, long long a_ld, const void* b, long long b_ld, int C, long long V,
+                           const float* gscale, float scale, void* ga, long long ga_ld, void* gb, long long gb_ld,
+                           void* stream);
+/* nn.L1Loss numerator, the contextual loss l_con (models/ganomaly.py:438,476): *sum += sum|a-b| over fp32
+ * tensors; ga (optional) = grad_scale * sign(a-b) */
+VFD_API int vfd_l1_loss(const float* a, const float* b, long long V, float grad_scale, double* sum, float* ga,
+                        void* stream);
+/* nn.BCELoss numerator (models/mygannet.py:267,326-332; lib/train_stcnn.py:90,107): *sum += -(t*max(log p,-100)
+ * + (1-t)*max(log(1-p),-100)); gp (optional) = grad_scale * (p-t)/max(p*(1-p),1e-12) */
+VFD_API int vfd_bce_loss(const float* p, const float* t, long long V, float grad_scale, double* sum, float* gp,
+                         void* stream);
+/* scores[i] = per_clip[i] * inv_count (fp32); minmax (optional, device float[2] pre-set to +inf/-inf by the
+ * caller) is updated with the running min / max of the sweep */
+VFD_API int vfd_score_finalize(const double* per_clip, int n, double inv_count, float* scores, float* minmax,
+                               void* stream);
+/* (s - min) / (max - min) over the whole sweep (models/ganomaly.py:396); minmax is device float[2] */
+VFD_API int vfd_score_scale(const float* scores, long long n, const float* minmax, float* out, void* stream);
+/* threshold (lib/utils.py:149-152) + morphology_proc (lib/utils.py:139-147): t_out (optional) = predict > thr;
+ * m_out = 5x5 opening of t in the (D, H) plane for every (clip, w) -- what cv2.morphologyEx does with the
+ * (D, H, W) array the reference hands it (rows = D, cols = H, channels = W; W <= 512). fp32 [N][D][H][W]. */
+VFD_API int vfd_threshold_open(const float* predict, int N, int D, int H, int W, float thr, float* t_out,
+                               float* m_out, void* stream);
+/* counts[0..3] += TP, FP, FN, TN with label = labels > 0.5 and prediction = scores >= thr: the inputs of the
+ * roc / pr / f1_score metrics of lib/evaluate.py:14-91 when the scores are binary masks (MyGAN.test) */
+VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long long n, float thr,
+                                 unsigned long long* counts, void* stream);
+/* exact tie-aware ROC area of n <= 16384 (score, label) pairs = sklearn auc(roc_curve(...))
+ * (lib/evaluate.py:37-38); out = device double[3]: AUC, #positives, #negatives */
+VFD_API int vfd_roc_auc(const float* scores, const float* labels, int n, double* out, void* stream);
+
 #endif /* VFD_B200_H */

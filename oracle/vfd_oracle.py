@@ -97,7 +97,8 @@ def st_conv(sd, prefix, x, kernel, train=True, round_bf16=False):
 # ------------------------------------------------------------------------------------------------
 # networks
 # ------------------------------------------------------------------------------------------------
-def netg_forward(sd, x, train=True, dropout_masks=None, dropout_p=0.25, round_bf16=False, return_latent=False):
+def netg_forward(sd, x, train=True, dropout_masks=None, dropout_p=0.25, round_bf16=False, return_latent=False,
+                 bottleneck=None):
     """NetG.forward (models/mygannet.py:55-101). ``dropout_masks``: optional list of four
     multiplier tensors (already scaled by 1/(1-p)) applied after uconv5..uconv2, replacing
     nn.Dropout so a test can share masks with the CUDA path; otherwise F.dropout draws from the
@@ -111,6 +112,8 @@ def netg_forward(sd, x, train=True, dropout_masks=None, dropout_p=0.25, round_bf
         skips.append(d)
         h = _r(F.avg_pool3d(d, 2), rb)
     latent = net_conv(sd, "dconv5", h, k, 0.2, train, rb)
+    if bottleneck is not None:      # builder-defined composition (config 3): see netg_lstm_forward
+        latent = bottleneck(latent)
 
     def drop(t, i):
         if dropout_masks is not None:
@@ -190,6 +193,134 @@ def convlstm_unroll(sd, prefix, x_btchw, round_bf16=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# builder-defined compositions of reference modules (D1, D3, D5)
+# ------------------------------------------------------------------------------------------------
+def netg_lstm_forward(sd, x, train=True, dropout_masks=None, round_bf16=False, return_latent=False):
+    """NetG with a one-layer bias-free ConvLSTM over the latent: ``ConvLSTM(...)(latent.transpose(1, 2))`` and
+    back, the wrapping idiom of models/convlstm.py:199-201; weights under ``clstm.cell_list.0.``."""
+    def bottleneck(latent):
+        out, _ = convlstm_unroll(sd, "clstm.cell_list.0.", latent.transpose(1, 2), round_bf16)
+        return _r(out.transpose(1, 2), round_bf16)
+    return netg_forward(sd, x, train, dropout_masks, round_bf16=round_bf16, return_latent=return_latent,
+                        bottleneck=bottleneck)
+
+
+def encoder_forward(sd, prefix, x, train=True, round_bf16=False):
+    """dconv1..dconv5 + AvgPool3d(2) between them (models/mygannet.py:57-71), weights under ``prefix``."""
+    h = x
+    for i in range(1, 5):
+        h = _r(F.avg_pool3d(net_conv(sd, f"{prefix}dconv{i}", h, (3, 3, 3), 0.2, train, round_bf16), 2), round_bf16)
+    return net_conv(sd, f"{prefix}dconv5", h, (3, 3, 3), 0.2, train, round_bf16)
+
+
+def enc_dec_enc_forward(sd, x, train=True, dropout_masks=None, round_bf16=False):
+    """(predict, latent_i, latent_o) of the enc-dec-enc composition (shape of models/ganomaly.py:160-175):
+    NetG under ``netg.``, second encoder under ``encoder2.``, fed with gray2rgb(predict)."""
+    sd_g = {k[len("netg."):]: v for k, v in sd.items() if k.startswith("netg.")}
+    predict, latent_i = netg_forward(sd_g, x, train, dropout_masks, round_bf16=round_bf16, return_latent=True)
+    for k, v in sd_g.items():      # running statistics updated in place on the views
+        sd["netg." + k] = v
+    latent_o = encoder_forward(sd, "encoder2.", gray2rgb(predict), train, round_bf16)
+    return predict, latent_i, latent_o
+
+
+def anomaly_scores(latent_i, latent_o):
+    """models/ganomaly.py:372 ``torch.mean(torch.pow(latent_i - latent_o, 2), dim=1)`` for a (B, nz, 1, 1)
+    latent, i.e. the mean over every non-batch dim of the 3-D latent."""
+    return torch.pow(latent_i - latent_o, 2).flatten(1).mean(dim=1)
+
+
+def minmax_scale(scores):
+    """models/ganomaly.py:396"""
+    return (scores - torch.min(scores)) / (torch.max(scores) - torch.min(scores))
+
+
+def l1_loss(a, b):
+    """nn.L1Loss() (models/ganomaly.py:438)"""
+    return torch.mean(torch.abs(a - b))
+
+
+# ------------------------------------------------------------------------------------------------
+# STCNN (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------
+def c2plus1d_block(sd, prefix, x, down_samp, train=True, dropout_mask=None, round_bf16=False):
+    """C2plus1d_Block.forward (models/mystcnn.py:26-50). ``dropout_mask``: multiplier tensor replacing
+    nn.Dropout on the shortcut input of the up-sampling blocks (None = no dropout)."""
+    rb = round_bf16
+    inp = x
+    y = _r(F.conv3d(_r(x, rb), _r(sd[prefix + "spaceconv.weight"], rb), None, padding=(0, 1, 1)), rb)
+    a = _r(F.relu(batch_norm(sd, prefix + "bn1", y, train)), rb)
+    y = _r(F.conv3d(a, _r(sd[prefix + "pointwise.weight"], rb), None, padding=(1, 0, 0)), rb)
+    h = _r(F.relu(batch_norm(sd, prefix + "bn2", y, train)), rb)
+    w1, b1 = _r(sd[prefix + "conv.weight"], rb), sd[prefix + "conv.bias"]
+    if down_samp:
+        h = _r(F.avg_pool3d(h, 2), rb)
+        inp = _r(F.avg_pool3d(_r(F.conv3d(_r(inp, rb), w1, b1), rb), 2), rb)
+    else:
+        h = _r(F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True), rb)
+        if dropout_mask is not None:
+            inp = _r(inp * dropout_mask, rb)
+        inp = _r(F.interpolate(inp, scale_factor=2, mode="trilinear", align_corners=True), rb)
+        inp = _r(F.conv3d(inp, w1, b1), rb)
+    h = torch.cat([h, inp], dim=1)
+    return _r(F.conv3d(h, _r(sd[prefix + "conv_last.weight"], rb), None, padding=1), rb)
+
+
+def autoencoder_forward(sd, x, train=True, dropout_masks=None, round_bf16=False):
+    """AutoEncoder.forward (models/mystcnn.py:69-88) -> predict (B,1,D,H,W)."""
+    rb = round_bf16
+    dm = dropout_masks if dropout_masks is not None else [None] * 4
+    d1 = c2plus1d_block(sd, "down_sep1.", x, True, train, None, rb)
+    d2 = c2plus1d_block(sd, "down_sep2.", d1, True, train, None, rb)
+    d3 = c2plus1d_block(sd, "down_sep3.", d2, True, train, None, rb)
+    d4 = c2plus1d_block(sd, "down_sep4.", d3, True, train, None, rb)
+    u1 = c2plus1d_block(sd, "up_sep1.", d4, False, train, dm[0], rb)
+    u2 = c2plus1d_block(sd, "up_sep2.", torch.cat([u1, d3], dim=1), False, train, dm[1], rb)
+    u3 = c2plus1d_block(sd, "up_sep3.", torch.cat([u2, d2], dim=1), False, train, dm[2], rb)
+    u4 = c2plus1d_block(sd, "up_sep4.", torch.cat([u3, d1], dim=1), False, train, dm[3], rb)
+    return torch.sigmoid(F.conv3d(u4, _r(sd["conv_last.weight"], rb), None, padding=1))
+
+
+# ------------------------------------------------------------------------------------------------
+# host detours of MyGAN.test (SURVEY.md section 8f rows 2-3)
+# ------------------------------------------------------------------------------------------------
+def threshold(data):
+    """lib/utils.py:149-152"""
+    return (data > 0.5).float()
+
+
+def morphology_proc(video):
+    """lib/utils.py:139-147 restated without cv2: ``cv2.morphologyEx(i, MORPH_OPEN, ones(5,5))`` is applied to
+    each clip's (D, H, W) array, which OpenCV reads as a D x H image with W channels, so the 5x5 opening
+    (erode then dilate, border pixels never win) runs in the (D, H) plane for every w. Pinned against cv2
+    itself by tests/golden/eval_small.pt."""
+    B, C, D, H, W = video.shape
+    planes = video.permute(0, 1, 4, 2, 3).reshape(B * C * W, 1, D, H)
+    eroded = -F.max_pool2d(-planes, 5, stride=1, padding=2)       # max_pool pads with -inf
+    opened = F.max_pool2d(eroded, 5, stride=1, padding=2)
+    return opened.reshape(B, C, W, D, H).permute(0, 1, 3, 4, 2).contiguous()
+
+
+def evaluate(labels, scores, metric):
+    """lib/evaluate.py:14-91 without the plotting / CSV side effects: the same sklearn calls
+    (``roc_curve`` + ``auc``; ``precision_recall_curve`` + ``auc``; ``f1_score`` after the 0.20 binarisation)."""
+    from sklearn.metrics import roc_curve, auc, f1_score, precision_recall_curve
+    import numpy as np
+    labels, scores = np.asarray(labels), np.asarray(scores, dtype=np.float64).copy()
+    if metric == "roc":
+        fpr, tpr, _ = roc_curve(labels, scores)
+        return float(auc(fpr, tpr))
+    if metric == "pr":
+        precision, recall, _ = precision_recall_curve(labels, scores)
+        return float(auc(recall, precision))
+    if metric == "f1_score":
+        scores[scores >= 0.20] = 1
+        scores[scores < 0.20] = 0
+        return float(f1_score(labels, scores))
+    raise NotImplementedError("Check the evaluation metric.")
+
+
+# ------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------
 def l2_loss(a, b):
@@ -224,7 +355,7 @@ class OracleTrainer:
     back-propagated with ``retain_graph`` exactly like the reference (its D gradients are wiped by
     ``optimizer_d.zero_grad()``)."""
 
-    def __init__(self, sd_g, sd_d, lr=2e-5, beta1=0.5, w_adv=1, w_con=10, round_bf16=False):
+    def __init__(self, sd_g, sd_d, lr=2e-5, beta1=0.5, w_adv=1, w_con=10, round_bf16=False, netg_fn=None):
         def split(sd):
             params, bufs = {}, {}
             for k, v in sd.items():
@@ -241,6 +372,7 @@ class OracleTrainer:
         self.opt_d = torch.optim.Adam(list(self.pd.values()), lr=lr, betas=(beta1, 0.999))
         self.w_adv, self.w_con = w_adv, w_con
         self.rb = round_bf16
+        self.netg_fn = netg_fn or netg_forward      # netg_lstm_forward for the config-3 composition
         self.bce = torch.nn.BCELoss()
 
     def sd_g(self):
@@ -252,7 +384,7 @@ class OracleTrainer:
     def step(self, inp, gt, gt_flow, pre_flow, dropout_masks=None):
         sd_g, sd_d = self.sd_g(), self.sd_d()
         # forward_g (:275-276)
-        predict = netg_forward(sd_g, inp, True, dropout_masks, round_bf16=self.rb)
+        predict = self.netg_fn(sd_g, inp, True, dropout_masks, round_bf16=self.rb)
         # forward_d (:278-286): every D input is detached
         pre_3ch, gt_3ch = gray2rgb(predict.detach()), gray2rgb(gt)
         s_pr, s_fr, t_pr, t_fr = netd_forward(sd_d, gt_3ch, gt_flow, True, self.rb)

@@ -9,6 +9,12 @@ Fixtures (small on purpose; weights are re-created from the seed, not stored, wh
   convlstm_cell.pt    ConvLSTMCell(16,32,(3,3)) state_dict + inputs + (h,c)
   losses.pt           l2_loss / weighted_bce / BCELoss values on seeded tensors
   netg_netd_small.pt  NetG(ngf=8) + SDisc/TDisc(ndf=8) outputs (train mode, dropout off); weights/inputs from seed 14
+  composed_small.pt   builder-defined compositions made of reference modules: NetG(3,8) + a
+                      ConvLSTMCell unrolled over the latent (config 3), NetG(3,8) -> gray2rgb -> second encoder with
+                      per-clip latent scores / min-max scaling / AUC over 16 clips (config 5)
+  stcnn_small.pt      models/mystcnn.py AutoEncoder: predict on a seeded clip + 3 BCELoss/Adam steps (config 4)
+  eval_small.pt       threshold + morphology_proc through cv2 (lib/utils.py:139-152) and lib/evaluate.py's
+                      roc / pr / f1_score through sklearn on seeded masks and scores
   step_traj_cfg1.pt   12 logged losses over 10 optimize_params steps of the full-size NetG/NetD at
                       BASELINE config 1 (B=4, 16x3x64x64; weights from torch.manual_seed(0) + weights_init,
                       NetD Linears sized for isize=64 as in SURVEY.md D4), dropout disabled.
@@ -35,7 +41,8 @@ sys.path.insert(0, "/root/reference")
 
 from models.spatiotempconv import SpatioTemporalConv  # noqa: E402
 from models.convlstm import ConvLSTMCell  # noqa: E402
-from models.mygannet import NetG, NetD, SDisc, TDisc  # noqa: E402
+from models.mygannet import NetG, NetD, SDisc, TDisc, NetgConv  # noqa: E402
+from models.mystcnn import AutoEncoder  # noqa: E402
 from lib.utils import weights_init, l2_loss, weighted_bce, gray2rgb  # noqa: E402
 from oracle.vfd_oracle import synthetic_batch  # noqa: E402  (only the seeded input generator)
 
@@ -44,7 +51,173 @@ def sd_clone(m):
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
+# per-clip contrast of the 16 scoring clips (a fixed shuffle of 16 levels, so every batch mixes them differently)
+SCORE_AMPS = [0.1 + 0.9 * k / 15 for k in (7, 0, 12, 3, 15, 9, 1, 5, 10, 14, 2, 6, 4, 13, 8, 11)]
+
+
+def composed_fixture():
+    """Compositions of reference modules only; the module construction / init order equals
+    vfd_gan_b200.composed's, so the tests re-create the weights from the seed."""
+    out = {}
+    # ---- config 3: NetG + ConvLSTM over the latent (models/convlstm.py:199-201 idiom, unrolled by hand because
+    #      ConvLSTM.forward's init_hidden hard-codes .cuda(), models/convlstm.py:60-62)
+    torch.manual_seed(21)
+    g = NetG(3, 8)
+    cell = ConvLSTMCell((2, 2), 128, 128, (3, 3), False)
+    g.apply(weights_init)
+    g.dropout.p = 0.0
+    g.train()
+    x = torch.rand(2, 3, 32, 32, 32) * 2 - 1
+    acts = {}
+    g.dconv5.register_forward_hook(lambda m, i, o: acts.__setitem__("latent", o))
+
+    def lstm_hook(m, inp):          # replace uconv5's input by the ConvLSTM output
+        lat = inp[0].transpose(1, 2)                        # (B, T, C, h, w)
+        h = torch.zeros(lat.shape[0], 128, 2, 2)
+        c = torch.zeros(lat.shape[0], 128, 2, 2)
+        hs = []
+        for t in range(lat.shape[1]):
+            h, c = cell(lat[:, t], (h, c))
+            hs.append(h)
+        acts["lstm"] = torch.stack(hs, dim=1).transpose(1, 2)
+        return (acts["lstm"],)
+    hook = g.uconv5.register_forward_pre_hook(lstm_hook)
+    pred = g(x)
+    gy = torch.randn(pred.shape)
+    pred.backward(gy)
+    hook.remove()
+    out["lstm"] = {"init_check": {"g": g.dconv1.conv.spatial_conv.weight.detach().flatten()[:8].clone(),
+                                  "cell": cell.conv.weight.detach().flatten()[:8].clone(), "x": x.flatten()[:8].clone()},
+                   "predict": pred.detach(), "latent": acts["lstm"].detach(), "gy": gy,
+                   "g_cell": cell.conv.weight.grad[::16].clone(),            # row samples keep the fixture small
+                   "g_dconv5_t": g.dconv5.conv.temporal_conv.weight.grad[::4].clone(),
+                   "g_uconv5_s": g.uconv5.conv.spatial_conv.weight.grad[::4].clone()}
+
+    # ---- config 5: enc-dec-enc scoring sweep (definitions: models/ganomaly.py:372,396)
+    torch.manual_seed(22)
+    g = NetG(3, 8)
+    enc = nn.ModuleList([NetgConv(3, 8), NetgConv(8, 16), NetgConv(16, 32), NetgConv(32, 64), NetgConv(64, 128)])
+    g.apply(weights_init)
+    enc.apply(weights_init)
+    g.dropout.p = 0.0
+    g.train()
+    enc.train()
+    latents = {}
+    g.dconv5.register_forward_hook(lambda m, i, o: latents.__setitem__("i", o))
+    scores, preds = [], []
+    with torch.no_grad():
+        for b in range(4):                                  # 4 batches x 4 clips; BN uses batch statistics
+            gen = torch.Generator().manual_seed(500 + b)
+            xb = torch.rand(4, 3, 16, 32, 32, generator=gen) * 2 - 1
+            amp = torch.tensor([SCORE_AMPS[4 * b + j] for j in range(4)]).view(4, 1, 1, 1, 1)
+            xb = xb * amp                                   # distinct contrast per clip spreads the scores out
+            p = g(xb)
+            h = gray2rgb(p)
+            for i, blk in enumerate(enc):
+                h = blk(h)
+                if i < 4:
+                    h = g.avgpool(h)
+            li, lo = latents["i"], h
+            scores.append(torch.mean(torch.pow(li - lo, 2).flatten(1), dim=1))     # ganomaly.py:372 over non-batch dims
+            if b == 0:
+                first = {"predict": p.clone(), "latent_i": li.clone(), "latent_o": lo.clone(),
+                         "l_enc": l2_loss(lo, li), "l_con": nn.L1Loss()(p, xb[:, :1])}
+    raw = torch.cat(scores)
+    scaled = (raw - torch.min(raw)) / (torch.max(raw) - torch.min(raw))             # ganomaly.py:396
+    # anomalous = the lowest-contrast clip of each batch: its score cluster sits between the other two, so the
+    # area is well away from 0 / 1 and no positive-negative pair is closer than 25 % (robust to bf16 compute)
+    labels = torch.tensor([int(SCORE_AMPS[i] == min(SCORE_AMPS[i // 4 * 4:i // 4 * 4 + 4])) for i in range(16)])
+    from sklearn.metrics import roc_curve, auc
+    fpr, tpr, _ = roc_curve(labels.numpy(), scaled.numpy())
+    out["score"] = {"init_check": {"g": g.dconv1.conv.spatial_conv.weight.detach().flatten()[:8].clone(),
+                                   "enc": enc[0].conv.spatial_conv.weight.detach().flatten()[:8].clone()},
+                    "first": first, "raw": raw, "scaled": scaled, "labels": labels, "auc": float(auc(fpr, tpr))}
+    torch.save(out, os.path.join(HERE, "composed_small.pt"))
+    print("composed: scores", raw.tolist(), "auc", out["score"]["auc"])
+
+
+def stcnn_fixture():
+    torch.manual_seed(15)
+    m = AutoEncoder()
+    m.apply(weights_init)
+    for blk in m.children():
+        if hasattr(blk, "dropout"):
+            blk.dropout.p = 0.0
+    m.train()
+    init_check = {"first": m.down_sep1.spaceconv.weight.detach().flatten()[:8].clone(),
+                  "last": m.conv_last.weight.detach().flatten()[:8].clone()}
+    gen = torch.Generator().manual_seed(600)
+    x = torch.rand(2, 3, 16, 32, 32, generator=gen) * 2 - 1
+    gt = (torch.rand(2, 1, 16, 32, 32, generator=gen) > 0.9).float()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-5, betas=(0.5, 0.999))      # lib/train_stcnn.py:91
+    bce = nn.BCELoss()
+    losses, first = [], None
+    for it in range(3):                                                       # lib/train_stcnn.py:104-109
+        opt.zero_grad()
+        predict = m(x)
+        err = bce(predict, gt)
+        err.backward()
+        if it == 0:
+            first = {"predict": predict.detach().clone(),
+                     "g_first": m.down_sep1.spaceconv.weight.grad.clone(),
+                     "g_up4_last": m.up_sep4.conv_last.weight.grad.clone(),
+                     "g_down4_conv_b": m.down_sep4.conv.bias.grad.clone(),
+                     "rm_bn2": m.up_sep4.bn2.running_mean.clone()}
+        opt.step()
+        losses.append(err.item())
+        print("stcnn", it, losses[-1], flush=True)
+    torch.save({"init_check": init_check, "first": first, "losses": losses}, os.path.join(HERE, "stcnn_small.pt"))
+
+
+def eval_fixture():
+    import cv2
+    import numpy as np
+    from sklearn.metrics import roc_curve, auc, f1_score, precision_recall_curve
+    gen = torch.Generator().manual_seed(700)
+    out = {}
+    cases = []
+    for shape, dens in (((2, 1, 16, 24, 40), 0.75), ((1, 1, 4, 7, 5), 0.9), ((2, 1, 16, 32, 33), 0.6)):
+        p = torch.rand(shape, generator=gen)
+        p = (p < dens).float() * (0.5 + 0.5 * torch.rand(shape, generator=gen)) + (p >= dens).float() * 0.5 * torch.rand(shape, generator=gen)
+        t = (p > torch.Tensor([0.5])).float() * 1                                     # lib/utils.py:149-152
+        kernel = np.ones((5, 5), np.uint8)                                            # lib/utils.py:139-147
+        m = np.stack([np.stack([cv2.morphologyEx(i, cv2.MORPH_OPEN, kernel) for i in v]) for v in t.numpy()])
+        cases.append({"predict": p, "t_pre": t, "m_pre": torch.from_numpy(m)})
+    out["morph"] = cases
+    # binary-mask metrics exactly as MyGAN.test feeds lib/evaluate.py (models/mygannet.py:444-448)
+    gts = (torch.rand(20000, generator=gen) > 0.85).int().numpy()
+    noise = torch.rand(20000, generator=gen).numpy()
+    pred = ((gts == 1) & (noise > 0.3) | (gts == 0) & (noise > 0.9)).astype(np.float32)
+    fpr, tpr, _ = roc_curve(gts, pred)
+    precision, recall, _ = precision_recall_curve(gts, pred)
+    sc = pred.copy()
+    sc[sc >= 0.20] = 1
+    sc[sc < 0.20] = 0
+    out["binary"] = {"gts": torch.from_numpy(gts), "pred": torch.from_numpy(pred), "roc": float(auc(fpr, tpr)),
+                     "pr": float(auc(recall, precision)), "f1": float(f1_score(gts, sc))}
+    # continuous per-clip scores with ties
+    n = 3000
+    lab = (torch.rand(n, generator=gen) > 0.7).int().numpy()
+    s = (torch.rand(n, generator=gen) * 0.6 + torch.from_numpy(lab).float() * 0.25 * torch.rand(n, generator=gen)).numpy()
+    s = np.round(s * 200) / 200                                                       # plenty of ties
+    s[:5] = 0.0
+    s[5] = -0.0
+    fpr, tpr, _ = roc_curve(lab, s)
+    out["scores"] = {"labels": torch.from_numpy(lab), "scores": torch.from_numpy(s.astype(np.float32)),
+                     "roc": float(auc(fpr, tpr))}
+    torch.save(out, os.path.join(HERE, "eval_small.pt"))
+    print("eval:", out["binary"]["roc"], out["binary"]["pr"], out["binary"]["f1"], out["scores"]["roc"])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "new":       # only the fixtures added after the first set
+        composed_fixture()
+        stcnn_fixture()
+        eval_fixture()
+        return
+    composed_fixture()
+    stcnn_fixture()
+    eval_fixture()
     # ---- SpatioTemporalConv
     torch.manual_seed(11)
     m = SpatioTemporalConv(8, 16, 3, padding=1)

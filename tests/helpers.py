@@ -48,3 +48,49 @@ def build_small_nets():
     xs = torch.rand(1, 3, 16, 128, 128)
     xt = torch.rand(2, 3, 16, 32, 32) * 2 - 1
     return g, xg, sdisc, xs, tdisc, xt
+
+
+# per-clip contrast of the 16 scoring clips of composed_small.pt (tests/golden/make_golden.py SCORE_AMPS)
+SCORE_AMPS = [0.1 + 0.9 * k / 15 for k in (7, 0, 12, 3, 15, 9, 1, 5, 10, 14, 2, 6, 4, 13, 8, 11)]
+
+
+def score_batch(b):
+    gen = torch.Generator().manual_seed(500 + b)
+    xb = torch.rand(4, 3, 16, 32, 32, generator=gen) * 2 - 1
+    return xb * torch.tensor([SCORE_AMPS[4 * b + j] for j in range(4)]).view(4, 1, 1, 1, 1)
+
+
+def build_lstm_net():
+    """NetGLstm(3, 8, isize=32) + input with the RNG sequence of make_golden.composed_fixture (seed 21)."""
+    import vfd_gan_b200 as V
+    torch.manual_seed(21)
+    g = V.NetGLstm(3, 8, isize=32)
+    g.apply(V.weights_init)
+    g.dropout.p = 0.0
+    x = torch.rand(2, 3, 32, 32, 32) * 2 - 1
+    return g, x
+
+
+def build_enc_dec_enc():
+    """EncDecEncG(3, 8) with the RNG sequence of make_golden.composed_fixture (seed 22)."""
+    import vfd_gan_b200 as V
+    torch.manual_seed(22)
+    m = V.EncDecEncG(3, 8)
+    m.apply(V.weights_init)
+    m.netg.dropout.p = 0.0
+    return m
+
+
+def build_stcnn():
+    """AutoEncoder + (clip, mask) with the RNG sequence of make_golden.stcnn_fixture (seed 15 / 600)."""
+    import vfd_gan_b200 as V
+    torch.manual_seed(15)
+    m = V.AutoEncoder()
+    m.apply(V.weights_init)
+    for blk in m.children():
+        if hasattr(blk, "dropout"):
+            blk.dropout.p = 0.0
+    gen = torch.Generator().manual_seed(600)
+    x = torch.rand(2, 3, 16, 32, 32, generator=gen) * 2 - 1
+    gt = (torch.rand(2, 1, 16, 32, 32, generator=gen) > 0.9).float()
+    return m, x, gt

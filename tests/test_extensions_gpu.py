@@ -1,0 +1,297 @@
+"""GPU (-m gpu): the scoring kernels, the builder-defined compositions (BASELINE configs 3 and 5), the STCNN
+(config 4) and the device versions of MyGAN.test's host detours, against the golden fixtures (reference modules /
+cv2 / sklearn, tests/golden/make_golden.py) and the CPU oracle. Tolerances as in test_parity_gpu.py: fp32 kernels
+1e-5, bf16-stored tensors against the operand-matched oracle 3e-3, network outputs against the fp32 fixtures
+1e-2 .. 2e-2; index / count / mask work is bit-exact."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vfd_gan_b200 as V
+from vfd_gan_b200 import ops
+from oracle import vfd_oracle as O
+from helpers import golden, rel, build_lstm_net, build_enc_dec_enc, build_stcnn, score_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------ reductions
+def test_latent_score_and_l2_gradients():
+    torch.manual_seed(0)
+    a = torch.randn(5, 20, 2, 3, 3)
+    b = torch.randn(5, 20, 2, 3, 3)
+    ac = ops.PackFn.apply(a.to(DEV), 0).requires_grad_(True)
+    bc = ops.PackFn.apply(b.to(DEV), 0).requires_grad_(True)          # 20 -> 24 padded channels
+    loss, scores = V.latent_l2_and_scores(ac, bc, 20)                  # l2_loss(latent_o, latent_i) + per-clip means
+    ar, br = a.bfloat16().float().requires_grad_(True), b.bfloat16().float().requires_grad_(True)
+    want = O.l2_loss(br, ar)
+    assert abs(float(loss) - float(want)) <= 1e-5 * float(want)
+    assert torch.allclose(scores.cpu(), O.anomaly_scores(ar, br).detach(), rtol=1e-5)
+    (loss * 3.0).backward()
+    (want * 3.0).backward()
+    ga, gb = torch.empty_like(a, device=DEV), torch.empty_like(b, device=DEV)
+    ops.unpack_ncdhw(ac.grad, ga)
+    ops.unpack_ncdhw(bc.grad, gb)
+    assert rel(ga, ar.grad) < 4e-3 and rel(gb, br.grad) < 4e-3        # gradients are stored in bf16
+    assert float(bc.grad[..., 20:].abs().max()) == 0.0
+
+
+def test_l1_and_bce_losses():
+    torch.manual_seed(1)
+    for n in (1, 7, 4096 + 3):
+        a, b = torch.randn(n), torch.randn(n)
+        b[0] = a[0]                                                    # sign(0) = 0
+        ad = a.to(DEV).requires_grad_(True)
+        ar = a.clone().requires_grad_(True)
+        got = ops.L1LossFn.apply(ad, b.to(DEV))
+        want = O.l1_loss(ar, b)
+        assert abs(float(got) - float(want)) <= 1e-5 * float(want) + 1e-7
+        (got * 2).backward()
+        (want * 2).backward()
+        assert torch.allclose(ad.grad.cpu(), ar.grad, atol=1e-7)
+        p = torch.rand(n)
+        p[0] = 0.0 if n > 1 else 0.3                                   # log clamp at -100
+        t = (torch.rand(n) > 0.5).float()
+        pd, pr = p.to(DEV).requires_grad_(True), p.clone().requires_grad_(True)
+        got = ops.BceLossFn.apply(pd, t.to(DEV))
+        want = F.binary_cross_entropy(pr, t)
+        assert abs(float(got) - float(want)) <= 1e-5 * float(want)
+        got.backward()
+        want.backward()
+        assert torch.allclose(pd.grad.cpu(), pr.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_score_scaling():
+    raw = torch.tensor([0.5, 2.0, 1.25, 0.75], device=DEV)
+    mm = torch.stack([raw.min(), raw.max()])
+    out = torch.empty_like(raw)
+    ops.score_scale(raw, mm, out)
+    assert torch.equal(out.cpu(), O.minmax_scale(raw.cpu()))
+    per_clip = torch.tensor([4.0, 1.0, 9.0], dtype=torch.float64, device=DEV)
+    scores = torch.empty(3, device=DEV)
+    mm2 = torch.tensor([float("inf"), float("-inf")], device=DEV)
+    ops.score_finalize(per_clip, 0.5, scores, mm2)
+    assert scores.tolist() == [2.0, 0.5, 4.5] and mm2.tolist() == [0.5, 4.5]
+
+
+# ------------------------------------------------------------------------------------------ config 3
+def test_netg_lstm_against_reference_fixture_and_oracle():
+    f = golden("composed_small.pt")["lstm"]
+    g, x = build_lstm_net()
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    g = g.to(DEV).train()
+    xc = ops.PackFn.apply(x.to(DEV), 0)
+    logits, latent = g.forward_cl(xc)
+    pred = ops.SigmoidHeadFn.apply(logits)
+    assert pred.shape == f["predict"].shape and rel(pred, f["predict"]) < 2e-2
+    assert rel(ops.UnpackFn.apply(latent, 128), f["latent"]) < 3e-2
+    pred.backward(f["gy"].to(DEV))
+    res = {}
+    for rb in (True, False):
+        sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        po, lo = O.netg_lstm_forward(sdo, x, True, [1.0] * 4, round_bf16=rb, return_latent=True)
+        po.backward(f["gy"])
+        res[rb] = (sdo, po.detach(), lo.detach())
+    assert rel(pred, res[True][1]) < 1e-2
+    # the ConvLSTM output is small (o * tanh(c)) and sits behind five BatchNorms over 16 samples: judge it
+    # by the bf16 envelope like the gradients (distance to fp32 <= 2x the operand-matched oracle's distance)
+    lat = ops.UnpackFn.apply(latent, 128)
+    assert rel(lat, f["latent"]) <= max(2.0 * rel(res[True][2], f["latent"]), 2e-2)
+    gw = g.clstm.cell_list[0].conv.weight.grad
+    gf, gm = res[False][0]["clstm.cell_list.0.conv.weight"].grad, res[True][0]["clstm.cell_list.0.conv.weight"].grad
+    assert rel(gw, gf) <= max(2.0 * rel(gm, gf), 2e-2)
+    assert rel(gw[::16], f["g_cell"]) <= max(2.0 * rel(gm[::16], f["g_cell"]), 2e-2)
+    for name, key in (("dconv5.conv.temporal_conv.weight", "g_dconv5_t"), ("uconv5.conv.spatial_conv.weight", "g_uconv5_s")):
+        got = dict(g.named_parameters())[name].grad
+        assert rel(got[::4], f[key]) <= max(2.0 * rel(res[True][0][name].grad[::4], f[key]), 2e-2), name
+
+
+def test_gan_step_with_convlstm_bottleneck_tracks_oracle():
+    """BASELINE config 3 in miniature: 32-frame clips, NetG + ConvLSTM bottleneck (T = 2), full GAN step."""
+    B, D, S = 2, 32, 64
+    torch.manual_seed(5)
+    netg = V.NetGLstm(3, 32, isize=S)
+    netd = V.NetD(types.SimpleNamespace(nfr=D, isize=S))
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    netg.dropout.p = 0.0
+    oracle = O.OracleTrainer(netg.state_dict(), netd.state_dict(), netg_fn=O.netg_lstm_forward)
+    w0 = netg.clstm.cell_list[0].conv.weight.detach().clone()
+    step = V.GanTrainStep(netg.to(DEV), netd.to(DEV), graph=False)
+    for it in range(2):
+        batch = O.synthetic_batch(B, D, S, seed=40 + it)
+        step.step(*(t.to(DEV) for t in batch))
+        got = step.losses_dict()
+        want, _ = oracle.step(*batch, dropout_masks=[1.0] * 4)
+        for k in want:
+            tol = 2e-2 if "adv" in k else 1e-2
+            assert abs(got[k] - want[k]) <= tol * abs(want[k]) + 1e-5, (it, k, got[k], want[k])
+    # the bottleneck trains: two Adam steps move every weight by about lr * sign(grad), so compare the updates
+    # (elements with a near-zero gradient may flip sign under bf16 compute; most must agree)
+    du = netg.clstm.cell_list[0].conv.weight.detach().cpu() - w0
+    do = oracle.pg["clstm.cell_list.0.conv.weight"].detach() - w0
+    assert float(du.abs().max()) > 1e-5
+    assert float((du * do).sum() / (du.norm() * do.norm())) > 0.9
+
+
+# ------------------------------------------------------------------------------------------ config 5
+def test_anomaly_score_sweep_against_reference_fixture():
+    f = golden("composed_small.pt")["score"]
+    m = build_enc_dec_enc()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV).train()
+    scorer = V.AnomalyScorer(m)
+    matched = []
+    for b in range(4):
+        xb = score_batch(b)
+        scorer.score_batch(xb.to(DEV))
+        with torch.no_grad():
+            _, li, lo = O.enc_dec_enc_forward(sd, xb, True, [1.0] * 4, round_bf16=True)
+        matched.append(O.anomaly_scores(li, lo))
+    scaled, raw = scorer.finish()
+    matched = torch.cat(matched)
+    raw_c, scaled_c = raw.cpu(), scaled.cpu()
+    assert torch.allclose(raw_c, matched, rtol=1e-2), (raw_c, matched)       # operand-matched oracle
+    assert torch.allclose(raw_c, f["raw"], rtol=3e-2), (raw_c, f["raw"])     # fp32 reference composition
+    assert torch.allclose(scaled_c, O.minmax_scale(raw_c), atol=1e-6)
+    assert torch.allclose(scaled_c, f["scaled"], atol=3e-2)
+    # ranking: identical wherever the reference separates two clips by more than the bf16 noise (2 %)
+    ref = f["raw"]
+    for i in range(16):
+        for j in range(16):
+            if ref[i] > 1.02 * ref[j]:
+                assert raw_c[i] > raw_c[j], (i, j)
+    # AUC to 3 decimals: device kernel on the device scores vs sklearn on the reference scores
+    labels = f["labels"].float()
+    area = V.evaluate.roc_auc(labels.to(DEV), scaled)
+    assert round(float(area[0]), 3) == round(f["auc"], 3)
+    assert int(area[1]) == int(labels.sum()) and int(area[2]) == 16 - int(labels.sum())
+    assert abs(O.evaluate(labels.numpy(), scaled_c.numpy(), "roc") - float(area[0])) < 1e-12
+
+
+def test_enc_dec_enc_training_losses_have_gradients():
+    """l_con (L1) and l_enc (latent L2) of the composition back-propagate into both encoders and the decoder."""
+    m = build_enc_dec_enc().to(DEV).train()
+    x = score_batch(1).to(DEV)
+    predict, li, lo = m.forward_cl(ops.PackFn.apply(x, 0))
+    l_enc, _ = V.latent_l2_and_scores(li, lo, m.latent_channels)
+    l_con = ops.L1LossFn.apply(predict, x[:, :1])
+    (l_con * 50 + l_enc).backward()
+    for name in ("netg.dconv1.conv.spatial_conv.weight", "netg.uconv1.conv.temporal_conv.weight",
+                 "encoder2.dconv5.conv.temporal_conv.weight", "netg.conv_last.weight"):
+        g = dict(m.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0, name
+
+
+# ------------------------------------------------------------------------------------------ config 4
+def test_stcnn_against_reference_fixture():
+    f = golden("stcnn_small.pt")
+    m, x, gt = build_stcnn()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    tr = V.StcnnTrainStep(m)
+    losses = []
+    for it in range(3):
+        err = tr.step(x.to(DEV), gt.to(DEV))
+        losses.append(float(err))
+        if it == 0:
+            first = f["first"]
+            with torch.no_grad():
+                pm = O.autoencoder_forward({k: v.clone() for k, v in sd.items()}, x, True, round_bf16=True)
+            assert rel(tr.predict, pm) < 1e-2 and rel(tr.predict, first["predict"]) < 2e-2
+            assert rel(m.up_sep4.bn2.running_mean, first["rm_bn2"]) < 3e-2
+    for got, want in zip(losses, f["losses"]):
+        assert abs(got - want) <= 1e-2 * abs(want), (losses, f["losses"])
+
+
+def test_stcnn_gradients_inside_bf16_envelope():
+    f = golden("stcnn_small.pt")["first"]
+    m, x, gt = build_stcnn()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV).train()
+    pred = m(x.to(DEV))
+    ops.BceLossFn.apply(pred, gt.to(DEV)).backward()
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    F.binary_cross_entropy(O.autoencoder_forward(sdo, x, True, round_bf16=True), gt).backward()
+    for name, key in (("down_sep1.spaceconv.weight", "g_first"), ("up_sep4.conv_last.weight", "g_up4_last"),
+                      ("down_sep4.conv.bias", "g_down4_conv_b")):
+        got, matched = dict(m.named_parameters())[name].grad, sdo[name].grad
+        assert rel(got, f[key]) <= max(2.0 * rel(matched, f[key]), 2e-2), (name, rel(got, f[key]), rel(matched, f[key]))
+
+
+def test_stcnn_dropout_path_runs():
+    m, x, gt = build_stcnn()
+    for blk in m.children():
+        if hasattr(blk, "dropout"):
+            blk.dropout.p = 0.25
+    m = m.to(DEV).train()
+    xc = ops.PackFn.apply(x.to(DEV), 0)
+    # the dropout op itself: deterministic in the seed, inverted scaling, keep rate 1 - p
+    t = torch.ones(2, 4, 16, 16, 64, dtype=torch.bfloat16, device=DEV)
+    d1, d2, d3 = (ops.IdentityPoolFn.apply(t, (1, 1, 1), 0.25, s) for s in (11, 11, 12))
+    assert torch.equal(d1, d2) and not torch.equal(d1, d3)
+    assert set(d1.float().unique().tolist()) == {0.0, float(torch.tensor(1 / 0.75).bfloat16())}
+    assert abs(float((d1 > 0).float().mean()) - 0.75) < 0.01
+    # whole net: same seeds -> same masks (run-to-run differences are fp32 atomics order amplified by the
+    # 8-sample BatchNorms at the bottleneck); other seeds -> visibly different output
+    a = m.forward_cl(xc, dropout_seeds=[1, 2, 3, 4])
+    b = m.forward_cl(xc, dropout_seeds=[1, 2, 3, 4])
+    c = m.forward_cl(xc, dropout_seeds=[5, 6, 7, 8])
+    assert torch.isfinite(a).all() and torch.isfinite(c).all()
+    print("stcnn dropout: same seeds", rel(a, b), "other seeds", rel(a, c))
+    assert rel(a, b) < 0.5 * rel(a, c)
+    a.float().sum().backward()
+    assert torch.isfinite(m.down_sep1.spaceconv.weight.grad).all()
+
+
+# ------------------------------------------------------------------------------------------ MyGAN.test detours
+def test_threshold_and_opening_bit_exact_against_cv2_fixture():
+    for case in golden("eval_small.pt")["morph"]:
+        t, m = V.evaluate.threshold_open(case["predict"].to(DEV))
+        assert torch.equal(t.cpu(), case["t_pre"])
+        assert torch.equal(m.cpu(), case["m_pre"])
+        assert torch.equal(V.evaluate.morphology_proc(case["t_pre"].to(DEV)).cpu(), case["m_pre"])
+
+
+def test_threshold_and_opening_at_full_size_properties():
+    """BASELINE-size masks (32 x 16 x 112 x 112): opening is idempotent and anti-extensive, and matches the
+    oracle restatement."""
+    torch.manual_seed(3)
+    p = torch.rand(32, 1, 16, 112, 112, device=DEV)
+    p = F.avg_pool3d(p, 3, stride=1, padding=1)                  # blobs, so the opening keeps something
+    t, m = V.evaluate.threshold_open(p, 0.5)
+    assert float(m.sum()) > 0 and bool((m <= t).all())
+    assert torch.equal(V.evaluate.morphology_proc(m), m)
+    assert torch.equal(m[:2].cpu(), O.morphology_proc(O.threshold(p[:2].cpu())))
+
+
+def test_confusion_counts_and_binary_metrics_against_sklearn_fixture():
+    b = golden("eval_small.pt")["binary"]
+    gts, pred = b["gts"].float().to(DEV), b["pred"].to(DEV)
+    counts = V.evaluate.confusion_counts(gts, pred, 0.20)
+    half = gts.numel() // 2 + 1                                   # accumulate over two ragged batches as well
+    c2 = V.evaluate.confusion_counts(gts[:half], pred[:half], 0.20)
+    c2 = V.evaluate.confusion_counts(gts[half:].clone(), pred[half:].clone(), 0.20, c2)
+    assert torch.equal(counts, c2) and int(counts.sum()) == gts.numel()
+    got = V.evaluate.binary_metrics_from_counts(*counts.tolist())
+    for key in ("roc", "pr", "f1"):
+        assert abs(got[key] - b[key]) < 1e-9, key
+
+
+def test_roc_auc_kernel_against_sklearn_fixture():
+    s = golden("eval_small.pt")["scores"]
+    out = V.evaluate.roc_auc(s["labels"].to(DEV), s["scores"].to(DEV))
+    assert abs(float(out[0]) - s["roc"]) < 1e-12
+    assert int(out[1]) == int(s["labels"].sum())
+    torch.manual_seed(9)
+    for n in (2, 1000, 1025, 16384):                              # padding / several elements per thread
+        lab = (torch.rand(n) > 0.5).float()
+        lab[0], lab[1] = 0.0, 1.0
+        sc = torch.randn(n).round(decimals=1)
+        got = V.evaluate.roc_auc(lab.to(DEV), sc.to(DEV))
+        assert abs(float(got[0]) - O.evaluate(lab.numpy(), sc.numpy(), "roc")) < 1e-12, n
+    with pytest.raises(RuntimeError):
+        V.evaluate.roc_auc(torch.zeros(20000, device=DEV), torch.zeros(20000, device=DEV))

@@ -89,3 +89,36 @@ def test_gradient_allreduce_two_ranks_gloo():
         out = mgr.dict()
         mp.spawn(_allreduce_worker, args=(world, 29731, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world))
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vfd_gan_b200.composed import gather_scores
+    local = torch.arange(3, dtype=torch.float32) + 10 * rank          # rank r scores clips [3r, 3r+3)
+    got = gather_scores(local)
+    out[rank] = got.tolist()
+    dist.destroy_process_group()
+
+
+def test_score_gather_two_ranks_gloo():
+    """Config 5 shards the clips over ranks with no data-path collective; only the per-clip scores are
+    all-gathered (rank-major) before the global min-max scaling."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gather_worker, args=(world, 29741, out), nprocs=world, join=True)
+        for r in range(world):
+            assert out[r] == [0.0, 1.0, 2.0, 10.0, 11.0, 12.0]
+
+
+def test_new_modules_fail_loudly_on_cpu():
+    import vfd_gan_b200 as V
+    with pytest.raises(RuntimeError):
+        V.evaluate.threshold_open(torch.rand(1, 1, 4, 8, 8))
+    with pytest.raises(RuntimeError):
+        V.evaluate.roc_auc(torch.zeros(4), torch.rand(4))
+    with pytest.raises(RuntimeError):
+        V.EncDecEncG(3, 8)(torch.rand(1, 3, 16, 16, 16))
+    with pytest.raises(RuntimeError):
+        V.AutoEncoder()(torch.rand(1, 3, 16, 16, 16))

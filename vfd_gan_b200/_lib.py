@@ -41,6 +41,15 @@ SIGNATURES = {
     "vfd_sqdiff": [_p, _ll, _p, _ll, _i, _ll, _p, _p],
     "vfd_convlstm_cell_fwd": [_p, _ll, _p, _i, _ll, _p, _p, _p, _p],
     "vfd_convlstm_cell_bwd": [_p, _p, _p, _p, _p, _i, _ll, _p, _ll, _p, _p],
+    "vfd_latent_score": [_p, _ll, _p, _ll, _i, _ll, _i, _p, _p],
+    "vfd_sqdiff_bwd": [_p, _ll, _p, _ll, _i, _ll, _p, _f, _p, _ll, _p, _ll, _p],
+    "vfd_l1_loss": [_p, _p, _ll, _f, _p, _p, _p],
+    "vfd_bce_loss": [_p, _p, _ll, _f, _p, _p, _p],
+    "vfd_score_finalize": [_p, _i, ctypes.c_double, _p, _p, _p],
+    "vfd_score_scale": [_p, _ll, _p, _p, _p],
+    "vfd_threshold_open": [_p, _i, _i, _i, _i, _f, _p, _p, _p],
+    "vfd_confusion_counts": [_p, _p, _ll, _f, _p, _p],
+    "vfd_roc_auc": [_p, _p, _i, _p, _p],
     "vfd_set_debug": [_i],
 }
 

@@ -119,6 +119,29 @@ class ConvLSTM(nn.Module):
             last_state_list = last_state_list[-1:]
         return layer_output_list, last_state_list
 
+    def forward_cl(self, x_cl):
+        """Channels-last unroll used inside the B200 nets: ``x_cl`` bf16 [N, T, H, W, C] (time on the depth
+        axis) -> hidden states of the last layer, bf16 [N, T, H, W, hid]. Same recurrence as ``forward``
+        (zero initial state, layers x time), without the NCHW round trips."""
+        N, T, H, W, C = x_cl.shape
+        if (H, W) != (self.height, self.width):
+            raise RuntimeError(f"ConvLSTM built for {self.height}x{self.width} maps, got {H}x{W}")
+        cur = x_cl
+        for layer_idx, cell in enumerate(self.cell_list):
+            cin = cell.input_dim
+            if cin % 8 or cell.hidden_dim % 8 or cur.shape[-1] != cin:
+                raise NotImplementedError("ConvLSTM.forward_cl needs input_dim and hidden_dim divisible by 8")
+            h = torch.zeros(N, 1, H, W, cell.hidden_dim, dtype=torch.bfloat16, device=x_cl.device)
+            c = torch.zeros(N, H, W, cell.hidden_dim, dtype=torch.float32, device=x_cl.device)
+            outs = []
+            for t in range(T):
+                comb = torch.cat([cur[:, t:t + 1], h], dim=-1)        # models/convlstm.py:46
+                h32, c = cell.forward_cl(comb, c)
+                h = h32.to(torch.bfloat16).unsqueeze(1)
+                outs.append(h)
+            cur = torch.cat(outs, dim=1)
+        return cur
+
     def _init_hidden(self, batch_size):
         return [cell.init_hidden(batch_size) for cell in self.cell_list]
 

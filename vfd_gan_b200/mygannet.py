@@ -95,6 +95,7 @@ class NetG(nn.Module):
             bufs.append(buf)
             skips.append(full)
         latent, _ = self.dconv5.forward_cl(x)
+        latent = self.bottleneck_cl(latent)
 
         p = self.dropout.p if self.dropout.training else 0.0
         if p > 0.0:
@@ -113,6 +114,18 @@ class NetG(nn.Module):
                 x, _ = blk.forward_cl(cat)
         logits = ops.ConvFn.apply(x, self.conv_last.weight, None, True, False)
         return logits, latent
+
+    def bottleneck_cl(self, latent):
+        """Hook between dconv5 and uconv5 (identity in the reference's NetG; composed.NetGLstm overrides it)."""
+        return latent
+
+    def encode_cl(self, xc):
+        """dconv1..dconv5 with the 2x2x2 average pools only (the encoder half, models/mygannet.py:57-71)."""
+        x = xc
+        for blk in (self.dconv1, self.dconv2, self.dconv3, self.dconv4):
+            _, x = blk.forward_cl(x, pool=(2, 2, 2), want_full=False, want_pool=True)
+        latent, _ = self.dconv5.forward_cl(x)
+        return latent
 
     def forward(self, x):
         logits, _ = self.forward_cl(ops.PackFn.apply(x, 0))

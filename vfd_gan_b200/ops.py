@@ -252,6 +252,53 @@ def _convlstm_cell_bwd(act, c_cur, c_next, dh, dc_in, dgates, dc_cur):
               hid, c_cur.numel() // hid, dgates.data_ptr(), _ld(dgates), dc_cur.data_ptr(), _stream())
 
 
+def _latent_score(a, b, per_clip):
+    N, D, H, W, C, ld = _check_cl(a, "latent_score a")
+    _check_cl(b, "latent_score b")
+    if tuple(b.shape) != tuple(a.shape):
+        raise RuntimeError(f"latent_score: shapes differ, {tuple(a.shape)} vs {tuple(b.shape)}")
+    _lib.call("vfd_latent_score", a.data_ptr(), ld, b.data_ptr(), _ld(b), C, D * H * W, N, per_clip.data_ptr(),
+              _stream())
+
+
+def _sqdiff_bwd(a, b, gscale, scale, ga, gb):
+    N, D, H, W, C, ld = _check_cl(a, "sqdiff_bwd a")
+    _check_cl(b, "sqdiff_bwd b")
+    _lib.call("vfd_sqdiff_bwd", a.data_ptr(), ld, b.data_ptr(), _ld(b), C, N * D * H * W, _ptr(gscale), scale,
+              _ptr(ga), 0 if ga is None else _ld(ga), _ptr(gb), 0 if gb is None else _ld(gb), _stream())
+
+
+def _l1_loss(a, b, grad_scale, out, ga):
+    _lib.call("vfd_l1_loss", a.data_ptr(), b.data_ptr(), a.numel(), grad_scale, out.data_ptr(), _ptr(ga), _stream())
+
+
+def _bce_loss(p, t, grad_scale, out, gp):
+    _lib.call("vfd_bce_loss", p.data_ptr(), t.data_ptr(), p.numel(), grad_scale, out.data_ptr(), _ptr(gp), _stream())
+
+
+def _score_finalize(per_clip, inv_count, scores, minmax):
+    _lib.call("vfd_score_finalize", per_clip.data_ptr(), per_clip.numel(), inv_count, scores.data_ptr(),
+              _ptr(minmax), _stream())
+
+
+def _score_scale(scores, minmax, out):
+    _lib.call("vfd_score_scale", scores.data_ptr(), scores.numel(), minmax.data_ptr(), out.data_ptr(), _stream())
+
+
+def _threshold_open(predict, thr, t_out, m_out):
+    N, D, H, W = predict.shape[0], predict.shape[-3], predict.shape[-2], predict.shape[-1]
+    _lib.call("vfd_threshold_open", predict.data_ptr(), N, D, H, W, thr, _ptr(t_out), m_out.data_ptr(), _stream())
+
+
+def _confusion_counts(labels, scores, thr, counts):
+    _lib.call("vfd_confusion_counts", labels.data_ptr(), scores.data_ptr(), labels.numel(), thr, counts.data_ptr(),
+              _stream())
+
+
+def _roc_auc(scores, labels, out):
+    _lib.call("vfd_roc_auc", scores.data_ptr(), labels.data_ptr(), scores.numel(), out.data_ptr(), _stream())
+
+
 conv3d_fwd = _define(
     "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
@@ -296,6 +343,20 @@ convlstm_cell_fwd = _define(
 convlstm_cell_bwd = _define(
     "convlstm_cell_bwd(Tensor act, Tensor c_cur, Tensor c_next, Tensor? dh, Tensor? dc_in, Tensor(a!) dgates, "
     "Tensor(b!) dc_cur) -> ()", _convlstm_cell_bwd)
+
+latent_score = _define("latent_score(Tensor a, Tensor b, Tensor(a!) per_clip) -> ()", _latent_score)
+sqdiff_bwd = _define("sqdiff_bwd(Tensor a, Tensor b, Tensor? gscale, float scale, Tensor(a!)? ga, Tensor(b!)? gb) -> ()",
+                     _sqdiff_bwd)
+l1_loss_op = _define("l1_loss(Tensor a, Tensor b, float grad_scale, Tensor(a!) out, Tensor(b!)? ga) -> ()", _l1_loss)
+bce_loss_op = _define("bce_loss(Tensor p, Tensor t, float grad_scale, Tensor(a!) out, Tensor(b!)? gp) -> ()", _bce_loss)
+score_finalize = _define("score_finalize(Tensor per_clip, float inv_count, Tensor(a!) scores, Tensor(b!)? minmax) -> ()",
+                         _score_finalize)
+score_scale = _define("score_scale(Tensor scores, Tensor minmax, Tensor(a!) out) -> ()", _score_scale)
+threshold_open_op = _define("threshold_open(Tensor predict, float thr, Tensor(a!)? t_out, Tensor(b!) m_out) -> ()",
+                            _threshold_open)
+confusion_counts_op = _define("confusion_counts(Tensor labels, Tensor scores, float thr, Tensor(a!) counts) -> ()",
+                              _confusion_counts)
+roc_auc_op = _define("roc_auc(Tensor scores, Tensor labels, Tensor(a!) out) -> ()", _roc_auc)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -771,6 +832,122 @@ class MeanDimsFn(torch.autograd.Function):
         for d in sorted(dims):
             gb = gb.unsqueeze(d)
         return gb.expand(shape).contiguous(), None, None
+
+
+class IdentityPoolFn(torch.autograd.Function):
+    """AvgPool3d (and / or Dropout) with no BatchNorm in front (the shortcut branch of C2plus1d_Block,
+    models/mystcnn.py:37-44): the fused BN+act kernel run with scale 1, shift 0 and slope 1."""
+
+    @staticmethod
+    def forward(ctx, x, pool, drop_p, seed):
+        N, D, H, W, C, _ = _check_cl(x, "pool input")
+        pd, ph, pw = pool
+        dev = x.device
+        k = torch.zeros(4, C, dtype=torch.float32, device=dev)   # mean 0, invstd 1, scale 1, shift 0
+        k[1:3] = 1.0
+        pooled = pd * ph * pw > 1
+        out = cl_empty(N, D // pd, H // ph, W // pw, C, dev)
+        bn_act_fwd(x, k[2], k[3], 1.0, None if pooled else out, out if pooled else None, pd, ph, pw, drop_p, seed)
+        ctx.save_for_backward(x, k)
+        ctx.cfg = (pool, drop_p, seed, pooled)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, k = ctx.saved_tensors
+        (pd, ph, pw), drop_p, seed, pooled = ctx.cfg
+        N, D, H, W, C, _ = _check_cl(x, "pool saved input")
+        g = as_cl_grad(g)
+        dx = cl_empty(N, D, H, W, C, x.device)
+        tmp = torch.empty(4, C, dtype=torch.float32, device=x.device)
+        bn_act_bwd(x, C, k[0], k[1], k[2], k[3], 1.0, None if pooled else g, g if pooled else None, pd, ph, pw,
+                   drop_p, seed, False, bn_scratch(x.device, C), tmp[0], tmp[1], tmp[2], tmp[3], dx)
+        return dx, None, None, None
+
+
+class UpsampleFn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) on channels-last bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, D, H, W, C, _ = _check_cl(x, "upsample input")
+        out = cl_empty(N, 2 * D, 2 * H, 2 * W, C, x.device)
+        upsample2x_fwd(x, out)
+        ctx.low_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = as_cl_grad(g)
+        gx = torch.empty(ctx.low_shape, dtype=torch.bfloat16, device=g.device)
+        upsample2x_bwd(g, gx)
+        return gx
+
+
+class LatentL2Fn(torch.autograd.Function):
+    """l2_loss of two channels-last bf16 latents (l_enc, models/ganomaly.py:439,477) with gradients to both,
+    returned together with the per-clip means the anomaly score uses (models/ganomaly.py:372)."""
+
+    @staticmethod
+    def forward(ctx, a, b, valid_channels):
+        N, D, H, W, C, _ = _check_cl(a, "latent a")
+        per_clip = torch.zeros(N, dtype=torch.float64, device=a.device)
+        latent_score(a, b, per_clip)
+        count = D * H * W * valid_channels
+        scores = torch.empty(N, dtype=torch.float32, device=a.device)
+        score_finalize(per_clip, 1.0 / max(count, 1), scores, None)
+        ctx.save_for_backward(a, b)
+        ctx.inv = 1.0 / max(N * count, 1)
+        ctx.mark_non_differentiable(scores)
+        return (per_clip.sum() * ctx.inv).float(), scores
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        a, b = ctx.saved_tensors
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        sqdiff_bwd(a, b, g.contiguous().float().reshape(1), ctx.inv, ga, gb)
+        return ga, gb, None
+
+
+class L1LossFn(torch.autograd.Function):
+    """nn.L1Loss() (mean) on fp32 tensors (l_con of the enc-dec-enc composition, models/ganomaly.py:438,476)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        if not a.is_cuda:
+            raise RuntimeError("l1_loss: vfd_gan_b200 has no CPU path")
+        out = torch.zeros((), dtype=torch.float64, device=a.device)
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] else None
+        l1_loss_op(a, b, 1.0 / max(a.numel(), 1), out, ga)
+        ctx.save_for_backward(ga)
+        return (out / max(a.numel(), 1)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (ga,) = ctx.saved_tensors
+        return (ga * g if ctx.needs_input_grad[0] else None), (-ga * g if ctx.needs_input_grad[1] else None)
+
+
+class BceLossFn(torch.autograd.Function):
+    """nn.BCELoss() (mean, log clamped at -100) on fp32 tensors, gradient to the prediction only."""
+
+    @staticmethod
+    def forward(ctx, p, t):
+        p, t = p.contiguous().float(), t.contiguous().float()
+        if not p.is_cuda:
+            raise RuntimeError("bce_loss: vfd_gan_b200 has no CPU path")
+        out = torch.zeros((), dtype=torch.float64, device=p.device)
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        bce_loss_op(p, t, 1.0 / max(p.numel(), 1), out, gp)
+        ctx.save_for_backward(gp)
+        return (out / max(p.numel(), 1)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return gp * g, None
 
 
 def mse_cl(a, b, valid_channels):
