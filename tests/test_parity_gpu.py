@@ -63,6 +63,31 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, N, D, H, W):
     assert rel(tc[3], gyr.sum((0, 2, 3, 4))) < 1e-4
 
 
+@pytest.mark.parametrize("cin,cout,N,D,H,W,bias", [(3, 2, 2, 5, 9, 11, False), (8, 8, 1, 3, 7, 5, True), (3, 2, 4, 16, 32, 32, False)])
+def test_tiny_pointwise_conv_and_fused_statistics(cin, cout, N, D, H, W, bias):
+    """1x1x1 convs with <= 8 channels on both sides take the CUDA-core streaming kernel (bf16 output): same
+    values as the fp32 reference on bf16 operands, and its fused BatchNorm statistics equal the sums of the
+    stored tensor."""
+    torch.manual_seed(cin * 10 + cout)
+    x = torch.randn(N, cin, D, H, W)
+    w = torch.randn(cout, cin, 1, 1, 1) * 0.3
+    b = torch.randn(cout) if bias else None
+    xc = ops.PackFn.apply(x.to(DEV), 0)
+    C = ops.round_up(cout, 8)
+    scratch = ops.bn_scratch(xc.device, C)
+    scratch.zero_()
+    yc = ops.ConvFn.apply(xc, w.to(DEV), None if b is None else b.to(DEV), False, False, True)
+    stats = scratch.clone()
+    scratch.zero_()
+    want = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), b)
+    got = ops.UnpackFn.apply(yc, cout).cpu()
+    assert rel(got, want) < 3e-3                                   # bf16-stored output
+    assert float(yc[..., cout:].abs().max()) == 0.0 if cout < C else True
+    yf = yc.float().reshape(-1, C).double()
+    exact = torch.cat([yf.sum(0), (yf ** 2).sum(0)])
+    assert float((stats - exact).abs().max()) <= 1e-5 * float(exact.abs().max())
+
+
 def test_conv_dgrad_fp32_output_meets_1e3():
     """dgrad with the fp32 epilogue: only accumulation order differs from the matched oracle."""
     x = torch.randn(2, 64, 2, 16, 16, device=DEV)

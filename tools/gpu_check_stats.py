@@ -8,7 +8,8 @@ ok = True
 for cin, cout, k, N, D, H, W in [(32, 48, (1, 3, 3), 2, 2, 16, 32), (96, 86, (1, 3, 3), 1, 2, 32, 32),
                                  (64, 230, (1, 3, 3), 2, 4, 8, 8), (256, 921, (1, 3, 3), 2, 1, 2, 2),
                                  (837, 1024, (1, 1, 1), 2, 16, 2, 2), (115, 64, (3, 1, 1), 2, 8, 16, 16),
-                                 (3, 21, (1, 3, 3), 2, 16, 32, 32), (21, 32, (3, 1, 1), 2, 16, 32, 32)]:
+                                 (3, 21, (1, 3, 3), 2, 16, 32, 32), (21, 32, (3, 1, 1), 2, 16, 32, 32),
+                                 (3, 2, (1, 1, 1), 2, 16, 32, 32)]:
     x = torch.randn(N, D, H, W, ops.round_up(cin, 8), device="cuda").bfloat16()
     x[..., cin:] = 0
     w = torch.randn(cout, cin, *k, device="cuda") * 0.1

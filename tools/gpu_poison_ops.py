@@ -131,6 +131,7 @@ CASES = {
     "conv 32->1 3x3x3 fp32": conv_case(32, 1, (3, 3, 3), 1, 4, 9, 10, out_fp32=True),
     "conv 2->32 3x1x1": conv_case(2, 32, (3, 1, 1), 1, 8, 12, 20, fuse=True),
     "conv 14->32 1x1x1": conv_case(14, 32, (1, 1, 1), 3, 5, 9, 11, fuse=True),
+    "conv 3->2 1x1x1 tiny": conv_case(3, 2, (1, 1, 1), 3, 5, 9, 11, fuse=True),
     "conv 3->64 1x1x1 bias": conv_case(3, 64, (1, 1, 1), 2, 4, 8, 8, bias=True),
     "conv 128->64 3x3x3": conv_case(128, 64, (3, 3, 3), 1, 2, 7, 7),
     "conv 256->600 1x3x3": conv_case(256, 600, (1, 3, 3), 2, 1, 6, 6, fuse=True),
@@ -151,7 +152,10 @@ CASES = {
 }
 
 bad = 0
-for name, fn in CASES.items():
+filt = [a for a in sys.argv[1:] if not a.startswith("x")]
+reps = max([int(a[1:]) for a in sys.argv[1:] if a.startswith("x")] + [1])
+todo = [(n, f) for n, f in CASES.items() if not filt or any(s in n for s in filt)] * reps
+for name, fn in todo:
     outs = []
     for pat in (0, 0, 0x7FC07FC0, 0x7F807F80):
         poison(pat)
@@ -166,8 +170,12 @@ for name, fn in CASES.items():
                 msgs.append(f"{k} not finite under {tag}-poison")
             else:
                 d = float((other[k].double() - ref[k].double()).norm() / (ref[k].double().norm() + 1e-30))
-                if d > 4 * noise + 1e-6:
-                    msgs.append(f"{k} moves {d:.2e} under {tag}-poison (noise {noise:.1e})")
+                if d > 4 * noise + 5e-4:   # a lone bf16-ulp flip (fp64 atomics order) stays below this
+                    diff = (other[k].double() - ref[k].double()).abs().flatten()
+                    nz = diff.nonzero().flatten()
+                    msgs.append(f"{k} moves {d:.2e} under {tag}-poison (noise {noise:.1e}; {nz.numel()} of "
+                                f"{diff.numel()} elements, first idx {nz[:6].tolist()}, max {float(diff.max()):.3e}, "
+                                f"ref there {float(ref[k].flatten()[diff.argmax()]):.4e})")
     bad += len(msgs)
     print(f"{name:32s}", "clean" if not msgs else "; ".join(msgs), flush=True)
 print("POISON OPS", "CLEAN" if bad == 0 else f"{bad} PROBLEMS")

@@ -1,5 +1,5 @@
 """Time the fused BatchNorm+activation(+pool) forward / backward kernels on the step's largest shapes.
-    python tools/gpu_time_bn.py [reps]"""
+    python tools/gpu_time_bn.py [reps] [case-name-substring ...]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -16,6 +16,8 @@ CASES = [  # name, C, (N, D, H, W), pool, want_full, want_pool, slope
     ("dconv1.inner", 21, (32, 16, 112, 112), (1, 1, 1), True, False, 0.0),
     ("uconv2.inner", 172, (32, 8, 56, 56), (1, 1, 1), True, False, 0.0),
 ]
+if len(sys.argv) > 2:
+    CASES = [c for c in CASES if any(s in c[0] for s in sys.argv[2:])]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 

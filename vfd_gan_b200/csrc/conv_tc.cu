@@ -1741,6 +1741,11 @@ static bool res_enabled() {
 
 }  // namespace vfd
 
+namespace vfd {
+int launch_tiny_pointwise(const void* x, long long x_ld, const void* w_packed, int cin_k, const float* bias, void* out,
+                          long long out_ld, long long V, double* stats, int stats_ld, cudaStream_t stream);
+}
+
 using namespace vfd;
 
 VFD_API int vfd_set_debug(int flags) {
@@ -1763,6 +1768,10 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
       (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(VFD_ERR_ARG, "conv3d_fwd: output must be 16-byte aligned");
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;  // empty batch: nothing to do
+  if (kd == 1 && kh == 1 && kw == 1 && cin <= 8 && out_cols == 8 && w_rows == 16 && !out_fp32 && !(g_dbg & 64) &&
+      (x_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    return launch_tiny_pointwise(x, x_ld, w_packed, cin_k, bias, out, out_ld, (long long)N * D * H * W, stats,
+                                 stats_ld, stream);
   Epilogue epi;
   epi.n_rows = w_rows;
   epi.out_cols = out_cols;

@@ -105,54 +105,66 @@ thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
 
   const long long groups = (V + 15) >> 4;
   const long long gstride = static_cast<long long>(gridDim.x) * (kThinThreads / 32);
-  for (long long grp = static_cast<long long>(blockIdx.x) * (kThinThreads / 32) + warp; grp < groups; grp += gstride) {
-    const long long v0 = grp << 4;
-    uint4 rx[2], ry[2];
+  // GU groups per iteration: all their loads are issued before the first one is consumed, so a warp keeps
+  // GU x 4 independent 128-bit loads in flight (a single 16-voxel group of a 3 -> 2 channel layer is 512 bytes --
+  // far too little to cover the DRAM latency). The on-the-fly tap gathers are instruction bound: GU = 1 there.
+  constexpr int GU = (FX::kFold || FY::kFold) ? 1 : 4;
+  for (long long grp0 = static_cast<long long>(blockIdx.x) * (kThinThreads / 32) + warp; grp0 < groups;
+       grp0 += gstride * GU) {
+    uint4 rx[GU][2], ry[GU][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const long long v = v0 + lrow + 8 * i;
-      rx[i] = make_uint4(0u, 0u, 0u, 0u);
-      ry[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (v < V) {
-        unsigned n = 0;
-        int d = 0, h = 0, w = 0;
-        if (FX::kFold || FY::kFold) {
-          const unsigned vv = static_cast<unsigned>(v);
-          const unsigned t1 = fdivt(vv, fg.fW);
-          w = vv - t1 * fg.W;
-          const unsigned t2 = fdivt(t1, fg.fH);
-          h = t1 - t2 * fg.H;
-          n = fdivt(t2, fg.fD);
-          d = t2 - n * fg.D;
-        }
-        if (lchunk < xchunks) {
-          if constexpr (FX::kFold) rx[i] = FX::chunk_of(x, x_ld, fg, n, d, h, w, lchunk, 1);
-          else rx[i] = __ldg(reinterpret_cast<const uint4*>(x + v * x_ld) + lchunk);
-        }
-        if (lchunk < NT) {
-          if constexpr (FY::kFold) ry[i] = FY::chunk_of(dy, dy_ld, fg, n, d, h, w, lchunk, -1);
-          else ry[i] = __ldg(reinterpret_cast<const uint4*>(dy + v * dy_ld) + lchunk);
+    for (int u = 0; u < GU; ++u) {
+      const long long v0 = (grp0 + u * gstride) << 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const long long v = v0 + lrow + 8 * i;
+        rx[u][i] = make_uint4(0u, 0u, 0u, 0u);
+        ry[u][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (v < V) {
+          unsigned n = 0;
+          int d = 0, h = 0, w = 0;
+          if (FX::kFold || FY::kFold) {
+            const unsigned vv = static_cast<unsigned>(v);
+            const unsigned t1 = fdivt(vv, fg.fW);
+            w = vv - t1 * fg.W;
+            const unsigned t2 = fdivt(t1, fg.fH);
+            h = t1 - t2 * fg.H;
+            n = fdivt(t2, fg.fD);
+            d = t2 - n * fg.D;
+          }
+          if (lchunk < xchunks) {
+            if constexpr (FX::kFold) rx[u][i] = FX::chunk_of(x, x_ld, fg, n, d, h, w, lchunk, 1);
+            else rx[u][i] = __ldg(reinterpret_cast<const uint4*>(x + v * x_ld) + lchunk);
+          }
+          if (lchunk < NT) {
+            if constexpr (FY::kFold) ry[u][i] = FY::chunk_of(dy, dy_ld, fg, n, d, h, w, lchunk, -1);
+            else ry[u][i] = __ldg(reinterpret_cast<const uint4*>(dy + v * dy_ld) + lchunk);
+          }
         }
       }
     }
-    __syncwarp();   // the previous group's ldmatrix reads are done
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      *reinterpret_cast<uint4*>(tx + (lrow + 8 * i) * kThinRowBytes + lchunk * 16) = rx[i];
-      *reinterpret_cast<uint4*>(ty + (lrow + 8 * i) * kThinRowBytes + lchunk * 16) = ry[i];
-    }
-    __syncwarp();
-    uint32_t a[MT][4];
+    for (int u = 0; u < GU; ++u) {
+      if (grp0 + u * gstride >= groups) break;   // warp-uniform
+      __syncwarp();   // the previous group's ldmatrix reads are done
 #pragma unroll
-    for (int m = 0; m < MT; ++m) ldmatrix_x4_trans(tx_s + a_off + m * 32, a[m][0], a[m][1], a[m][2], a[m][3]);
+      for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<uint4*>(tx + (lrow + 8 * i) * kThinRowBytes + lchunk * 16) = rx[u][i];
+        *reinterpret_cast<uint4*>(ty + (lrow + 8 * i) * kThinRowBytes + lchunk * 16) = ry[u][i];
+      }
+      __syncwarp();
+      uint32_t a[MT][4];
 #pragma unroll
-    for (int np = 0; np < (NT + 1) / 2; ++np) {
-      uint32_t b0, b1, b2, b3;   // n-tile 2np: (b0, b1); n-tile 2np+1: (b2, b3)
-      ldmatrix_x4_trans(ty_s + b_off + np * 32, b0, b1, b2, b3);
+      for (int m = 0; m < MT; ++m) ldmatrix_x4_trans(tx_s + a_off + m * 32, a[m][0], a[m][1], a[m][2], a[m][3]);
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        mma_bf16_16816(c[m][2 * np], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
-        if (2 * np + 1 < NT) mma_bf16_16816(c[m][2 * np + 1], a[m][0], a[m][1], a[m][2], a[m][3], b2, b3);
+      for (int np = 0; np < (NT + 1) / 2; ++np) {
+        uint32_t b0, b1, b2, b3;   // n-tile 2np: (b0, b1); n-tile 2np+1: (b2, b3)
+        ldmatrix_x4_trans(ty_s + b_off + np * 32, b0, b1, b2, b3);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          mma_bf16_16816(c[m][2 * np], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
+          if (2 * np + 1 < NT) mma_bf16_16816(c[m][2 * np + 1], a[m][0], a[m][1], a[m][2], a[m][3], b2, b3);
+        }
       }
     }
   }
@@ -173,6 +185,78 @@ thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
   for (int i = threadIdx.x; i < 32 * 32; i += kThinThreads) {
     const int ci = i >> 5, co = i & 31;
     if (ci < cin && co < cout) atomicAdd(acc + static_cast<size_t>(ci) * co_pad + co, red[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tiny 1x1x1 forward
+// 1x1x1 conv with at most 8 input and 8 output channels (the temporal discriminator's first "spatial" conv,
+// 3 -> 2 channels, models/spatiotempconv.py:49-50 with kernel (3,1,1)): 32 bytes of traffic per voxel and 64
+// FMAs -- a pure HBM stream that the 128-row tcgen05 tile serves at a fifth of the bandwidth. One thread per
+// voxel: one 128-bit load, the 8 x 8 product from registers, one 128-bit store; the BatchNorm statistics of the
+// stored (bf16-rounded) values are kept in registers and reduced once per block.
+__global__ void __launch_bounds__(256)
+tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __restrict__ w_packed, int cin_k,
+                      const float* __restrict__ bias, bf16* __restrict__ out, long long out_ld, long long V,
+                      double* __restrict__ stats, int stats_ld) {
+  __shared__ float s_stat[16];
+  float w[8][8], b[8], ssum[8], ssq[8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    b[co] = bias != nullptr ? __ldg(bias + co) : 0.f;
+    ssum[co] = ssq[co] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) w[co][ci] = __bfloat162float(w_packed[co * cin_k + ci]);
+  }
+  if (threadIdx.x < 16) s_stat[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + v * x_ld));
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    float xi[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xi[2 * i] = __uint_as_float(uu[i] << 16);
+      xi[2 * i + 1] = __uint_as_float(uu[i] & 0xFFFF0000u);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      float a0 = b[2 * cp], a1 = b[2 * cp + 1];
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        a0 = fmaf(xi[ci], w[2 * cp][ci], a0);
+        a1 = fmaf(xi[ci], w[2 * cp + 1][ci], a1);
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+      o[cp] = *reinterpret_cast<const uint32_t*>(&h);
+      const float r0 = __uint_as_float(o[cp] << 16), r1 = __uint_as_float(o[cp] & 0xFFFF0000u);
+      ssum[2 * cp] += r0;
+      ssum[2 * cp + 1] += r1;
+      ssq[2 * cp] = fmaf(r0, r0, ssq[2 * cp]);
+      ssq[2 * cp + 1] = fmaf(r1, r1, ssq[2 * cp + 1]);
+    }
+    *reinterpret_cast<uint4*>(out + v * out_ld) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = ssum[c], q = ssq[c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        q += __shfl_xor_sync(0xffffffffu, q, off);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_stat[c], a);
+        atomicAdd(&s_stat[8 + c], q);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int c = threadIdx.x & 7;
+      const float val = s_stat[threadIdx.x];
+      if (c < stats_ld && val != 0.f) atomicAdd(stats + (threadIdx.x < 8 ? 0 : stats_ld) + c, (double)val);
+    }
   }
 }
 
@@ -244,3 +328,15 @@ VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, con
 #undef VFD_THIN_ARGS
   return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: unsupported tile shape / fold combination");
 }
+
+// Internal (called from vfd_conv3d_fwd): 1x1x1, <= 8 input and <= 8 output channels, bf16 output.
+namespace vfd {
+int launch_tiny_pointwise(const void* x, long long x_ld, const void* w_packed, int cin_k, const float* bias, void* out,
+                          long long out_ld, long long V, double* stats, int stats_ld, cudaStream_t stream) {
+  long long blocks = (V + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tiny_pointwise_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)x, x_ld, (const bf16*)w_packed, cin_k, bias,
+                                                         (bf16*)out, out_ld, V, stats, stats_ld);
+  return check_launch("tiny_pointwise");
+}
+}  // namespace vfd
