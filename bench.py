@@ -102,6 +102,36 @@ class KernelProfiler:
         with open(path, "w") as f:
             json.dump(rows, f)
 
+    def conv_by_bound(self, steps, peak_tflops, peak_gbs):
+        """Every conv launch is bounded either by the tensor pipe or by HBM, whichever of
+        FLOPs / peak and algorithmic bytes / peak is larger (ridge = peak_tflops / peak_gbs FLOP per byte).
+        -> achieved fraction of the applicable roofline for each class, and the attainable time of the lot."""
+        cls = {"tensor": {"ms": 0.0, "flop": 0.0, "bytes": 0.0, "launches": 0, "t_min_ms": 0.0},
+               "hbm": {"ms": 0.0, "flop": 0.0, "bytes": 0.0, "launches": 0, "t_min_ms": 0.0}}
+        for kind, work, a, b, nb in self.records:
+            if not kind.startswith("conv"):
+                continue
+            t_tc, t_mem = work / (peak_tflops * 1e12) * 1e3, nb / (peak_gbs * 1e9) * 1e3
+            c = cls["tensor" if t_tc >= t_mem else "hbm"]
+            c["ms"] += a.elapsed_time(b)
+            c["flop"] += work
+            c["bytes"] += nb
+            c["launches"] += 1
+            c["t_min_ms"] += max(t_tc, t_mem)
+        out = {}
+        for name, c in cls.items():
+            if not c["launches"]:
+                continue
+            ach = c["flop"] / (c["ms"] * 1e-3) / 1e12 if name == "tensor" else c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            peak = peak_tflops if name == "tensor" else peak_gbs
+            out[name + "_bound_layers"] = {"launches_per_step": c["launches"] / steps, "ms_per_step": c["ms"] / steps,
+                                           "achieved": ach, "unit": "TFLOP/s" if name == "tensor" else "GB/s",
+                                           "peak": peak, "frac": ach / peak}
+        tot_ms = sum(c["ms"] for c in cls.values())
+        out["attainable_ms_per_step"] = sum(c["t_min_ms"] for c in cls.values()) / steps
+        out["frac_of_attainable"] = sum(c["t_min_ms"] for c in cls.values()) / tot_ms if tot_ms else None
+        return out
+
     def summary(self, steps):
         out = {}
         for kind, work, a, b, _nb in self.records:
@@ -340,7 +370,8 @@ def main():
                     "note": "aggregate over all launches of the dominant conv kernel kind in one step: algorithmic "
                             "FLOPs / CUDA-event time; most of these launches are thin HBM-bound layers",
                     "all_conv": {"tflops": conv_flops / (conv_ms * 1e-3) / 1e12, "ms_per_step": conv_ms,
-                                 "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}}
+                                 "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]},
+                    "conv_by_bound": prof.conv_by_bound(psteps, peaks["bf16_tflops"], peaks["hbm_gbs"])}
         bn = {k: v for k, v in kernels.items() if k in ("bn_act_fwd", "bn_act_bwd")}
         if bn:
             bn_bytes = sum(v["work"] for v in bn.values())
