@@ -13,6 +13,8 @@ Fixtures (small on purpose; weights are re-created from the seed, not stored, wh
                       ConvLSTMCell unrolled over the latent (config 3), NetG(3,8) -> gray2rgb -> second encoder with
                       per-clip latent scores / min-max scaling / AUC over 16 clips (config 5)
   stcnn_small.pt      models/mystcnn.py AutoEncoder: predict on a seeded clip + 3 BCELoss/Adam steps (config 4)
+  flow_small.pt       lib/utils.py video_to_flow (the reference function itself: cv2 Farneback + HSV encoding) on a
+                      seeded smooth clip, as uint8 levels, plus cv2.calcOpticalFlowFarneback fields of two frame pairs
   eval_small.pt       threshold + morphology_proc through cv2 (lib/utils.py:139-152) and lib/evaluate.py's
                       roc / pr / f1_score through sklearn on seeded masks and scores
   step_traj_cfg1.pt   12 logged losses over 10 optimize_params steps of the full-size NetG/NetD at
@@ -23,6 +25,7 @@ import os
 import sys
 import types
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -209,7 +212,39 @@ def eval_fixture():
     print("eval:", out["binary"]["roc"], out["binary"]["pr"], out["binary"]["f1"], out["scores"]["roc"])
 
 
+def flow_clip(B, D, S, seed):
+    """Seeded smooth clip in [-1, 1] (blurred noise + per-frame brightness drift) -- shared with the tests."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(B, 3, D, S + 16, S + 16, generator=g)
+    vid = torch.nn.functional.avg_pool3d(base, (1, 9, 9), stride=1, padding=(0, 4, 4))[:, :, :, 8:8 + S, 8:8 + S]
+    vid = (vid - vid.min()) / (vid.max() - vid.min())
+    return (vid * 0.8 + 0.2 * torch.rand(B, 3, D, 1, 1, generator=g)) * 2 - 1
+
+
+def flow_fixture():
+    import warnings
+    import cv2
+    from lib.utils import video_to_flow
+    from oracle import flow_oracle as FO
+    warnings.simplefilter("ignore")                # np.uint8() of out-of-range floats warns in numpy 2
+    out = {}
+    for name, (B, D, S, seed) in {"s64": (2, 4, 64, 800), "s112": (1, 3, 112, 801), "s128": (1, 3, 128, 802)}.items():
+        vid = flow_clip(B, D, S, seed)
+        ref = video_to_flow(vid)                                               # the reference function, on CPU
+        levels = torch.round((ref + 1) * 0.5 * 255).to(torch.uint8)
+        assert float(((levels.float() / 255) * 2 - 1 - ref).abs().max()) < 1e-6
+        grey = FO.gray_frames(vid.numpy())
+        raw = [cv2.calcOpticalFlowFarneback(grey[0, i], grey[0, i + 1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+               for i in range(2)]
+        out[name] = {"cfg": (B, D, S, seed), "levels": levels, "cv2_flow_b0": torch.from_numpy(np.stack(raw))}
+        print("flow", name, tuple(ref.shape), float(ref.mean()), flush=True)
+    torch.save(out, os.path.join(HERE, "flow_small.pt"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "flow":
+        flow_fixture()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "new":       # only the fixtures added after the first set
         composed_fixture()
         stcnn_fixture()
@@ -218,6 +253,7 @@ def main():
     composed_fixture()
     stcnn_fixture()
     eval_fixture()
+    flow_fixture()
     # ---- SpatioTemporalConv
     torch.manual_seed(11)
     m = SpatioTemporalConv(8, 16, 3, padding=1)

@@ -94,3 +94,19 @@ def build_stcnn():
     x = torch.rand(2, 3, 16, 32, 32, generator=gen) * 2 - 1
     gt = (torch.rand(2, 1, 16, 32, 32, generator=gen) > 0.9).float()
     return m, x, gt
+
+
+def flow_clip(B, D, S, seed):
+    """Seeded smooth clip in [-1, 1] -- same generator as tests/golden/make_golden.py flow_clip."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(B, 3, D, S + 16, S + 16, generator=g)
+    vid = torch.nn.functional.avg_pool3d(base, (1, 9, 9), stride=1, padding=(0, 4, 4))[:, :, :, 8:8 + S, 8:8 + S]
+    vid = (vid - vid.min()) / (vid.max() - vid.min())
+    return (vid * 0.8 + 0.2 * torch.rand(B, 3, D, 1, 1, generator=g)) * 2 - 1
+
+
+def flow_level_agreement(levels, want):
+    """(fraction of bytes equal, fraction within one grey level modulo 256) between two uint8 level tensors."""
+    d = (levels.int() - want.int()).abs()
+    d = torch.minimum(d, 256 - d)
+    return float((d == 0).float().mean()), float((d <= 1).float().mean())
