@@ -220,4 +220,14 @@ VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long 
  * (lib/evaluate.py:37-38); out = device double[3]: AUC, #positives, #negatives */
 VFD_API int vfd_roc_auc(const float* scores, const float* labels, int n, double* out, void* stream);
 
+/* ---- video_to_flow (lib/utils.py:94-129; called at models/mygannet.py:281-282,404-405) on the device -----
+ * video fp32 [B][3][D][H][W] in [-1, 1] -> out fp32 [B][3][D][H][W] in [-1, 1]: per-frame-index normalize over the
+ * batch, RGB2GRAY, cv2.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0) for every frame pair,
+ * cartToPolar / HSV (S = 255) / HSV2RGB on float32 / np.uint8 wrap / ClipToTensor / *2-1, last frame repeated.
+ * raw_flow (optional) receives the Farneback fields [B][D-1][H][W][2]. workspace: 256-byte aligned device scratch of
+ * at least vfd_video_to_flow_workspace(B, D, H, W) bytes. */
+VFD_API long long vfd_video_to_flow_workspace(int B, int D, int H, int W);
+VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, float* out, float* raw_flow,
+                              void* workspace, long long ws_bytes, void* stream);
+
 #endif /* VFD_B200_H */

@@ -132,18 +132,21 @@ def poly_exp(src, n=5, sigma=1.2):
         row2 = row2 + xxg[n + k] * p
 
     def at(r, dx):
-        return r[:, np.clip(xs + dx, 0, w - 1)].astype(np.float64)
+        return r[:, np.clip(xs + dx, 0, w - 1)]
 
-    b1, b3, b5 = row0.astype(np.float64) * g[n], row1.astype(np.float64) * g[n], row2.astype(np.float64) * g[n]
+    # C semantics of the reference loop: float (op) float is evaluated in float and only then widened to the
+    # double accumulators; only ``tg`` (a double holding a float sum) multiplies in double
+    d = np.float64
+    b1, b3, b5 = (row0 * g[n]).astype(d), (row1 * g[n]).astype(d), (row2 * g[n]).astype(d)
     b2 = b4 = b6 = 0.0
     for k in range(1, n + 1):
-        tg = at(row0, k) + at(row0, -k)
-        b1 = b1 + tg * g[n + k]
-        b4 = b4 + tg * xxg[n + k]
-        b2 = b2 + (at(row0, k) - at(row0, -k)) * xg[n + k]
-        b3 = b3 + (at(row1, k) + at(row1, -k)) * g[n + k]
-        b6 = b6 + (at(row1, k) - at(row1, -k)) * xg[n + k]
-        b5 = b5 + (at(row2, k) + at(row2, -k)) * g[n + k]
+        tg = (at(row0, k) + at(row0, -k)).astype(d)
+        b1 = b1 + tg * d(g[n + k])
+        b4 = b4 + tg * d(xxg[n + k])
+        b2 = b2 + ((at(row0, k) - at(row0, -k)) * xg[n + k]).astype(d)
+        b3 = b3 + ((at(row1, k) + at(row1, -k)) * g[n + k]).astype(d)
+        b6 = b6 + ((at(row1, k) - at(row1, -k)) * xg[n + k]).astype(d)
+        b5 = b5 + ((at(row2, k) + at(row2, -k)) * g[n + k]).astype(d)
     R = np.empty((h, w, 5), F32)
     R[..., 0], R[..., 1] = b3 * ig11, b2 * ig11
     R[..., 2], R[..., 3], R[..., 4] = b1 * ig03 + b5 * ig33, b1 * ig03 + b4 * ig33, b6 * ig55

@@ -1,0 +1,93 @@
+"""GPU (-m gpu): video_to_flow on the device against the fixture written by the reference's own
+lib/utils.video_to_flow (cv2 Farneback + HSV encoding) and against the numpy oracle.
+
+Tolerances: the Farneback field is fp32 arithmetic in the reference's order (rel <= 1e-5 to the oracle, 2e-6 to
+cv2's own fields when the oracle meets it); the encoded video is uint8 levels obtained by truncating floats of
+magnitude up to 65 025, so a last-bit difference moves a byte by one level now and then: >= 97 % of the bytes
+equal, >= 99.9 % within one level (modulo 256)."""
+import numpy as np
+import pytest
+import torch
+
+import vfd_gan_b200 as V
+from oracle import flow_oracle as FO
+from helpers import golden, flow_clip, flow_level_agreement
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _levels(t):
+    return torch.round((t.cpu() + 1) * 0.5 * 255).to(torch.uint8)
+
+
+@pytest.mark.parametrize("name", ["s64", "s112", "s128"])
+def test_video_to_flow_against_reference_fixture(name):
+    case = golden("flow_small.pt")[name]
+    B, D, S, seed = case["cfg"]
+    vid = flow_clip(B, D, S, seed)
+    out, raw = V.video_to_flow(vid.to(DEV), return_raw=True)
+    assert out.shape == vid.shape and raw.shape == (B, D - 1, S, S, 2)
+    # Farneback fields: cv2's own output for the first clip's first two pairs
+    want = case["cv2_flow_b0"]
+    for i in range(2):
+        got = raw[0, i].cpu()
+        assert float((got - want[i]).norm() / want[i].norm()) < 1e-5, (name, i)
+    # encoded video: byte levels against the reference function's output
+    exact, near = flow_level_agreement(_levels(out), case["levels"])
+    assert exact > 0.97 and near > 0.999, (name, exact, near)
+    assert torch.equal(out[:, :, -1], out[:, :, -2])                # last frame repeated (lib/utils.py:125)
+    # the levels are exact multiples of 1/255 mapped to [-1, 1]
+    lv = _levels(out).float()
+    assert float((lv / 255 * 2 - 1 - out.cpu()).abs().max()) < 1e-6
+
+
+def test_video_to_flow_against_oracle_ragged():
+    """Non-square frames, odd sizes (no exact 2x pyramid), several clips: oracle restatement on the same input."""
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(3, 3, 3, 90, 120, generator=g)
+    vid = torch.nn.functional.avg_pool3d(base, (1, 7, 7), stride=1, padding=(0, 3, 3))[:, :, :, 10:81, 10:107] * 2 - 1
+    assert vid.shape[-2:] == (71, 97)
+    out, raw = V.video_to_flow(vid.to(DEV), return_raw=True)
+    want, flows = FO.video_to_flow(vid.numpy())
+    flows = torch.from_numpy(flows)
+    assert float((raw.cpu() - flows).norm() / flows.norm()) < 1e-5
+    exact, near = flow_level_agreement(_levels(out), _levels(torch.from_numpy(want)))
+    assert exact > 0.97 and near > 0.999, (exact, near)
+
+
+def test_video_to_flow_properties_at_bench_size():
+    """BASELINE config 2 geometry (32 x 16 x 112 x 112): deterministic, finite, on the 1/255 grid, and each clip's
+    result does not depend on which other clips share the batch except through the per-frame min / max."""
+    torch.manual_seed(0)
+    vid = torch.rand(32, 3, 16, 112, 112, device=DEV) * 2 - 1
+    vid = torch.nn.functional.avg_pool3d(vid, (1, 5, 5), stride=1, padding=(0, 2, 2))
+    a = V.video_to_flow(vid)
+    b = V.video_to_flow(vid)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    lv = torch.round((a + 1) * 0.5 * 255)
+    assert float((lv / 255 * 2 - 1 - a).abs().max()) < 1e-6
+    # same global min / max per frame index when the extreme clips stay in the batch -> identical clip results
+    mn = vid.amin(dim=(1, 3, 4)).argmin(dim=0).unique().tolist() + vid.amax(dim=(1, 3, 4)).argmax(dim=0).unique().tolist()
+    keep = sorted(set(mn) | {0, 1})
+    sub = V.video_to_flow(vid[keep].contiguous())
+    assert torch.equal(sub, a[keep])
+
+
+def test_gan_step_with_device_flow_runs():
+    """The reference's forward_d order with both flows computed on the device (models/mygannet.py:279-286)."""
+    import types
+    B, D, S = 2, 16, 64
+    torch.manual_seed(3)
+    netg, netd = V.NetG(), V.NetD(types.SimpleNamespace(nfr=D, isize=S))
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    step = V.GanTrainStep(netg.to(DEV), netd.to(DEV), graph=False)
+    inp = flow_clip(B, D, S, 11).to(DEV)
+    gt = (flow_clip(B, D, S, 12)[:, :1] > 0.2).float().to(DEV)
+    gt_flow = V.video_to_flow(V.gray2rgb(gt))
+    with torch.no_grad():
+        predict = netg(inp)
+    pre_flow = V.video_to_flow(V.gray2rgb(predict))
+    step.step(inp, gt, gt_flow, pre_flow)
+    assert all(np.isfinite(v) for v in step.losses_dict().values())

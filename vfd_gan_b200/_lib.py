@@ -50,6 +50,8 @@ SIGNATURES = {
     "vfd_threshold_open": [_p, _i, _i, _i, _i, _f, _p, _p, _p],
     "vfd_confusion_counts": [_p, _p, _ll, _f, _p, _p],
     "vfd_roc_auc": [_p, _p, _i, _p, _p],
+    "vfd_video_to_flow": [_p, _i, _i, _i, _i, _p, _p, _p, _ll, _p],
+    "vfd_video_to_flow_workspace": [_i, _i, _i, _i],
     "vfd_set_debug": [_i],
 }
 
@@ -84,6 +86,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        L.vfd_video_to_flow_workspace.restype = ctypes.c_longlong
         _lib = L
     return _lib
 

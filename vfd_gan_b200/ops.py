@@ -295,6 +295,13 @@ def _confusion_counts(labels, scores, thr, counts):
               _stream())
 
 
+def _video_to_flow(video, out, raw, ws):
+    B, _, D, H, W = video.shape
+    _lib.call("vfd_video_to_flow", video.data_ptr(), B, D, H, W, out.data_ptr(), _ptr(raw), ws.data_ptr(), ws.numel(),
+              _stream())
+    _lib.KERNEL_LAUNCHES += 40          # ~45 small kernels per call (the counter above added one)
+
+
 def _roc_auc(scores, labels, out):
     _lib.call("vfd_roc_auc", scores.data_ptr(), labels.data_ptr(), scores.numel(), out.data_ptr(), _stream())
 
@@ -356,6 +363,8 @@ threshold_open_op = _define("threshold_open(Tensor predict, float thr, Tensor(a!
                             _threshold_open)
 confusion_counts_op = _define("confusion_counts(Tensor labels, Tensor scores, float thr, Tensor(a!) counts) -> ()",
                               _confusion_counts)
+video_to_flow_op = _define("video_to_flow(Tensor video, Tensor(a!) out, Tensor(b!)? raw, Tensor(c!) ws) -> ()",
+                           _video_to_flow)
 roc_auc_op = _define("roc_auc(Tensor scores, Tensor labels, Tensor(a!) out) -> ()", _roc_auc)
 
 
