@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-flow", action="store_true", help="skip the supplementary in-step optical-flow measurement")
     ap.add_argument("--dump-kernels", default="", help="write the per-call CUDA-event table of one step to this file")
     args = ap.parse_args()
 
@@ -388,6 +389,39 @@ def main():
                 v["tflops"] = v["work"] / (v["ms"] * 1e-3) / 1e12
             del v["work"]
 
+    # ---- supplementary: the step with both optical flows computed inside it, where the reference computes them
+    # (models/mygannet.py:281-282), on the device; plus cv2's Farneback on the host cores for scale (N = 1 only)
+    flow_extra = None
+    if world == 1 and not args.no_flow:
+        tflow = V.GanTrainStep(netg, netd)
+        for _ in range(4):
+            tflow.step(d_inp, d_gt)
+        ms_flow = timed(lambda: tflow.step(d_inp, d_gt), args.steps)
+        for _ in range(2):
+            V.video_to_flow(d_inp)
+        ms_v2f = timed(lambda: V.video_to_flow(d_inp), args.steps)
+        flow_extra = {"value": B * args.steps / (ms_flow * 1e-3), "unit": "clips/s", "ms_per_step": ms_flow / args.steps,
+                      "cuda_graph": bool(tflow._graph is not None),
+                      "video_to_flow_ms_per_call": ms_v2f / args.steps,
+                      "note": "gt_flow and pre_flow computed in-step by vfd_gan_b200.video_to_flow (2 calls per step)"}
+        try:
+            import cv2
+            import numpy as np
+            rng = np.random.default_rng(0)
+            a, b_ = (cv2.GaussianBlur(rng.random((ISIZE, ISIZE)).astype(np.float32), (0, 0), 2) for _ in range(2))
+            cv2.calcOpticalFlowFarneback(a, b_, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+            t0 = time.perf_counter()
+            npairs = 20
+            for _ in range(npairs):
+                cv2.calcOpticalFlowFarneback(a, b_, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+            per_pair = (time.perf_counter() - t0) / npairs
+            flow_extra["host_cv2_farneback_ms_per_step"] = per_pair * 1e3 * 2 * B * (NFR - 1)
+            flow_extra["host_cv2_sample"] = f"{npairs} calls of cv2.calcOpticalFlowFarneback on {ISIZE}x{ISIZE} float32 frames, " \
+                                            f"scaled to the 2 x {B} x {NFR - 1} pairs of one step (the reference's single-threaded loop)"
+        except Exception as e:   # cv2 missing on the box: report only the device side
+            flow_extra["host_cv2_farneback_ms_per_step"] = None
+            flow_extra["host_cv2_sample"] = f"unavailable: {e}"
+
     if rank != 0:
         finish(world)
         return
@@ -412,6 +446,7 @@ def main():
         "e2e": {"value": e2e, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "with_device_flow": flow_extra,
         "losses_last_step": {k: round(v, 6) for k, v in losses.items()},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -49,6 +49,25 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+// warp results -> one atomic pair per block
+__device__ __forceinline__ void block_minmax(float lo, float hi, float* dst) {
+  __shared__ float s_lo[32], s_hi[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) {
+    s_lo[wid] = lo;
+    s_hi[wid] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; ++i) {
+      lo = fminf(lo, s_lo[i]);
+      hi = fmaxf(hi, s_hi[i]);
+    }
+    atomic_min_f(dst, lo);
+    atomic_max_f(dst + 1, hi);
+  }
+}
+
 // mm[2k] = +inf, mm[2k+1] = -inf
 __global__ void fill_minmax_kernel(float* mm, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,10 +93,7 @@ frame_minmax_kernel(const float* __restrict__ video, int B, int D, int HW, float
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomic_min_f(mm + 2 * d, lo);
-    atomic_max_f(mm + 2 * d + 1, hi);
-  }
+  block_minmax(lo, hi, mm + 2 * d);
 }
 
 // grey[b][d][p] = cv2.cvtColor(RGB2GRAY) of (x - min_d) / (max_d - min_d + 1e-5)
@@ -262,43 +278,59 @@ update_matrices_kernel(const float* __restrict__ R, const float* __restrict__ fl
   }
 }
 
-// FarnebackUpdateFlow_Blur: 15 x 15 box sums with replicated borders (double), vertical part
-__global__ void __launch_bounds__(256)
-box_v_kernel(const float* __restrict__ M, int pairs, int h, int w, double* __restrict__ V) {
-  const long long total = (long long)pairs * h * w * 5;
+// FarnebackUpdateFlow_Blur: 15 x 15 box sums of the five matrix channels with replicated borders, accumulated in
+// double like the reference, and the 2 x 2 solve with the 1e-3 regulariser. One block = one 16 x 16 tile of one
+// field: the (16+14)^2 x 5 halo is staged in shared memory (clamped loads are the replicated border), column sums
+// go to a second shared array in double, row sums and the solve finish per pixel.
+constexpr int kBoxT = 16;
+constexpr int kBoxS = kBoxT + kWin - 1;   // 30
+__global__ void __launch_bounds__(kBoxT * kBoxT)
+box_blur_solve_kernel(const float* __restrict__ M, int h, int w, int tiles_x, int tiles_y, float* __restrict__ flow) {
+  __shared__ float s_in[kBoxS * kBoxS * 5];
+  __shared__ double s_v[kBoxT * kBoxS * 5];
+  const int tiles = tiles_x * tiles_y;
+  const long long pair = blockIdx.x / tiles;
+  const int t = blockIdx.x - (int)(pair * tiles);
+  const int y0 = (t / tiles_x) * kBoxT, x0 = (t % tiles_x) * kBoxT;
+  const float* img = M + pair * (long long)h * w * 5;
+  const int tid = threadIdx.x;
   constexpr int m = kWin / 2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / 5;
-    const int c = (int)(i - px * 5);
-    const int x = (int)(px % w), y = (int)((px / w) % h);
-    const float* img = M + (px / ((long long)w * h)) * (long long)h * w * 5;
-    double s = 0.0;
-#pragma unroll
-    for (int k = -m; k <= m; ++k) s += (double)img[((long long)min(max(y + k, 0), h - 1) * w + x) * 5 + c];
-    V[i] = s;
+  for (int i = tid; i < kBoxS * kBoxS * 5; i += kBoxT * kBoxT) {
+    const int c = i % 5, col = (i / 5) % kBoxS, row = i / (5 * kBoxS);
+    const int gy = min(max(y0 + row - m, 0), h - 1), gx = min(max(x0 + col - m, 0), w - 1);
+    s_in[i] = img[((long long)gy * w + gx) * 5 + c];
   }
-}
-// horizontal part + the 2 x 2 solve with the 1e-3 regulariser
-__global__ void __launch_bounds__(256)
-box_h_solve_kernel(const double* __restrict__ V, int pairs, int h, int w, float* __restrict__ flow) {
-  const long long total = (long long)pairs * h * w;
-  constexpr int m = kWin / 2;
-  const double scale = 1.0 / (double)(kWin * kWin);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % w);
-    const double* row = V + (i - x) * 5;
-    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  __syncthreads();
+  // column sums: one thread per (column, channel) slides the 15-row window down the tile (running sums in
+  // double, like the reference's vsum)
+  for (int cc = tid; cc < kBoxS * 5; cc += kBoxT * kBoxT) {
+    double sum = 0.0;
 #pragma unroll
-    for (int k = -m; k <= m; ++k) {
-      const double* p = row + (long long)min(max(x + k, 0), w - 1) * 5;
+    for (int k = 0; k < kWin; ++k) sum += (double)s_in[k * kBoxS * 5 + cc];
+    s_v[cc] = sum;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) s[c] += p[c];
+    for (int r = 1; r < kBoxT; ++r) {
+      sum += (double)s_in[(r + kWin - 1) * kBoxS * 5 + cc] - (double)s_in[(r - 1) * kBoxS * 5 + cc];
+      s_v[r * kBoxS * 5 + cc] = sum;
     }
-    const double g11 = s[0] * scale, g12 = s[1] * scale, g22 = s[2] * scale, h1 = s[3] * scale, h2 = s[4] * scale;
-    const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-    flow[i * 2] = (float)((g11 * h2 - g12 * h1) * idet);
-    flow[i * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
   }
+  __syncthreads();
+  const int py = tid / kBoxT, px = tid % kBoxT;
+  const int y = y0 + py, x = x0 + px;
+  if (y >= h || x >= w) return;
+  double sacc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < kWin; ++k) {
+    const double* p = s_v + (py * kBoxS + px + k) * 5;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) sacc[c] += p[c];
+  }
+  const double scale = 1.0 / (double)(kWin * kWin);
+  const double g11 = sacc[0] * scale, g12 = sacc[1] * scale, g22 = sacc[2] * scale, h1 = sacc[3] * scale, h2 = sacc[4] * scale;
+  const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+  float* o = flow + ((pair * h + y) * (long long)w + x) * 2;
+  o[0] = (float)((g11 * h2 - g12 * h1) * idet);
+  o[1] = (float)((g22 * h1 - g12 * h2) * idet);
 }
 
 // resize(prevFlow, (w, h), INTER_LINEAR) * (1 / pyr_scale)
@@ -359,10 +391,7 @@ mag_minmax_kernel(const float* __restrict__ flow, int hw, float* __restrict__ mm
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomic_min_f(mm + 2 * blockIdx.y, lo);
-    atomic_max_f(mm + 2 * blockIdx.y + 1, hi);
-  }
+  block_minmax(lo, hi, mm + 2 * blockIdx.y);
 }
 
 // HSV (H = ang / 2, S = 255, V = minmax-normalised magnitude) -> cv::cvtColor(HSV2RGB) on float -> np.uint8 wrap ->
@@ -524,7 +553,7 @@ using namespace vfd;
 
 // Workspace layout (bytes, each region 256-byte aligned):
 //   frame min/max [2*D] f32 | pair min/max [2*pairs] f32 | grey [B*D*H*W] f32 | level image [frames*H*W] f32 |
-//   rows [frames*H*W*3] f32 | R per level [frames*h*w*5] f32 | M [pairs*H*W*5] f32 | V [pairs*H*W*5] f64 |
+//   rows [frames*H*W*3] f32 | R per level [frames*h*w*5] f32 | M [pairs*H*W*5] f32 |
 //   flow A, flow B [pairs*H*W*2] f32
 VFD_API long long vfd_video_to_flow_workspace(int B, int D, int H, int W) {
   if (B <= 0 || D < 2 || H <= 0 || W <= 0) return 0;
@@ -534,7 +563,7 @@ VFD_API long long vfd_video_to_flow_workspace(int B, int D, int H, int W) {
   long long total = align256(2LL * D * 4) + align256(2 * pairs * 4) + align256(frames * hw * 4) * 2 +
                     align256(frames * hw * 3 * 4);
   for (int k = 0; k <= levels; ++k) total += align256(frames * lv[k].h * lv[k].w * 5 * 4);
-  total += align256(pairs * hw * 5 * 4) + align256(pairs * hw * 5 * 8) + 2 * align256(pairs * hw * 2 * 4);
+  total += align256(pairs * hw * 5 * 4) + 2 * align256(pairs * hw * 2 * 4);
   return total;
 }
 
@@ -560,7 +589,6 @@ VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, fl
   float* R[kMaxLevels + 1];
   for (int k = 0; k <= levels; ++k) R[k] = reinterpret_cast<float*>(take(frames * lv[k].h * lv[k].w * 5 * 4));
   float* M = reinterpret_cast<float*>(take(pairs * hw * 5 * 4));
-  double* V = reinterpret_cast<double*>(take(pairs * hw * 5 * 8));
   float* flowA = reinterpret_cast<float*>(take(pairs * hw * 2 * 4));
   float* flowB = reinterpret_cast<float*>(take(pairs * hw * 2 * 4));
 
@@ -592,6 +620,7 @@ VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, fl
   for (int k = levels; k >= 0; --k) {
     const int h = lv[k].h, w = lv[k].w;
     const long long n = pairs * h * w;
+    const int tiles_x = (w + kBoxT - 1) / kBoxT, tiles_y = (h + kBoxT - 1) / kBoxT;
     const float* init = nullptr;
     if (k < levels) {
       flow_upsample_kernel<<<grid_for(n), 256, 0, stream>>>(cur, (int)pairs, lv[k + 1].h, lv[k + 1].w, h, w, 2.0f, other);
@@ -600,8 +629,7 @@ VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, fl
     }
     update_matrices_kernel<<<grid_for(n), 256, 0, stream>>>(R[k], init, (int)pairs, D, h, w, M);
     for (int it = 0; it < kIters; ++it) {
-      box_v_kernel<<<grid_for(n * 5), 256, 0, stream>>>(M, (int)pairs, h, w, V);
-      box_h_solve_kernel<<<grid_for(n), 256, 0, stream>>>(V, (int)pairs, h, w, cur);
+      box_blur_solve_kernel<<<(unsigned)(pairs * tiles_x * tiles_y), kBoxT * kBoxT, 0, stream>>>(M, h, w, tiles_x, tiles_y, cur);
       if (it < kIters - 1) update_matrices_kernel<<<grid_for(n), 256, 0, stream>>>(R[k], cur, (int)pairs, D, h, w, M);
     }
   }

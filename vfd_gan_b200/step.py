@@ -37,6 +37,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import _lib, ops, spatiotempconv
+from .flow import video_to_flow
 
 LOSS_KEYS = ("g/err_g", "g/err_g_adv", "g/err_g_adv_s", "g/err_g_adv_t", "g/err_g_con",
              "d/err_d_real_s", "d/err_d_real_t", "d/err_d_fake_s", "d/err_d_fake_t",
@@ -157,9 +158,13 @@ class GanTrainStep:
 
     GRAPH_WARMUP_STEPS = 2
 
-    def step(self, inp, gt, gt_flow, pre_flow, dropout_seeds=None):
+    def step(self, inp, gt, gt_flow=None, pre_flow=None, dropout_seeds=None):
         """inp (B,3,D,H,W) in [-1,1]; gt (B,1,D,H,W) in {0,1}; flows (B,3,D,H,W). Returns the device
-        tensor of the 12 logged scalars in LOSS_KEYS order (no host synchronisation)."""
+        tensor of the 12 logged scalars in LOSS_KEYS order (no host synchronisation).
+
+        A flow left as ``None`` is computed inside the step exactly where the reference computes it
+        (``video_to_flow(gray2rgb(gt))`` / ``video_to_flow(gray2rgb(predict.detach()))``,
+        models/mygannet.py:279-282) -- on the device (vfd_gan_b200.flow) instead of on the host."""
         args = (inp, gt, gt_flow, pre_flow)
         if not self.use_graph or dropout_seeds is not None:
             return self._step_impl(*args, dropout_seeds=dropout_seeds)
@@ -168,10 +173,11 @@ class GanTrainStep:
                 self._eager_steps += 1
                 return self._step_impl(*args, seed_dev=self._step_counter)
             self._capture(args)
-        elif any(s.shape != t.shape for s, t in zip(self._static_in, args)):
+        elif any((s is None) != (t is None) or (s is not None and s.shape != t.shape)
+                 for s, t in zip(self._static_in, args)):
             return self._step_impl(*args, seed_dev=self._step_counter)   # other batch geometry: stay eager
         for s, t in zip(self._static_in, args):
-            if s.data_ptr() != t.data_ptr():
+            if s is not None and s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
         self._graph.replay()
         _lib.LAUNCHES += self.graph_calls
@@ -182,7 +188,8 @@ class GanTrainStep:
     def _capture(self, args):
         """Record one step into a CUDA graph. The caller's tensors become the graph's static inputs (later
         calls with other tensors are copied into them)."""
-        self._static_in = [t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+        self._static_in = [None if t is None else
+                           (t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float())
                            for t in args]
         self.netg.train()
         self.netd.train()
@@ -223,6 +230,12 @@ class GanTrainStep:
         logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds, seed_dev=seed_dev)
         predict = ops.SigmoidHeadFn.apply(logits)
         self.predict = predict.detach()
+
+        # optical flow of the mask and of the prediction, when not supplied (models/mygannet.py:281-282)
+        if gt_flow is None:
+            gt_flow = video_to_flow(gt.expand(-1, 3, -1, -1, -1))
+        if pre_flow is None:
+            pre_flow = video_to_flow(self.predict.expand(-1, 3, -1, -1, -1))
 
         # forward_d: gray2rgb folded into the layout pack (1 -> 3 replicated channels)
         gt_cl = ops.PackFn.apply(gt, 3)
