@@ -299,7 +299,16 @@ def _video_to_flow(video, out, raw, ws):
     B, _, D, H, W = video.shape
     _lib.call("vfd_video_to_flow", video.data_ptr(), B, D, H, W, out.data_ptr(), _ptr(raw), ws.data_ptr(), ws.numel(),
               _stream())
-    _lib.KERNEL_LAUNCHES += 40          # ~45 small kernels per call (the counter above added one)
+    # kernels launched by the call (the counter above added one): 2 fills, frame min/max, grey, 3 per pyramid
+    # level for the polynomial expansion, per level 1 + 3 + 2 flow kernels (+ 1 upsample below the coarsest),
+    # field min/max, encode
+    levels, scale = 0, 1.0
+    while levels < 3:
+        scale *= 0.5
+        if W * scale < 32 or H * scale < 32:
+            break
+        levels += 1
+    _lib.KERNEL_LAUNCHES += 2 + 1 + 1 + 3 * (levels + 1) + 6 * (levels + 1) + levels + 2 - 1
 
 
 def _roc_auc(scores, labels, out):
