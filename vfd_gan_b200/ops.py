@@ -479,7 +479,8 @@ class WeightPacker:
             if pw is None:
                 pw = PackedWeights()
                 w._vfd_packed = pw
-            pw._allocate(w)
+            if pw.shape_key != (tuple(w.shape), w.device):   # keep buffers another packer / a captured graph points at
+                pw._allocate(w)
             cout, cin = w.shape[0], w.shape[1]
             taps = w[0, 0].numel()
             for dst, mode in ((pw.fwd, 0), (pw.dgrad, 1)):
