@@ -122,3 +122,5 @@ def test_new_modules_fail_loudly_on_cpu():
         V.EncDecEncG(3, 8)(torch.rand(1, 3, 16, 16, 16))
     with pytest.raises(RuntimeError):
         V.AutoEncoder()(torch.rand(1, 3, 16, 16, 16))
+    with pytest.raises(RuntimeError):
+        V.video_to_flow(torch.rand(1, 3, 4, 32, 32))
