@@ -130,7 +130,9 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
                            void* stream);
 /* Backward of the above through BatchNorm: given the gradients of out_full / out_pool (either may
  * be NULL) computes dy (bf16), dgamma and dbeta (fp32 [Cvalid]). sums: zeroed double [2*C] scratch,
- * c1 / c2: fp32 [C] scratch. */
+ * c1 / c2: fp32 [C] scratch. train: bit 0 = training-mode BatchNorm (batch statistics); bit 1 = g_pool is
+ * [N][D/pd][C] and broadcast over the H and W axes (the gradient of the global spatial mean of TDisc,
+ * models/mygannet.py:175,189-191), only for windows (1,1,1) and (2,1,1). */
 VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, int W, int C, int Cvalid,
                            const float* mean, const float* invstd, const float* scale,
                            const float* shift, float slope, const void* g_full, long long gf_ld,

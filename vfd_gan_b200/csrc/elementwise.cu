@@ -286,6 +286,7 @@ struct ActGeom {
   int QD, QH, QW;     // pooled extent (floor)
   unsigned nwin;
   FastDiv fWW, fWH, fWD;
+  int pool_bcast;     // backward only: g_pool is [N][QD][C], broadcast over the H and W axes
 };
 
 // The BN/activation kernels map one thread to (pool window, 8-channel group). A block owns a
@@ -328,7 +329,7 @@ struct Window {
   bool pool_ok;
   unsigned pvox;
   __device__ __forceinline__ void locate(unsigned win, bool wv, const ActGeom& g) {
-    if (NV == 1) {
+    if (NV == 1 && !g.pool_bcast) {
       vox[0] = win;
       ok[0] = wv;
       pool_ok = wv;
@@ -338,7 +339,7 @@ struct Window {
     int n, wd, wh, ww;
     decode_win(wv ? win : 0u, g, n, wd, wh, ww);
     pool_ok = wv && wd < g.QD && wh < g.QH && ww < g.QW;
-    pvox = ((n * g.QD + wd) * g.QH + wh) * g.QW + ww;
+    pvox = g.pool_bcast ? (n * g.QD + wd) : (((n * g.QD + wd) * g.QH + wh) * g.QW + ww);
     const unsigned base = ((n * g.D + wd * PD) * g.H + wh * PH) * g.W + ww * PW;
 #pragma unroll
     for (int a = 0; a < PD; ++a)
@@ -1396,6 +1397,7 @@ static int fill_act_geom(ActGeom& g, int N, int D, int H, int W, int C, int pd, 
   g.QD = D / pd; g.QH = H / ph; g.QW = W / pw;
   g.nwin = (unsigned)((long long)N * g.WD * g.WH * g.WW);
   g.fWW = make_fastdiv(g.WW); g.fWH = make_fastdiv(g.WH); g.fWD = make_fastdiv(g.WD);
+  g.pool_bcast = 0;
   return 0;
 }
 
@@ -1474,10 +1476,15 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   if (V == 0) return 0;
   const bool drop = drop_p > 0.f;
   if (drop && (pd != 1 || ph != 1)) return set_error(VFD_ERR_ARG, "dropout is only fused into un-pooled BN+activation");
+  const int pool_bcast = (train >> 1) & 1;   // bit 1: g_pool is [N][D/pd][C], broadcast over H and W
+  train &= 1;
+  if (pool_bcast && (ph != 1 || g_pool == nullptr))
+    return set_error(VFD_ERR_ARG, "bn_act_bwd: a broadcast pooled gradient needs a (1,1,1) or (2,1,1) window");
   if (ph == 1) {
     // un-pooled / depth-pooled: 8-channel window-per-thread kernels
     ActGeom g;
     if (int e = fill_act_geom(g, N, D, H, W, C, pd, ph, pw)) return e;
+    g.pool_bcast = pool_bcast;
     const int nvi = 4 / (pd * ph * pw) > 0 ? 4 / (pd * ph * pw) : 1;
     const int grid = win_grid(g, pd, ph, pw, nvi, 2);
 #define VFD_BWD8_LAUNCH(KERNEL, SMEM, ...)                                                             \

@@ -186,12 +186,12 @@ def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, 
 
 
 def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd, ph, pw, drop_p, seed, train,
-                sums, c1, c2, dgamma, dbeta, dy, seed_dev=None):
+                sums, c1, c2, dgamma, dbeta, dy, seed_dev=None, pool_bcast=False):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_bwd input")
     _lib.call("vfd_bn_act_bwd", y.data_ptr(), ld, N, D, H, W, C, cvalid, mean.data_ptr(), invstd.data_ptr(),
               scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
               _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev),
-              1 if train else 0, sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
+              (1 if train else 0) | (2 if pool_bcast else 0), sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
               dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
 
 
@@ -340,7 +340,7 @@ bn_act_bwd = _define(
     "bn_act_bwd(Tensor y, int cvalid, Tensor mean, Tensor invstd, Tensor scale, Tensor shift, float slope, "
     "Tensor? g_full, Tensor? g_pool, int pd, int ph, int pw, float drop_p, int seed, bool train, "
     "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy, "
-    "Tensor? seed_dev=None) -> ()", _bn_act_bwd)
+    "Tensor? seed_dev=None, bool pool_bcast=False) -> ()", _bn_act_bwd)
 tap_gather = _define("tap_gather(Tensor src, int cs, Tensor(a!) dst, int kd, int kh, int kw, int sign) -> ()",
                      _tap_gather)
 channel_sum = _define("channel_sum(Tensor x, Tensor(a!) out) -> ()", _channel_sum)
@@ -503,6 +503,68 @@ class WeightPacker:
             pw.key = pw.current_key(w)
 
 
+class StepArena:
+    """Zero-initialised fp32 scratch for the weight-gradient accumulators of one train step: one fill per step
+    instead of one per conv. Sized by the first step that uses it (which still gets ordinary ``torch.zeros``);
+    buffers are never freed while the process lives because a captured CUDA graph keeps their addresses."""
+
+    def __init__(self):
+        self.buf, self.off, self.want, self.active, self.retired = None, 0, 0, False, []
+
+    def begin(self, device):
+        if self.buf is not None and (self.buf.device != device or self.buf.numel() < self.want):
+            self.retired.append(self.buf)
+            self.buf = None
+        if self.buf is None and self.want:
+            self.buf = torch.empty(self.want + self.want // 8, dtype=torch.float32, device=device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off, self.want, self.active = 0, 0, True
+
+    def end(self):
+        self.active = False
+
+    def take(self, shape, device):
+        if not self.active:
+            return None
+        n = 1
+        for d in shape:
+            n *= d
+        n = round_up(n, 64)
+        self.want += n
+        if self.buf is None or self.buf.device != device or self.off + n > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + n]
+        self.off += n
+        numel = 1
+        for d in shape:
+            numel *= d
+        return t[:numel].view(*shape)
+
+
+ARENA = StepArena()
+_const_zeros = {}
+
+
+def acc_zeros(shape, device):
+    """fp32 zeros for a wgrad accumulator (arena slice inside a GanTrainStep, a fresh tensor otherwise)."""
+    t = ARENA.take(shape, device)
+    return t if t is not None else torch.zeros(*shape, dtype=torch.float32, device=device)
+
+
+def zero_grad(n, device):
+    """Gradient of a parameter whose gradient is identically zero (a conv bias folded into a training-mode
+    BatchNorm). Inside a GanTrainStep it is a view of one shared, never-written zero buffer (no fill kernel);
+    elsewhere a fresh tensor, because user code may update ``.grad`` in place."""
+    if not ARENA.active:
+        return torch.zeros(n, dtype=torch.float32, device=device)
+    z = _const_zeros.get(device)
+    if z is None or z.numel() < n:
+        z = torch.zeros(max(n, 4096), dtype=torch.float32, device=device)
+        _const_zeros[device] = z
+    return z[:n]
+
+
 def cl_empty(N, D, H, W, C, device, dtype=torch.bfloat16):
     return torch.empty(N, D, H, W, C, dtype=dtype, device=device)
 
@@ -625,10 +687,10 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
                 _wgrad_1x1(folded, taps * cout, x, cin, acc)
 
     if mode == "x":
-        acc = torch.zeros(1, cols, round_up(cout, 32), dtype=torch.float32, device=g.device)
+        acc = acc_zeros((1, cols, round_up(cout, 32)), g.device)
         _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
         return acc[0, :taps * cin, :cout].reshape(taps, cin, cout).permute(2, 1, 0).contiguous()
-    acc = torch.zeros(1, round_up(cin, 8), round_up(taps * cout, 32), dtype=torch.float32, device=g.device)
+    acc = acc_zeros((1, round_up(cin, 8), round_up(taps * cout, 32)), g.device)
     _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
     return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1).contiguous()
 
@@ -685,18 +747,18 @@ class ConvFn(torch.autograd.Function):
             if fold is None:
                 layout = 0 if CONV_IMPL_DIRECT else wgrad_layout(cout, cin, kd, kh, kw, H, W)
                 if taps == 1 and cout <= 32 and cin <= 32 and THIN_WGRAD and not CONV_IMPL_DIRECT:
-                    acc = torch.zeros(1, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+                    acc = acc_zeros((1, round_up(cin, 8), round_up(cout, 32)), g.device)
                     _timed("conv_wgrad", flops, lambda: conv3d_wgrad_thin(g, cout, x, cin, acc),
                            2.0 * (g.numel() + x.numel()))
                     gw = torch.empty_like(weight, dtype=torch.float32)
                     unpack_wgrad(acc, gw)
                 elif layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
-                    acc = torch.zeros(taps, round_up(cout, 8), round_up(cin, 32), dtype=torch.float32, device=g.device)
+                    acc = acc_zeros((taps, round_up(cout, 8), round_up(cin, 32)), g.device)
                     _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1),
                            2.0 * (g.numel() + x.numel()))
                     gw = acc[:, :cout, :cin].permute(1, 2, 0).contiguous().reshape(weight.shape)
                 else:
-                    acc = torch.zeros(taps, round_up(cin, 8), round_up(cout, 32), dtype=torch.float32, device=g.device)
+                    acc = acc_zeros((taps, round_up(cin, 8), round_up(cout, 32)), g.device)
                     _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT),
                            2.0 * (g.numel() + x.numel()))
                     gw = torch.empty_like(weight, dtype=torch.float32)
@@ -705,7 +767,7 @@ class ConvFn(torch.autograd.Function):
                 gw = _folded_wgrad(fold, g, x, cin, cout, kd, kh, kw, flops).reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             if ctx.bias_zero:
-                gb = torch.zeros(cout, dtype=torch.float32, device=g.device)
+                gb = zero_grad(cout, g.device)
             else:
                 s = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
                 channel_sum(g, s)
@@ -752,6 +814,14 @@ class BnActFn(torch.autograd.Function):
         cvalid, slope, (pd, ph, pw), drop_p, seed, train = ctx.cfg
         N, D, H, W, C, _ = _check_cl(y, "bn saved input")
         dev = y.device
+        # the gradient of a global spatial mean (TDisc head) arrives as a stride-0 expansion over H and W: hand the
+        # kernel the [N, D/pd, C] base instead of materialising the broadcast
+        bcast = False
+        if (g_pool is not None and ph == 1 and pw == 1 and g_pool.dim() == 5 and g_pool.dtype == torch.bfloat16
+                and g_pool.shape[2] * g_pool.shape[3] > 1 and g_pool.stride(2) == 0 and g_pool.stride(3) == 0):
+            base = g_pool[:, :, 0, 0, :]
+            if base.is_contiguous() and base.data_ptr() % 16 == 0:
+                g_pool, bcast = base.unsqueeze(2).unsqueeze(3), True
         g_full, g_pool = as_cl_grad(g_full), as_cl_grad(g_pool)
         dy = cl_empty(N, D, H, W, C, dev)
         tmp = torch.empty(2, C, dtype=torch.float32, device=dev)
@@ -761,9 +831,9 @@ class BnActFn(torch.autograd.Function):
         _timed("bn_act_bwd", nbytes,
                lambda: bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw,
                                   drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy,
-                                  ctx.seed_dev))
+                                  ctx.seed_dev, bcast))
         # a conv bias folded into training-mode BN has an identically zero gradient
-        gpb = torch.zeros(cvalid, dtype=torch.float32, device=dev) if ctx.has_pre_bias else None
+        gpb = zero_grad(cvalid, dev) if ctx.has_pre_bias else None
         return (dy, dgamma, dbeta, gpb) + (None,) * 14
 
 
@@ -850,6 +920,8 @@ class MeanDimsFn(torch.autograd.Function):
         gb[..., :c] = g / count
         for d in sorted(dims):
             gb = gb.unsqueeze(d)
+        if dims == (2, 3):      # BnActFn.backward reads the stride-0 expansion directly (no broadcast copy)
+            return gb.expand(shape), None, None
         return gb.expand(shape).contiguous(), None, None
 
 

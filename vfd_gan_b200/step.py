@@ -211,9 +211,11 @@ class GanTrainStep:
         if self.packer is not None:
             self.packer.pack_all()          # every conv weight's bf16 GEMM operands, one launch
         spatiotempconv.DEFER_BN_COUNTERS = counters = []
+        ops.ARENA.begin(inp.device)       # one zero fill for all weight-gradient accumulators of the step
         try:
             return self._step_body(inp, gt, gt_flow, pre_flow, dropout_seeds, seed_dev)
         finally:
+            ops.ARENA.end()
             spatiotempconv.DEFER_BN_COUNTERS = None
             if counters:   # num_batches_tracked of every BatchNorm call of the step (NetD runs twice)
                 seen = {}
