@@ -123,3 +123,25 @@ def test_oracle_is_bit_exact_against_reference_modules(reference_modules):
     p, t = torch.rand(2, 1, 4, 8, 8), (torch.rand(2, 1, 4, 8, 8) > 0.5).float()
     assert torch.equal(r.utils.weighted_bce(p, t), O.weighted_bce(p, t))
     assert torch.equal(r.utils.l2_loss(p, t), O.l2_loss(p, t))
+
+
+def test_compat_install_rebinds_the_reference_names(reference_modules):
+    """vfd_gan_b200.compat.install() is the 'two import lines' of INTEGRATION.md done programmatically: the
+    reference's own modules then build the B200 nets, and uninstall() restores them."""
+    import vfd_gan_b200 as V
+    from vfd_gan_b200 import compat
+    mg, lu = reference_modules.mygannet, reference_modules.utils
+    ref_netg, ref_flow = mg.NetG, lu.video_to_flow
+    compat.install()
+    try:
+        assert mg.NetG is V.NetG and mg.NetD is V.NetD and mg.SpatioTemporalConv is V.SpatioTemporalConv
+        assert reference_modules.spatiotempconv.SpatioTemporalConv is V.SpatioTemporalConv
+        assert reference_modules.convlstm.ConvLSTMCell is V.ConvLSTMCell
+        assert mg.video_to_flow is V.video_to_flow and lu.morphology_proc is V.evaluate.morphology_proc
+        assert mg.weighted_bce is V.weighted_bce
+        net = mg.NetG()                               # what MyGAN.__init__ does (models/mygannet.py:232)
+        assert isinstance(net, V.NetG)
+        net.apply(lu.weights_init)                    # the reference's own initialiser works on our modules
+    finally:
+        compat.uninstall()
+    assert mg.NetG is ref_netg and lu.video_to_flow is ref_flow
