@@ -295,3 +295,17 @@ def test_roc_auc_kernel_against_sklearn_fixture():
         assert abs(float(got[0]) - O.evaluate(lab.numpy(), sc.numpy(), "roc")) < 1e-12, n
     with pytest.raises(RuntimeError):
         V.evaluate.roc_auc(torch.zeros(20000, device=DEV), torch.zeros(20000, device=DEV))
+
+
+def test_empty_batches_are_no_ops():
+    """Zero clips: every new entry point returns without launching (like the conv path, test_parity_gpu)."""
+    e5 = torch.empty(0, 1, 16, 24, 24, device=DEV)
+    t, m = V.evaluate.threshold_open(e5)
+    assert t.shape == e5.shape and m.shape == e5.shape
+    counts = V.evaluate.confusion_counts(torch.empty(0, device=DEV), torch.empty(0, device=DEV), 0.2)
+    assert counts.tolist() == [0, 0, 0, 0]
+    lat = torch.empty(0, 1, 2, 2, 128, dtype=torch.bfloat16, device=DEV)
+    assert V.anomaly_scores(lat, lat, 128).shape == (0,)
+    assert V.video_to_flow(torch.empty(0, 3, 16, 32, 32, device=DEV)).shape == (0, 3, 16, 32, 32)
+    out = V.evaluate.roc_auc(torch.empty(0, device=DEV), torch.empty(0, device=DEV))
+    assert out[0].isnan() and out[1] == 0 and out[2] == 0

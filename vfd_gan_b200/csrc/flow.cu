@@ -570,9 +570,9 @@ VFD_API long long vfd_video_to_flow_workspace(int B, int D, int H, int W) {
 VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, float* out, float* raw_flow,
                               void* workspace, long long ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (video == nullptr || out == nullptr || workspace == nullptr) return set_error(VFD_ERR_ARG, "video_to_flow: null pointer");
   if (B < 0 || D < 2 || H < 12 || W < 12) return set_error(VFD_ERR_ARG, "video_to_flow: needs D >= 2 and frames of at least 12 x 12");
-  if (B == 0) return VFD_OK;
+  if (B == 0) return VFD_OK;   // empty batch: nothing to do
+  if (video == nullptr || out == nullptr || workspace == nullptr) return set_error(VFD_ERR_ARG, "video_to_flow: null pointer");
   if (ws_bytes < vfd_video_to_flow_workspace(B, D, H, W)) return set_error(VFD_ERR_ARG, "video_to_flow: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(VFD_ERR_ARG, "video_to_flow: workspace must be 256-byte aligned");
   const long long frames = (long long)B * D, pairs = (long long)B * (D - 1), hw = (long long)H * W;

@@ -452,9 +452,10 @@ static inline int bad_cl(const void* p, long long ld, int C) {
 
 VFD_API int vfd_latent_score(const void* a, long long a_ld, const void* b, long long b_ld, int C,
                              long long rows_per_clip, int N, double* per_clip, void* stream_) {
+  if (rows_per_clip < 0 || N < 0) return set_error(VFD_ERR_ARG, "latent_score: bad arguments");
+  if (N == 0 || rows_per_clip == 0) return VFD_OK;   // empty batch: nothing to do
   if (bad_cl(a, a_ld, C) || bad_cl(b, b_ld, C)) return set_error(VFD_ERR_ARG, "latent_score: bad latent tensor");
-  if (per_clip == nullptr || rows_per_clip < 0 || N < 0) return set_error(VFD_ERR_ARG, "latent_score: bad arguments");
-  if (N == 0 || rows_per_clip == 0) return VFD_OK;
+  if (per_clip == nullptr) return set_error(VFD_ERR_ARG, "latent_score: bad arguments");
   if (N > 65535) return set_error(VFD_ERR_ARG, "latent_score: at most 65535 clips per call");
   // whole waves: about 148 * 8 blocks in total
   int per = blocks_for(rows_per_clip * (C / 8), 256, (148 * 8 + N - 1) / N);
@@ -466,6 +467,7 @@ VFD_API int vfd_latent_score(const void* a, long long a_ld, const void* b, long 
 VFD_API int vfd_sqdiff_bwd(const void* a, long long a_ld, const void* b, long long b_ld, int C, long long V,
                            const float* gscale, float scale, void* ga, long long ga_ld, void* gb, long long gb_ld,
                            void* stream_) {
+  if (V <= 0) return VFD_OK;
   if (bad_cl(a, a_ld, C) || bad_cl(b, b_ld, C)) return set_error(VFD_ERR_ARG, "sqdiff_bwd: bad input tensor");
   if ((ga != nullptr && bad_cl(ga, ga_ld, C)) || (gb != nullptr && bad_cl(gb, gb_ld, C)))
     return set_error(VFD_ERR_ARG, "sqdiff_bwd: bad gradient tensor");
@@ -477,6 +479,7 @@ VFD_API int vfd_sqdiff_bwd(const void* a, long long a_ld, const void* b, long lo
 
 VFD_API int vfd_l1_loss(const float* a, const float* b, long long V, float grad_scale, double* sum, float* ga,
                         void* stream_) {
+  if (V <= 0) return VFD_OK;
   if (a == nullptr || b == nullptr || sum == nullptr) return set_error(VFD_ERR_ARG, "l1_loss: null pointer");
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ga)) % 16)
     return set_error(VFD_ERR_ARG, "l1_loss: tensors must be 16-byte aligned");
@@ -487,6 +490,7 @@ VFD_API int vfd_l1_loss(const float* a, const float* b, long long V, float grad_
 
 VFD_API int vfd_bce_loss(const float* p, const float* t, long long V, float grad_scale, double* sum, float* gp,
                          void* stream_) {
+  if (V <= 0) return VFD_OK;
   if (p == nullptr || t == nullptr || sum == nullptr) return set_error(VFD_ERR_ARG, "bce_loss: null pointer");
   if (V <= 0) return VFD_OK;
   bce_kernel<<<blocks_for(V, 256, 148 * 4), 256, 0, STREAM>>>(p, t, V, grad_scale, sum, gp);
@@ -495,22 +499,23 @@ VFD_API int vfd_bce_loss(const float* p, const float* t, long long V, float grad
 
 VFD_API int vfd_score_finalize(const double* per_clip, int n, double inv_count, float* scores, float* minmax,
                                void* stream_) {
-  if (per_clip == nullptr || scores == nullptr || n < 0) return set_error(VFD_ERR_ARG, "score_finalize: bad arguments");
   if (n == 0) return VFD_OK;
+  if (per_clip == nullptr || scores == nullptr || n < 0) return set_error(VFD_ERR_ARG, "score_finalize: bad arguments");
   score_finalize_kernel<<<1, 256, 0, STREAM>>>(per_clip, n, inv_count, scores, minmax);
   return check_launch("score_finalize");
 }
 
 VFD_API int vfd_score_scale(const float* scores, long long n, const float* minmax, float* out, void* stream_) {
+  if (n == 0) return VFD_OK;
   if (scores == nullptr || minmax == nullptr || out == nullptr || n < 0)
     return set_error(VFD_ERR_ARG, "score_scale: bad arguments");
-  if (n == 0) return VFD_OK;
   score_scale_kernel<<<blocks_for(n, 256, 148 * 4), 256, 0, STREAM>>>(scores, n, minmax, out);
   return check_launch("score_scale");
 }
 
 VFD_API int vfd_threshold_open(const float* predict, int N, int D, int H, int W, float thr, float* t_out,
                                float* m_out, void* stream_) {
+  if (N == 0) return VFD_OK;
   if (predict == nullptr || m_out == nullptr || N < 0 || D <= 0 || H <= 0 || W <= 0)
     return set_error(VFD_ERR_ARG, "threshold_open: bad arguments");
   if (W > 512) return set_error(VFD_ERR_ARG, "threshold_open: W > 512 (OpenCV's channel limit; the reference fails too)");
@@ -528,6 +533,7 @@ VFD_API int vfd_threshold_open(const float* predict, int N, int D, int H, int W,
 
 VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long long n, float thr,
                                  unsigned long long* counts, void* stream_) {
+  if (n == 0) return VFD_OK;
   if (labels == nullptr || scores == nullptr || counts == nullptr || n < 0)
     return set_error(VFD_ERR_ARG, "confusion_counts: bad arguments");
   if ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(scores)) % 16)
@@ -538,7 +544,7 @@ VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long 
 }
 
 VFD_API int vfd_roc_auc(const float* scores, const float* labels, int n, double* out, void* stream_) {
-  if (scores == nullptr || labels == nullptr || out == nullptr || n < 0)
+  if (out == nullptr || n < 0 || (n > 0 && (scores == nullptr || labels == nullptr)))
     return set_error(VFD_ERR_ARG, "roc_auc: bad arguments");
   if (n > kAucMax) return set_error(VFD_ERR_ARG, "roc_auc: at most 16384 scores per call");
   int npad = kAucThreads;
