@@ -309,3 +309,51 @@ def test_empty_batches_are_no_ops():
     assert V.video_to_flow(torch.empty(0, 3, 16, 32, 32, device=DEV)).shape == (0, 3, 16, 32, 32)
     out = V.evaluate.roc_auc(torch.empty(0, device=DEV), torch.empty(0, device=DEV))
     assert out[0].isnan() and out[1] == 0 and out[2] == 0
+
+
+def test_gan_evaluator_against_oracle_composition():
+    """MyGAN.test on the device (models/mygannet.py:369-475) vs the same loop written with the oracle pieces
+    (generator, threshold, cv2-pinned opening, cv2-pinned flow, discriminator, sklearn metrics). About 1-2 % of
+    the voxels of a random-init generator sit within bf16 noise of the 0.5 threshold, hence the 2e-2 tolerance on
+    the mask metrics."""
+    import numpy as np
+    from oracle import flow_oracle as FO
+    from helpers import build_cfg1_nets, flow_clip
+    B, D, S = 2, 16, 64
+    netg, netd = build_cfg1_nets()
+    sd_g = {k: v.clone() for k, v in netg.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netd.state_dict().items()}
+    ev = V.evaluate.GanEvaluator(netg.to(DEV).train(), netd.to(DEV).train())
+    want = {k: 0.0 for k in V.evaluate.TEST_KEYS}
+    gts, preds = [], []
+    bce = torch.nn.BCELoss()
+    for it in range(2):
+        inp = flow_clip(B, D, S, 60 + it)
+        gt = (flow_clip(B, D, S, 70 + it)[:, :1] > 0.1).float()
+        ev.add_batch(inp.to(DEV), gt.to(DEV))
+        with torch.no_grad():
+            p = O.netg_forward(sd_g, inp, True, [1.0] * 4)
+            m = O.morphology_proc(O.threshold(p))
+            gt3, pre3 = O.gray2rgb(gt), O.gray2rgb(p)
+            gt_flow = torch.from_numpy(FO.video_to_flow(gt3.numpy())[0])
+            pre_flow = torch.from_numpy(FO.video_to_flow(pre3.numpy())[0])
+            s_pr, s_fr, t_pr, t_fr = O.netd_forward(sd_d, gt3, gt_flow, True)
+            s_pf, s_ff, t_pf, t_ff = O.netd_forward(sd_d, pre3, pre_flow, True)
+            adv_s, adv_t, con = O.l2_loss(s_fr, s_ff), O.l2_loss(t_fr, t_ff), O.weighted_bce(p, gt)
+            ones, zeros = torch.ones(B), torch.zeros(B)
+            e = [bce(s_pr, ones), bce(t_pr, ones), bce(s_pf, zeros), bce(t_pf, zeros)]
+            real, fake = (e[0] + e[1]) * 0.5, (e[2] + e[3]) * 0.5
+            vals = e + [real, fake, (real + fake) * 0.5, adv_s, adv_t, adv_s + adv_t, con, adv_t * 1 + con * 10]
+        for k, v in zip(V.evaluate.TEST_KEYS, vals):
+            want[k] += float(v) / 2
+        gts.append(gt.numpy().astype(np.int32).ravel())
+        preds.append(m.numpy().ravel())
+    errors, scores = ev.result()
+    gts, preds = np.concatenate(gts), np.concatenate(preds)
+    assert 0.02 < preds.mean() < 0.98                       # a non-trivial mask survives the opening
+    for metric, key in (("roc", "score/roc"), ("pr", "score/pr"), ("f1_score", "score/f1")):
+        assert abs(scores[key] - O.evaluate(gts, preds, metric)) < 2e-2, (key, scores[key])
+    for k in V.evaluate.TEST_KEYS:
+        tol = 5e-2 if ("adv" in k or "/err_g/" in k) else 2e-2
+        assert np.isfinite(want[k]), k
+        assert abs(errors[k] - want[k]) <= tol * abs(want[k]) + 1e-4, (k, errors[k], want[k])

@@ -78,3 +78,60 @@ def roc_auc(labels, scores):
     out = torch.empty(3, dtype=torch.float64, device=scores.device)
     ops.roc_auc_op(scores.contiguous().float().view(-1), labels.contiguous().float().view(-1), out)
     return out
+
+
+TEST_KEYS = ("d/err_d_real_s/test", "d/err_d_real_t/test", "d/err_d_fake_s/test", "d/err_d_fake_t/test",
+             "d/err_d_real/test", "d/err_d_fake/test", "d/err_d/test", "g/err_g_adv_s/test", "g/err_g_adv_t/test",
+             "g/err_g_adv/test", "g/err_g_con/test", "g/err_g/test")
+
+
+class GanEvaluator:
+    """``MyGAN.test`` (models/mygannet.py:369-475) without its host detours: per batch the generator, threshold +
+    5x5 opening, both optical flows, the discriminator on (gt, gt_flow) and (predict, pre_flow) and the twelve
+    losses; the flattened (gt, m_pre) voxel arrays the reference hands to sklearn are reduced to confusion counts
+    on the fly. ``result()`` does the one device->host read and returns the dictionaries the reference logs
+    (``errors_dict`` means :459-472, ``score_dict`` :454-458).
+
+    Like the reference, it does not switch the nets to ``eval()`` (BatchNorm keeps using batch statistics and
+    updating its running ones) -- call ``.eval()`` yourself if that is not what you want -- and it
+    keeps the reference's quirk that ``err_g`` is built from the temporal adversarial term only (:414)."""
+
+    def __init__(self, netg, netd, w_adv=1, w_con=10, pos_weight=2):
+        self.netg, self.netd = netg, netd
+        self.w_adv, self.w_con, self.pos_weight = w_adv, w_con, pos_weight
+        dev = next(netg.parameters()).device
+        self.sums = torch.zeros(len(TEST_KEYS), dtype=torch.float64, device=dev)
+        self.counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.batches = 0
+
+    @torch.no_grad()
+    def add_batch(self, inp, gt):
+        """inp (B,3,D,H,W), gt (B,1,D,H,W) on the GPU -> (predict, t_pre, m_pre) of the batch (device tensors)."""
+        import torch.nn.functional as F
+        from .flow import video_to_flow
+        netg, netd = self.netg, self.netd
+        logits, _ = netg.forward_cl(ops.PackFn.apply(inp, 0))
+        predict = ops.SigmoidHeadFn.apply(logits)
+        t_pre, m_pre = threshold_open(predict)
+        gt_flow = video_to_flow(gt.expand(-1, 3, -1, -1, -1))
+        pre_flow = video_to_flow(predict.expand(-1, 3, -1, -1, -1))
+        s_pr, s_fr, t_pr, t_fr = netd.forward_cl(ops.PackFn.apply(gt, 3), ops.PackFn.apply(gt_flow, 0))
+        s_pf, s_ff, t_pf, t_ff = netd.forward_cl(ops.PackFn.apply(predict, 3), ops.PackFn.apply(pre_flow, 0))
+        adv_s = ops.mse_cl(s_fr, s_ff, netd.spatdisc.feat_channels)
+        adv_t = ops.mse_cl(t_fr, t_ff, netd.tempdisc.feat_channels)
+        con = ops.WeightedBceFn.apply(predict, gt, float(self.pos_weight))
+        ones, zeros = torch.ones_like(s_pr), torch.zeros_like(s_pf)
+        e_rs, e_rt = F.binary_cross_entropy(s_pr, ones), F.binary_cross_entropy(t_pr, ones)
+        e_fs, e_ft = F.binary_cross_entropy(s_pf, zeros), F.binary_cross_entropy(t_pf, zeros)
+        real, fake = (e_rs + e_rt) * 0.5, (e_fs + e_ft) * 0.5
+        self.sums += torch.stack([e_rs, e_rt, e_fs, e_ft, real, fake, (real + fake) * 0.5, adv_s, adv_t, adv_s + adv_t,
+                                  con, adv_t * self.w_adv + con * self.w_con]).double()
+        confusion_counts(gt, m_pre, 0.20, self.counts)
+        self.batches += 1
+        return predict, t_pre, m_pre
+
+    def result(self):
+        """-> (errors_dict, score_dict): per-batch means of the twelve losses; roc / pr / f1 of the opened masks."""
+        vals = (self.sums / max(self.batches, 1)).tolist()
+        scores = binary_metrics_from_counts(*self.counts.tolist())
+        return dict(zip(TEST_KEYS, vals)), {"score/roc": scores["roc"], "score/pr": scores["pr"], "score/f1": scores["f1"]}
