@@ -88,6 +88,21 @@ def test_tiny_pointwise_conv_and_fused_statistics(cin, cout, N, D, H, W, bias):
     assert float((stats - exact).abs().max()) <= 1e-5 * float(exact.abs().max())
 
 
+def test_batched_weight_packing_equals_per_weight_packing():
+    """WeightPacker (one launch for every conv weight of a net) writes the same bf16 operands as pack_weight."""
+    torch.manual_seed(2)
+    net = V.NetD(types.SimpleNamespace(nfr=16, isize=64)).to(DEV)
+    net.apply(V.weights_init)
+    packer = ops.WeightPacker([net])
+    packer.pack_all()
+    assert len(packer.weights) == 18
+    for w, pw in packer.entries:
+        fwd, dgrad = torch.empty_like(pw.fwd), torch.empty_like(pw.dgrad)
+        ops.pack_weight(w.detach(), fwd, 0)
+        ops.pack_weight(w.detach(), dgrad, 1)
+        assert torch.equal(fwd, pw.fwd) and torch.equal(dgrad, pw.dgrad), tuple(w.shape)
+
+
 def test_conv_dgrad_fp32_output_meets_1e3():
     """dgrad with the fp32 epilogue: only accumulation order differs from the matched oracle."""
     x = torch.randn(2, 64, 2, 16, 16, device=DEV)

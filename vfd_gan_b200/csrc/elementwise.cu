@@ -134,21 +134,39 @@ struct PackJob {
   int cout, cin, taps, rows, ck, mode;
   long long begin;   // first flattened element of this job
 };
+constexpr int kPackPerBlock = 256 * 8;   // flattened output elements per block
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = njobs - 1;   // last job with begin <= i
+  // one job lookup per block (binary search for the block's first element); a block that straddles job
+  // boundaries walks forward from there
+  __shared__ int s_job;
+  const long long base = (long long)blockIdx.x * kPackPerBlock;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;   // last job with begin <= base
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+      if (jobs[mid].begin <= base) lo = mid; else hi = mid - 1;
     }
-    const PackJob jb = jobs[lo];
-    const long long e = i - jb.begin;
-    const int c = (int)(e % jb.ck);
-    const long long t = e / jb.ck;
-    const int tap = (int)(t % jb.taps);
-    const int row = (int)(t / jb.taps);
+    s_job = lo;
+  }
+  __syncthreads();
+  int j = s_job;
+  PackJob jb = jobs[j];
+  long long next_begin = j + 1 < njobs ? jobs[j + 1].begin : total;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i >= total) break;
+    while (i >= next_begin) {
+      ++j;
+      jb = jobs[j];
+      next_begin = j + 1 < njobs ? jobs[j + 1].begin : total;
+    }
+    const unsigned e = (unsigned)(i - jb.begin);          // a single packed weight has < 2^32 elements
+    const unsigned t = e / (unsigned)jb.ck;
+    const int c = (int)(e - t * (unsigned)jb.ck);
+    const int row = (int)(t / (unsigned)jb.taps);
+    const int tap = (int)(t - (unsigned)row * (unsigned)jb.taps);
     float v = 0.f;
     if (jb.mode == 0) {
       if (row < jb.cout && c < jb.cin) v = jb.w[((long long)row * jb.cin + c) * jb.taps + tap];
@@ -1335,7 +1353,9 @@ VFD_API int vfd_pack_weight(const float* w, void* wp, int Cout, int Cin, int tap
 
 VFD_API int vfd_pack_weights_batched(const void* jobs, int njobs, long long total, void* stream_) {
   if (njobs <= 0 || total <= 0) return 0;
-  pack_weights_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>((const PackJob*)jobs, njobs, total);
+  const long long blocks = (total + kPackPerBlock - 1) / kPackPerBlock;
+  if (blocks >= (1LL << 31)) return set_error(VFD_ERR_ARG, "pack_weights_batched: too many elements");
+  pack_weights_batched_kernel<<<(unsigned)blocks, 256, 0, STREAM>>>((const PackJob*)jobs, njobs, total);
   return check_launch("pack_weights_batched");
 }
 
