@@ -228,6 +228,28 @@ def cpu_baseline_sample():
             "sample": f"{n} steps of batch 2 of the same {NFR}x3x{ISIZE}x{ISIZE} workload (oracle port, fp32, torch CPU)"}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, ...) write to the process's stdout; the contract is ONE JSON line there.
+    Point file descriptor 1 at stderr for the duration of the run and keep the real stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def finish(world):
     """Leave without tearing NCCL down: the captured CUDA graph still references the communicator and
     destroy_process_group() can block on it. All ranks synchronise, flush and exit 0."""
@@ -266,6 +288,7 @@ def main():
     import vfd_gan_b200 as V
     from vfd_gan_b200 import _lib, ops
 
+    claim_stdout()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: vfd_gan_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -451,7 +474,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample()
-    print(json.dumps(line), flush=True)
+    emit(line)
     finish(world)
 
 
