@@ -219,7 +219,8 @@ VFD_API int vfd_threshold_open(const float* predict, int N, int D, int H, int W,
 VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long long n, float thr,
                                  unsigned long long* counts, void* stream);
 /* exact tie-aware ROC area of n <= 16384 (score, label) pairs = sklearn auc(roc_curve(...))
- * (lib/evaluate.py:37-38); out = device double[3]: AUC, #positives, #negatives */
+ * (lib/evaluate.py:37-38) and the precision-recall area auc(recall, precision) of precision_recall_curve
+ * (lib/evaluate.py:67-68); out = device double[4]: ROC area, #positives, #negatives, PR area */
 VFD_API int vfd_roc_auc(const float* scores, const float* labels, int n, double* out, void* stream);
 
 /* ---- video_to_flow (lib/utils.py:94-129; called at models/mygannet.py:281-282,404-405) on the device -----

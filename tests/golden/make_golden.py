@@ -206,8 +206,9 @@ def eval_fixture():
     s[:5] = 0.0
     s[5] = -0.0
     fpr, tpr, _ = roc_curve(lab, s)
+    precision, recall, _ = precision_recall_curve(lab, s)
     out["scores"] = {"labels": torch.from_numpy(lab), "scores": torch.from_numpy(s.astype(np.float32)),
-                     "roc": float(auc(fpr, tpr))}
+                     "roc": float(auc(fpr, tpr)), "pr": float(auc(recall, precision))}
     torch.save(out, os.path.join(HERE, "eval_small.pt"))
     print("eval:", out["binary"]["roc"], out["binary"]["pr"], out["binary"]["f1"], out["scores"]["roc"])
 

@@ -285,6 +285,7 @@ def test_roc_auc_kernel_against_sklearn_fixture():
     s = golden("eval_small.pt")["scores"]
     out = V.evaluate.roc_auc(s["labels"].to(DEV), s["scores"].to(DEV))
     assert abs(float(out[0]) - s["roc"]) < 1e-12
+    assert abs(float(out[3]) - s["pr"]) < 1e-12                   # lib/evaluate.py 'pr': auc(recall, precision)
     assert int(out[1]) == int(s["labels"].sum())
     torch.manual_seed(9)
     for n in (2, 1000, 1025, 16384):                              # padding / several elements per thread
@@ -293,6 +294,7 @@ def test_roc_auc_kernel_against_sklearn_fixture():
         sc = torch.randn(n).round(decimals=1)
         got = V.evaluate.roc_auc(lab.to(DEV), sc.to(DEV))
         assert abs(float(got[0]) - O.evaluate(lab.numpy(), sc.numpy(), "roc")) < 1e-12, n
+        assert abs(float(got[3]) - O.evaluate(lab.numpy(), sc.numpy(), "pr")) < 1e-12, n
     with pytest.raises(RuntimeError):
         V.evaluate.roc_auc(torch.zeros(20000, device=DEV), torch.zeros(20000, device=DEV))
 

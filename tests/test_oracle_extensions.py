@@ -106,3 +106,4 @@ def test_metrics_match_sklearn_fixture():
     upto = np.searchsorted(neg, sc[lab], side="right")
     area = float((below + 0.5 * (upto - below)).sum() / (lab.sum() * (~lab).sum()))
     assert abs(area - s["roc"]) < 1e-12
+    assert abs(O.evaluate(s["labels"].numpy(), s["scores"].numpy(), "pr") - s["pr"]) < 1e-12

@@ -316,7 +316,8 @@ confusion_kernel(const float* __restrict__ labels, const float* __restrict__ sco
 // memory, an inclusive scan of the negatives, and the tie-aware Mann-Whitney count
 //   AUC = sum over positives of (#negatives below + 0.5 * #negatives tied) / (P * N),
 // which is what sklearn's auc(roc_curve(labels, scores)) (lib/evaluate.py:37-38) integrates.
-// out[0] = AUC (NaN when a class is empty), out[1] = P, out[2] = N.
+// out[0] = AUC (NaN when a class is empty), out[1] = P, out[2] = N, out[3] = area under the precision-recall curve
+// as lib/evaluate.py:67-68 computes it (auc(recall, precision) of precision_recall_curve).
 constexpr int kAucMax = 16384;
 constexpr int kAucThreads = 1024;
 
@@ -405,32 +406,55 @@ auc_kernel(const float* __restrict__ scores, const float* __restrict__ labels, i
     }
   }
   __syncthreads();
-  double local = 0.0;
+  double local = 0.0, local_pr = 0.0;
   for (int i = tid; i < n; i += kAucThreads) {
-    if ((val[i] & 3u) != 1u) continue;
     const uint32_t kk = key[i];
-    int lo = 0, hi = i;                 // first index whose key == kk
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (key[mid] < kk) lo = mid + 1; else hi = mid;
-    }
-    const int first = lo;
-    lo = i;
-    hi = n - 1;                         // last index whose key == kk
+    const bool group_start = i == 0 || key[i - 1] != kk;
+    const bool is_pos = (val[i] & 3u) == 1u;
+    if (!is_pos && !group_start) continue;
+    int lo = i, hi = n - 1;              // last index whose key == kk
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (key[mid] > kk) hi = mid - 1; else lo = mid;
     }
     const int last = lo;
-    const uint32_t below = first > 0 ? (val[first - 1] >> 2) : 0u;
-    const uint32_t upto = val[last] >> 2;
-    local += (double)below + 0.5 * (double)(upto - below);
+    if (is_pos) {
+      lo = 0;
+      hi = i;                            // first index whose key == kk
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key[mid] < kk) lo = mid + 1; else hi = mid;
+      }
+      const int first = lo;
+      const uint32_t below = first > 0 ? (val[first - 1] >> 2) : 0u;
+      const uint32_t upto = val[last] >> 2;
+      local += (double)below + 0.5 * (double)(upto - below);
+    }
+    if (group_start && P > 0) {
+      // precision-recall point of the threshold "score >= this value" and of the next higher distinct value
+      // (or the end point (recall 0, precision 1)): one trapezoid of sklearn's auc(recall, precision)
+      const uint32_t nb = i > 0 ? (val[i - 1] >> 2) : 0u;          // negatives below the threshold
+      const double tp = (double)P - (double)((uint32_t)i - nb), fp = (double)N - (double)nb;
+      const double r0 = tp / (double)P, p0 = tp / (tp + fp);
+      double r1 = 0.0, p1 = 1.0;
+      const int j = last + 1;
+      if (j < n) {
+        const uint32_t nbj = val[j - 1] >> 2;
+        const double tpj = (double)P - (double)((uint32_t)j - nbj), fpj = (double)N - (double)nbj;
+        r1 = tpj / (double)P;
+        p1 = tpj / (tpj + fpj);
+      }
+      local_pr += (r0 - r1) * (p0 + p1) * 0.5;
+    }
   }
   local = block_sum_d(local);
+  __syncthreads();
+  local_pr = block_sum_d(local_pr);
   if (tid == 0) {
     out[0] = (P > 0 && N > 0) ? local / ((double)P * (double)N) : nan("");
     out[1] = (double)P;
     out[2] = (double)N;
+    out[3] = P > 0 ? local_pr : nan("");
   }
 }
 

@@ -71,11 +71,11 @@ def binary_metrics_from_counts(tp, fp, fn, tn):
 
 def roc_auc(labels, scores):
     """Exact ROC area of up to 16384 (score, label) pairs on the device (the per-clip anomaly-score sweep);
-    equals ``lib/evaluate.py``'s ``roc`` = ``auc(*roc_curve(labels, scores)[:2])``. Returns a device double[3]:
-    area, #positives, #negatives (no host synchronisation)."""
+    equals ``lib/evaluate.py``'s ``roc`` = ``auc(*roc_curve(labels, scores)[:2])``. Returns a device double[4]:
+    ROC area, #positives, #negatives, PR area (``lib/evaluate.py``'s ``pr``) -- no host synchronisation."""
     if not scores.is_cuda:
         raise RuntimeError("roc_auc: vfd_gan_b200 has no CPU path")
-    out = torch.empty(3, dtype=torch.float64, device=scores.device)
+    out = torch.empty(4, dtype=torch.float64, device=scores.device)
     ops.roc_auc_op(scores.contiguous().float().view(-1), labels.contiguous().float().view(-1), out)
     return out
 
