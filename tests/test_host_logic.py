@@ -124,3 +124,46 @@ def test_new_modules_fail_loudly_on_cpu():
         V.AutoEncoder()(torch.rand(1, 3, 16, 16, 16))
     with pytest.raises(RuntimeError):
         V.video_to_flow(torch.rand(1, 3, 4, 32, 32))
+
+
+def test_step_arena_sizing_reuse_and_growth():
+    """ops.StepArena (weight-gradient accumulators of one train step): the first step only measures, later steps
+    hand out zeroed, 256-byte aligned slices of one buffer, and a grown arena keeps the old buffer alive (a captured
+    CUDA graph may still point into it)."""
+    from vfd_gan_b200 import ops
+    a = ops.StepArena()
+    dev = torch.device("cpu")
+    assert a.take((2, 3), dev) is None                      # inactive outside a step
+    a.begin(dev)
+    assert a.take((3, 8, 32), dev) is None and a.take((1, 8, 32), dev) is None   # first step: measure only
+    a.end()
+    a.begin(dev)
+    x, y = a.take((3, 8, 32), dev), a.take((1, 8, 32), dev)
+    assert x.shape == (3, 8, 32) and y.shape == (1, 8, 32) and x.dtype == torch.float32
+    assert x.data_ptr() % 256 == a.buf.data_ptr() % 256 and (y.data_ptr() - x.data_ptr()) % 256 == 0
+    x.fill_(1.0)
+    y.fill_(2.0)
+    a.end()
+    first = a.buf
+    a.begin(dev)                                            # same demand: same buffer, zeroed again
+    x2 = a.take((3, 8, 32), dev)
+    assert a.buf is first and x2.data_ptr() == x.data_ptr() and float(x2.abs().max()) == 0.0
+    a.take((1, 8, 32), dev)
+    assert a.take((64, 64, 64), dev) is None                # over the capacity: falls back, remembers the demand
+    a.end()
+    a.begin(dev)
+    assert a.buf is not first and first in a.retired and a.take((64, 64, 64), dev) is not None
+    a.end()
+
+
+def test_zero_grad_views_are_shared_only_inside_a_step():
+    from vfd_gan_b200 import ops
+    dev = torch.device("cpu")
+    g1, g2 = ops.zero_grad(5, dev), ops.zero_grad(5, dev)
+    assert g1.data_ptr() != g2.data_ptr()                   # outside a fused step: private tensors
+    ops.ARENA.begin(dev)
+    try:
+        h1, h2 = ops.zero_grad(5, dev), ops.zero_grad(7, dev)
+        assert h1.data_ptr() == h2.data_ptr() and float(h2.abs().max()) == 0.0
+    finally:
+        ops.ARENA.end()
