@@ -107,3 +107,24 @@ def test_metrics_match_sklearn_fixture():
     area = float((below + 0.5 * (upto - below)).sum() / (lab.sum() * (~lab).sum()))
     assert abs(area - s["roc"]) < 1e-12
     assert abs(O.evaluate(s["labels"].numpy(), s["scores"].numpy(), "pr") - s["pr"]) < 1e-12
+
+
+def test_binary_metric_formulas_on_edge_cases():
+    """binary_metrics_from_counts against the sklearn calls of lib/evaluate.py on masks with no predicted
+    positives, all predicted positives, a perfect mask and an inverted one."""
+    import warnings
+    from vfd_gan_b200.evaluate import binary_metrics_from_counts
+    rng = np.random.default_rng(3)
+    gts = (rng.random(4000) > 0.7).astype(np.int32)
+    cases = {"none": np.zeros(4000, np.float32), "all": np.ones(4000, np.float32), "perfect": gts.astype(np.float32),
+             "inverted": 1.0 - gts.astype(np.float32), "noisy": ((gts == 1) ^ (rng.random(4000) > 0.8)).astype(np.float32)}
+    for name, pred in cases.items():
+        tp = int(((gts == 1) & (pred >= 0.2)).sum())
+        fp = int(((gts == 0) & (pred >= 0.2)).sum())
+        fn = int(((gts == 1) & (pred < 0.2)).sum())
+        tn = int(((gts == 0) & (pred < 0.2)).sum())
+        got = binary_metrics_from_counts(tp, fp, fn, tn)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for metric, key in (("roc", "roc"), ("pr", "pr"), ("f1_score", "f1")):
+                assert abs(got[key] - O.evaluate(gts, pred, metric)) < 1e-9, (name, key, got[key])
