@@ -145,3 +145,28 @@ def test_compat_install_rebinds_the_reference_names(reference_modules):
     finally:
         compat.uninstall()
     assert mg.NetG is ref_netg and lu.video_to_flow is ref_flow
+
+
+def test_checkpoint_files_load_both_ways(reference_modules, tmp_path):
+    """Checkpoints are ``{'epoch', 'state_dict'}`` files (lib/train_gan.py:52-57), possibly with DataParallel's
+    ``module.`` prefix (lib/utils.py:15-22; test.py:117-120 loads them into NetG()). A file written from the
+    reference's nets loads into ours and back, bit for bit."""
+    import types
+    import vfd_gan_b200 as V
+    mg = reference_modules.mygannet
+    torch.manual_seed(4)
+    rg, rd = mg.NetG(), mg.NetD(types.SimpleNamespace(nfr=16, isize=128))
+    path_g, path_d = tmp_path / "roc_ep0003_netG.pth", tmp_path / "roc_ep0003_netD.pth"
+    torch.save({"epoch": 4, "state_dict": {"module." + k: v for k, v in rg.state_dict().items()}}, path_g)
+    torch.save({"epoch": 4, "state_dict": rd.state_dict()}, path_d)
+    og, od = V.NetG(), V.NetD(types.SimpleNamespace(nfr=16, isize=128))
+    og.load_state_dict(V.strip_module_prefix(torch.load(path_g)["state_dict"]))
+    od.load_state_dict(V.strip_module_prefix(torch.load(path_d)["state_dict"]))
+    for k, v in rg.state_dict().items():
+        assert torch.equal(og.state_dict()[k], v), k
+    for k, v in rd.state_dict().items():
+        assert torch.equal(od.state_dict()[k], v), k
+    torch.save({"epoch": 5, "state_dict": og.state_dict()}, path_g)          # and back into the reference's NetG
+    rg2 = mg.NetG()
+    rg2.load_state_dict(torch.load(path_g)["state_dict"])
+    assert all(torch.equal(rg2.state_dict()[k], v) for k, v in rg.state_dict().items())

@@ -9,7 +9,7 @@ from . import _lib, ops  # noqa: F401
 from .spatiotempconv import SpatioTemporalConv  # noqa: F401
 from .mygannet import NetgConv, NetG, NetdConv, SDisc, TDisc, NetD  # noqa: F401
 from .convlstm import ConvLSTMCell, ConvLSTM  # noqa: F401
-from .losses import weights_init, l2_loss, weighted_bce, gray2rgb  # noqa: F401
+from .losses import weights_init, l2_loss, weighted_bce, gray2rgb, strip_module_prefix  # noqa: F401
 from .composed import NetGLstm, Encoder, EncDecEncG, AnomalyScorer, anomaly_scores, latent_l2_and_scores  # noqa: F401
 from .stcnn import C2plus1d_Block, AutoEncoder, StcnnTrainStep  # noqa: F401
 from . import evaluate  # noqa: F401
@@ -17,6 +17,6 @@ from .flow import video_to_flow  # noqa: F401
 from .step import GanTrainStep, HostBatchStep, GradAllReducer, LOSS_KEYS  # noqa: F401
 
 __all__ = ["SpatioTemporalConv", "NetgConv", "NetG", "NetdConv", "SDisc", "TDisc", "NetD", "ConvLSTMCell",
-           "ConvLSTM", "weights_init", "l2_loss", "weighted_bce", "gray2rgb", "GanTrainStep", "HostBatchStep",
+           "ConvLSTM", "weights_init", "l2_loss", "weighted_bce", "gray2rgb", "strip_module_prefix", "GanTrainStep", "HostBatchStep",
            "GradAllReducer", "LOSS_KEYS", "NetGLstm", "Encoder", "EncDecEncG", "AnomalyScorer", "anomaly_scores",
            "latent_l2_and_scores", "C2plus1d_Block", "AutoEncoder", "StcnnTrainStep", "evaluate", "video_to_flow"]

@@ -28,5 +28,16 @@ def weighted_bce(input, target, pos_weight=2):
     return ops.WeightedBceFn.apply(input, target, float(pos_weight))
 
 
+def strip_module_prefix(state_dict):
+    """What ``fix_model_state_dict`` (lib/utils.py:15-22) is meant to do -- drop the ``module.`` prefix that
+    ``nn.DataParallel`` puts on every key -- without its NameError (it uses an ``OrderedDict`` the module never
+    imports). Checkpoints are ``{'epoch': int, 'state_dict': ...}`` files (lib/train_gan.py:52-57)."""
+    from collections import OrderedDict
+    out = OrderedDict()
+    for k, v in state_dict.items():
+        out[k[7:] if k.startswith("module.") else k] = v
+    return out
+
+
 def gray2rgb(video):
     return torch.cat([video, video, video], dim=1)
