@@ -3,7 +3,7 @@
  * The reference (umaionigiri/vfd_gan) has no native layer: its hot path bottoms out in torch
  * library calls (nn.Conv3d / nn.BatchNorm3d / nn.AvgPool3d / nn.Upsample / nn.Dropout ...).
  * Each entry point below replaces one of those call sites; the citation is reference file:line.
- * The host side (vfd_gan_b200/*.py) binds these with ctypes and registers them as torch.library
+ * The host side (the vfd_gan_b200 Python package) binds these with ctypes and registers them as torch.library
  * ops; see INTEGRATION.md.
  *
  * Conventions
