@@ -167,3 +167,22 @@ def test_zero_grad_views_are_shared_only_inside_a_step():
         assert h1.data_ptr() == h2.data_ptr() and float(h2.abs().max()) == 0.0
     finally:
         ops.ARENA.end()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/vfd_b200.h is the drop-in boundary: it must compile as C99 and as C++ with no torch / CUDA types."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "vfd_b200.h"\nint main(void) { return vfd_abi_version() == 0; }\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not installed")
+        args = [cc, std, "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "include")]
+        if cc == "g++":
+            args += ["-x", "c++"]
+        r = subprocess.run(args + [str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(os.path.join(root, "include", "vfd_b200.h")).read()
+    assert "at::" not in text and "c10::" not in text and "#include <torch" not in text
