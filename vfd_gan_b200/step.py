@@ -21,7 +21,7 @@ Optical flow (``video_to_flow``, host cv2 Farneback, lib/utils.py:94-129) is an 
 SURVEY.md section 8d.
 
 CUDA graph: after two eager steps the whole step (both forward passes, both backward passes, the weight
-re-packing, the gradient all-reduces and the two fused-Adam updates -- about 1100 kernel launches) is
+re-packing, the gradient all-reduces and the two fused-Adam updates -- about 830 kernel launches) is
 captured once into a CUDA graph and replayed, which removes the Python / dispatcher launch overhead
 that otherwise bounds the step. Dropout masks stay fresh under replay because the kernels add a device
 resident step counter to their Philox seed. ``VFD_CUDA_GRAPH=0`` (or ``graph=False``) keeps the step eager.
