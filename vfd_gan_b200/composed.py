@@ -119,7 +119,9 @@ class AnomalyScorer:
     @torch.no_grad()
     def finish(self):
         """-> (scaled scores over all ranks in rank-major order, raw scores)."""
-        local = torch.cat(self.chunks) if self.chunks else torch.empty(0)
+        if not self.chunks:
+            raise RuntimeError("AnomalyScorer.finish(): no batch was scored")
+        local = torch.cat(self.chunks)
         self.chunks = []
         raw = gather_scores(local, self.group)
         mm = torch.stack([raw.min(), raw.max()])
