@@ -8,9 +8,9 @@ batch of synthetic clips. Workload at every N: BASELINE.json configs[1] -- 16x3x
 batch 32 PER GPU (weak scaling), bf16 tensor-core convs with fp32 accumulation / fp32 master weights.
 Prints ONE JSON line on rank 0.
 
-``--impl reference`` times the reference's own CPU implementation of the step (the oracle port in
-oracle/vfd_oracle.py, validated bit-exact against the reference modules; the reference itself is
-pure Python importing /root/reference, which does not exist on the GPU box) on the host cores.
+``--impl reference`` times the reference's own CPU implementation of the step on the host cores: its unmodified
+modules, staged under oracle/_ref by oracle/make_ref.py (git-ignored, shipped to the GPU box); the oracle port
+only if that copy is missing.
 """
 import argparse
 import json
@@ -174,58 +174,104 @@ def model_conv_shapes(nfr, s):
     return g, sd + td
 
 
+class CpuReferenceStep:
+    """The reference's own CPU implementation of the step: its unmodified ``NetG`` / ``NetD`` modules and losses
+    (staged under oracle/_ref by oracle/make_ref.py) driven by ``optimize_params``' sequence
+    (models/mygannet.py:350-366; ``MyGAN`` itself hard-codes 'cuda', so the loop is restated around the modules).
+    112 is not a size the reference's NetD accepts: its two Linears and TDisc's global pool are
+    re-created for the workload's geometry, every conv / BatchNorm is the reference's. Falls back to the oracle
+    port (validated bit-exact against these modules) when oracle/_ref is not staged."""
+
+    def __init__(self, batch):
+        import torch.nn as nn
+        from oracle import make_ref
+        from oracle import vfd_oracle as O
+        self.batch = O.synthetic_batch(batch, NFR, ISIZE, seed=0)
+        torch.manual_seed(0)
+        if make_ref.ref_root() is not None:
+            R = make_ref.import_ref()
+            mg, self.lu = R.mygannet, R.utils
+            self.netg = mg.NetG()
+            self.netd = mg.NetD(types.SimpleNamespace(nfr=NFR, isize=128))
+            self.netd.tempdisc.gpool = nn.AvgPool3d((1, ISIZE, ISIZE), stride=1)
+            self.netd.spatdisc.linear = nn.Linear(32 * 32 * (ISIZE // 64) ** 2, 1)
+            self.netd.tempdisc.linear = nn.Linear(32 * 4 * (NFR // 8), 1)
+            self.netg.apply(self.lu.weights_init)
+            self.netd.apply(self.lu.weights_init)
+            self.opt_d = torch.optim.Adam(self.netd.parameters(), lr=2e-5, betas=(0.5, 0.999))
+            self.opt_g = torch.optim.Adam(self.netg.parameters(), lr=2e-5, betas=(0.5, 0.999))
+            self.bce = nn.BCELoss()
+            self.kind = "reference"
+            self.what = "the reference's own modules (oracle/_ref), fp32, torch CPU"
+        else:
+            import vfd_gan_b200 as V
+            netg, netd = V.NetG(), V.NetD(types.SimpleNamespace(nfr=NFR, isize=ISIZE))
+            netg.apply(V.weights_init)
+            netd.apply(V.weights_init)
+            self.port = O.OracleTrainer(netg.state_dict(), netd.state_dict())
+            self.kind = "port"
+            self.what = "oracle port, fp32, torch CPU"
+
+    def step(self):
+        if self.kind == "port":
+            self.port.step(*self.batch)
+            return
+        lu, netg, netd = self.lu, self.netg, self.netd
+        inp, gt, gt_flow, pre_flow = self.batch
+        netg.train(), netd.train()
+        predict = netg(inp)                                                       # forward_g
+        pre_3ch, gt_3ch = lu.gray2rgb(predict.detach()), lu.gray2rgb(gt.detach())  # forward_d (flows are inputs)
+        s_pr, s_fr, t_pr, t_fr = netd(gt_3ch, gt_flow)
+        s_pf, s_ff, t_pf, t_ff = netd(pre_3ch.detach(), pre_flow)
+        self.opt_g.zero_grad()                                                    # backward_g
+        err_g = (lu.l2_loss(s_fr, s_ff) + lu.l2_loss(t_fr, t_ff)) * 1 + lu.weighted_bce(predict, gt) * 10
+        err_g.backward(retain_graph=True)
+        self.opt_g.step()
+        self.opt_d.zero_grad()                                                    # backward_d
+        ones, zeros = torch.ones_like(s_pr), torch.zeros_like(s_pf)
+        err_d = ((self.bce(s_pr, ones) + self.bce(t_pr, ones)) * 0.5 +
+                 (self.bce(s_pf, zeros) + self.bce(t_pf, zeros)) * 0.5) * 0.5
+        err_d.backward()
+        self.opt_d.step()
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of optimize_params on the host cores, bounded sample of the workload."""
-    from oracle import vfd_oracle as O
-    import vfd_gan_b200 as V
+    """CPU arm: the reference's own step on the host cores, bounded sample of the workload."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample_batch = 2
-    torch.manual_seed(0)
-    a = types.SimpleNamespace(nfr=NFR, isize=ISIZE)
-    netg, netd = V.NetG(), V.NetD(a)
-    netg.apply(V.weights_init)
-    netd.apply(V.weights_init)
-    tr = O.OracleTrainer(netg.state_dict(), netd.state_dict())
-    batch = O.synthetic_batch(sample_batch, NFR, ISIZE, seed=0)
+    ref = CpuReferenceStep(sample_batch)
     for _ in range(args.warmup):
-        tr.step(*batch)
+        ref.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        tr.step(*batch)
+        ref.step()
     dt = (time.perf_counter() - t0) / args.steps
     val = sample_batch / dt
-    sample = f"{args.steps} steps of batch {sample_batch} (of the {BATCH_PER_GPU}-clip workload), {NFR}x3x{ISIZE}x{ISIZE}, fp32, torch CPU"
+    sample = (f"{args.steps} steps of batch {sample_batch} (of the {BATCH_PER_GPU}-clip workload), "
+              f"{NFR}x3x{ISIZE}x{ISIZE}, {ref.what}")
     line = {"impl": "reference", "metric": "train_clips_per_sec", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_sample():
     """Bounded CPU sample timed next to the GPU number on rank 0 (N = 1 only)."""
-    from oracle import vfd_oracle as O
-    import vfd_gan_b200 as V
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    a = types.SimpleNamespace(nfr=NFR, isize=ISIZE)
-    netg, netd = V.NetG(), V.NetD(a)
-    netg.apply(V.weights_init)
-    netd.apply(V.weights_init)
-    tr = O.OracleTrainer(netg.state_dict(), netd.state_dict())
-    batch = O.synthetic_batch(2, NFR, ISIZE, seed=0)
-    tr.step(*batch)
+    ref = CpuReferenceStep(2)
+    ref.step()
     t0 = time.perf_counter()
     n = 2
     for _ in range(n):
-        tr.step(*batch)
+        ref.step()
     dt = (time.perf_counter() - t0) / n
-    return {"value": 2 / dt, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{n} steps of batch 2 of the same {NFR}x3x{ISIZE}x{ISIZE} workload (oracle port, fp32, torch CPU)"}
+    return {"value": 2 / dt, "unit": "clips/s", "cores": cores, "kind": ref.kind,
+            "sample": f"{n} steps of batch 2 of the same {NFR}x3x{ISIZE}x{ISIZE} workload ({ref.what})"}
 
 
 _JSON_FD = None

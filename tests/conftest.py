@@ -26,22 +26,9 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def reference_modules():
-    """The reference's own modules, importable only in the build container (read-only mount)."""
-    if not os.path.isdir(REFERENCE):
-        pytest.skip("/root/reference not present (GPU box)")
-    import types
-    for n in ("matplotlib", "matplotlib.pyplot", "skimage", "skimage.transform"):
-        sys.modules.setdefault(n, types.ModuleType(n))
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.modules["matplotlib"].rc = lambda *a, **k: None
-    sys.modules["matplotlib.pyplot"].figure = lambda *a, **k: None
-    sys.modules["skimage"].transform = sys.modules["skimage.transform"]
-    sys.modules["skimage.transform"].resize = None
-    sys.dont_write_bytecode = True
-    if REFERENCE not in sys.path:
-        sys.path.insert(0, REFERENCE)
-    import models.mygannet as mg
-    import models.spatiotempconv as stc
-    import models.convlstm as cl
-    import lib.utils as lu
-    return types.SimpleNamespace(mygannet=mg, spatiotempconv=stc, convlstm=cl, utils=lu)
+    """The reference's own modules: from the read-only mount in the build container, else from the copy staged
+    under oracle/_ref (oracle/make_ref.py; shipped to the GPU box)."""
+    from oracle import make_ref
+    if make_ref.ref_root() is None:
+        pytest.skip("the reference is neither at /root/reference nor staged under oracle/_ref")
+    return make_ref.import_ref()

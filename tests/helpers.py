@@ -110,3 +110,34 @@ def flow_level_agreement(levels, want):
     d = (levels.int() - want.int()).abs()
     d = torch.minimum(d, 256 - d)
     return float((d == 0).float().mean()), float((d <= 1).float().mean())
+
+
+def build_headline_nets(dropout=0.0):
+    """Full-size NetG / NetD for the headline geometry (16 x 112 x 112) with the RNG call sequence of
+    tests/golden/make_golden_headline.py::reference_nets_112."""
+    import vfd_gan_b200 as V
+    torch.manual_seed(0)
+    netg = V.NetG()
+    netd = V.NetD(types.SimpleNamespace(nfr=16, isize=128))       # RNG consumption of the reference's NetD
+    netd.tempdisc.gpool = nn.AvgPool3d((1, 112, 112), stride=1)
+    netd.spatdisc.linear = nn.Linear(32 * 32 * 1, 1)
+    netd.tempdisc.linear = nn.Linear(32 * 4 * 2, 1)
+    netg.apply(V.weights_init)
+    netd.apply(V.weights_init)
+    netg.dropout.p = dropout
+    return netg, netd
+
+
+def dropout_masks_from_seeds(seeds, B, D, S, device, p=0.25):
+    """The Philox keep-masks (scaled by 1/(1-p)) NetG's four decoder dropouts drew for ``seeds``, as fp32 NCDHW CPU
+    tensors the oracle accepts as ``dropout_masks`` (the fused BN+act kernel run on zeros with shift 1, slope 1)."""
+    from vfd_gan_b200 import ops
+    shapes = [(B, 256, D // 16, S // 16, S // 16), (B, 256, D // 8, S // 8, S // 8), (B, 128, D // 4, S // 4, S // 4),
+              (B, 64, D // 2, S // 2, S // 2)]
+    masks = []
+    for seed, (N, C, d, h, w) in zip(seeds, shapes):
+        o = torch.empty(N, d, h, w, C, dtype=torch.bfloat16, device=device)
+        ops.bn_act_fwd(torch.zeros_like(o), torch.zeros(C, device=device), torch.ones(C, device=device), 1.0, o, None,
+                       1, 1, 1, p, seed)
+        masks.append(o.float().permute(0, 4, 1, 2, 3).cpu().contiguous())
+    return masks

@@ -503,3 +503,21 @@ def test_module_step_equals_fused_step():
         got = fused.losses_dict()
         assert abs(got["g/err_g"] - float(err_g)) <= 2e-3 * abs(float(err_g))
         assert abs(got["d/err_d"] - float(err_d)) <= 2e-3 * abs(float(err_d))
+
+
+def test_block_wider_than_the_fused_statistics_limit():
+    """A block whose BatchNorm is wider than the conv epilogue's 1024 statistics columns (reachable through the
+    reference's constructor arguments: NetG(ngf >= 72), SDisc(ndf >= 40)) takes the stand-alone statistics pass
+    and still normalises correctly."""
+    torch.manual_seed(3)
+    blk = V.NetdConv(64, 1040, kernel_size=(1, 3, 3), padding=(0, 1, 1))
+    assert not ops.conv_fuses_stats(1040) and ops.conv_fuses_stats(1024)
+    blk.apply(V.weights_init)
+    sd = {("b." + k): v.clone() for k, v in blk.state_dict().items()}
+    blk = blk.to(DEV).train()
+    x = torch.rand(2, 64, 2, 8, 8) * 2 - 1
+    y = blk(x.to(DEV))
+    want = O.net_conv(sd, "b", x, (1, 3, 3), 0.01, True, round_bf16=True)
+    assert rel(y, want) < 3e-3
+    assert rel(blk.bn.running_var, sd["b.bn.running_var"]) < 1e-2
+    assert rel(blk.bn.running_mean, sd["b.bn.running_mean"]) < 1e-2 + 1e-3

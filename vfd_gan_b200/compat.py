@@ -9,7 +9,7 @@ own modules resolve at call time, so ``trainer.py`` / ``lib/train_gan.py`` / ``t
 What is rebound (reference file:line of the definition that gets shadowed):
   models.spatiotempconv.SpatioTemporalConv                        models/spatiotempconv.py:7
   models.mygannet.{SpatioTemporalConv, NetgConv, NetG, NetdConv, SDisc, TDisc, NetD}   models/mygannet.py:10,13-213
-  models.mygannet.{weighted_bce, video_to_flow, threshold, morphology_proc, fix_model_state_dict} and the same in
+  models.mygannet.{weighted_bce, weights_init, video_to_flow, threshold, morphology_proc, fix_model_state_dict} and the same in
   lib.utils (fix_model_state_dict raises NameError in the reference)   lib/utils.py:15-22,65-71,94-129,139-152
   models.convlstm.{ConvLSTMCell, ConvLSTM}                        models/convlstm.py:6-169
   models.mystcnn.{C2plus1d_Block, AutoEncoder}                    models/mystcnn.py:6-88
@@ -44,7 +44,8 @@ def install(device_flow=True, device_morphology=True):
         _rebind(cl, name, getattr(V, name))
     for name in ("C2plus1d_Block", "AutoEncoder"):
         _rebind(ms, name, getattr(V, name))
-    repl = {"weighted_bce": V.weighted_bce, "fix_model_state_dict": V.strip_module_prefix}
+    repl = {"weighted_bce": V.weighted_bce, "fix_model_state_dict": V.strip_module_prefix,
+            "weights_init": V.weights_init}   # same initialiser + invalidation of the packed bf16 weight copies
     if device_flow:
         repl["video_to_flow"] = V.video_to_flow
     if device_morphology:

@@ -12,6 +12,8 @@ def weights_init(m):
     elif isinstance(m, nn.BatchNorm3d):
         m.weight.data.normal_(1.0, 0.02)
         m.bias.data.fill_(0)
+    # writes through .data do not bump Tensor._version: drop the packed bf16 copies of the conv weights explicitly
+    ops.invalidate_packed_weights()
 
 
 def l2_loss(input, target, size_average=True):

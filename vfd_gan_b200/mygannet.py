@@ -36,7 +36,8 @@ class NetgConv(nn.Module):
     def forward_cl(self, xc, **kw):
         if self.bn.training or self.bn.running_mean is None:
             y, tb = self.conv.forward_cl(xc, fold_bias=True)
-            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, stats_ready=True, **kw)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb,
+                            stats_ready=ops.conv_fuses_stats(self.out_fi), **kw)
         return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):
@@ -145,7 +146,8 @@ class NetdConv(nn.Module):
     def forward_cl(self, xc, **kw):
         if self.bn.training or self.bn.running_mean is None:
             y, tb = self.conv.forward_cl(xc, fold_bias=True)
-            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb, stats_ready=True, **kw)
+            return bn_apply(self.bn, y, self.lrelu.negative_slope, pre_bias=tb,
+                            stats_ready=ops.conv_fuses_stats(self.out_fi), **kw)
         return bn_apply(self.bn, self.conv.forward_cl(xc), self.lrelu.negative_slope, **kw)
 
     def forward(self, x):

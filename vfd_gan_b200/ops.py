@@ -78,6 +78,11 @@ def _is_cl(t):
 def _check_cl(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: vfd_gan_b200 has no CPU path; tensor is on {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        # the C-ABI launches on the current device's stream: refuse tensors of another device instead of
+        # launching over peer access without ordering
+        raise RuntimeError(f"{what}: tensor is on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(...)")
     if t.dtype != torch.bfloat16 or not _is_cl(t):
         raise RuntimeError(f"{what}: expected a channels-last bf16 [N,D,H,W,C] tensor (C % 8 == 0, dense voxel "
                            f"dims, 16-byte aligned), got {tuple(t.shape)} {t.dtype} strides {t.stride()}")
@@ -695,6 +700,16 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1).contiguous()
 
 
+MAX_FUSED_STATS_CHANNELS = 1024   # the conv epilogue keeps per-CTA sum / sum-of-squares for at most this many columns
+
+
+def conv_fuses_stats(cout, out_fp32=False):
+    """Whether ``ConvFn(..., fuse_stats=True)`` really accumulates the following BatchNorm's statistics in its
+    epilogue (bf16 output, at most MAX_FUSED_STATS_CHANNELS padded channels). Callers derive ``stats_ready`` from
+    this, so a wider layer takes the stand-alone ``vfd_bn_stats`` pass instead of reading an empty scratch."""
+    return (not out_fp32) and round_up(cout, 8) <= MAX_FUSED_STATS_CHANNELS
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
     training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
@@ -715,7 +730,7 @@ class ConvFn(torch.autograd.Function):
         flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
         # fuse_stats: the epilogue also accumulates the following BatchNorm's sum / sum-of-squares
         # into the shared self-clearing scratch (the caller passes stats_ready=True to BnActFn)
-        st = bn_scratch(x.device, cout_p) if (fuse_stats and not out_fp32 and cout_p <= 1024) else None
+        st = bn_scratch(x.device, cout_p) if (fuse_stats and conv_fuses_stats(cout, out_fp32)) else None
         ctx.stats_fused = st is not None
         _timed("conv_fwd", flops,
                lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT),

@@ -86,7 +86,8 @@ class SpatioTemporalConv(nn.Module):
         if bn_train:
             # bias folded into the BN (if any) and BN statistics accumulated by the conv epilogue
             y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, None, False, False, True)
-            a1, _ = bn_apply(self.bn, y1, 0.0, pre_bias=sb, stats_ready=True)
+            a1, _ = bn_apply(self.bn, y1, 0.0, pre_bias=sb,
+                             stats_ready=ops.conv_fuses_stats(self.spatial_conv.out_channels))
         else:
             y1 = ops.ConvFn.apply(xc, self.spatial_conv.weight, sb, False, False)
             a1, _ = bn_apply(self.bn, y1, 0.0)

@@ -41,8 +41,9 @@ class C2plus1d_Block(nn.Module):
         tr1 = self.bn1.training or self.bn1.running_mean is None
         tr2 = self.bn2.training or self.bn2.running_mean is None
         y = ops.ConvFn.apply(xc, self.spaceconv.weight, None, False, False, tr1)
-        a, _ = bn_apply(self.bn1, y, 0.0, stats_ready=tr1)
+        a, _ = bn_apply(self.bn1, y, 0.0, stats_ready=tr1 and ops.conv_fuses_stats(self.spaceconv.out_channels))
         y = ops.ConvFn.apply(a, self.pointwise.weight, None, False, False, tr2)
+        tr2 = tr2 and ops.conv_fuses_stats(self.pointwise.out_channels)
         if down_samp:
             _, x = bn_apply(self.bn2, y, 0.0, pool=(2, 2, 2), want_full=False, want_pool=True, stats_ready=tr2)
             inp = ops.ConvFn.apply(inp, self.conv.weight, self.conv.bias, False, False)

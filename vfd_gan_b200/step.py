@@ -154,6 +154,7 @@ class GanTrainStep:
         self.predict = None
         self.packer = ops.WeightPacker([netg, netd]) if fused else None
         self._graph, self._static_in, self._eager_steps = None, None, 0
+        self.adopt_inputs = False
         self._step_counter = torch.zeros((), dtype=torch.int64, device=dev) if fused else None
 
     GRAPH_WARMUP_STEPS = 2
@@ -186,10 +187,12 @@ class GanTrainStep:
         return self.losses
 
     def _capture(self, args):
-        """Record one step into a CUDA graph. The caller's tensors become the graph's static inputs (later
-        calls with other tensors are copied into them)."""
+        """Record one step into a CUDA graph. The graph's static inputs are private copies (every call copies its
+        tensors into them), unless the caller hands its buffers over with ``adopt_inputs`` (HostBatchStep does: it
+        owns them), in which case calls with those very tensors skip the copy."""
         self._static_in = [None if t is None else
-                           (t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float())
+                           (t if (self.adopt_inputs and t.is_contiguous() and t.dtype == torch.float32)
+                            else t.detach().clone().contiguous().float())
                            for t in args]
         self.netg.train()
         self.netd.train()
@@ -297,6 +300,7 @@ class HostBatchStep:
 
     def __init__(self, trainer, batch, nfr, isize, device):
         self.trainer = trainer
+        trainer.adopt_inputs = True     # self.dev below are the CUDA graph's static inputs (no extra copy per step)
         shp3, shp1 = (batch, 3, nfr, isize, isize), (batch, 1, nfr, isize, isize)
         mk = lambda: [torch.empty(shp3, device=device), torch.empty(shp1, device=device),
                       torch.empty(shp3, device=device), torch.empty(shp3, device=device)]
