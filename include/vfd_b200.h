@@ -98,9 +98,9 @@ VFD_API int vfd_pack_weight(const float* w, void* w_packed, int Cout, int Cin, i
  *   { const float* w; void* dst; int cout, cin, taps, rows, ck, mode; long long begin; }   (48 bytes)
  * where begin is the running sum of rows*taps*ck over the preceding jobs and total the overall sum. */
 VFD_API int vfd_pack_weights_batched(const void* jobs, int njobs, long long total, void* stream);
-/* wgrad accumulator [taps][ci_pad][co_pad] -> fp32 weight gradient [Cout][Cin][taps] */
+/* wgrad accumulator [taps][ci_pad][co_pad] -> fp32 weight gradient [Cout][Cin][taps] (accumulate != 0: added to gw) */
 VFD_API int vfd_unpack_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int co_pad,
-                             int ci_pad, void* stream);
+                             int ci_pad, int accumulate, void* stream);
 
 /* ---- BatchNorm3d + (Leaky)ReLU (+ AvgPool3d, + Dropout) ----------------------------------------
  * Replaces nn.BatchNorm3d + nn.ReLU (models/spatiotempconv.py:51-52,63), nn.BatchNorm3d +
@@ -132,7 +132,8 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
  * be NULL) computes dy (bf16), dgamma and dbeta (fp32 [Cvalid]). sums: zeroed double [2*C] scratch,
  * c1 / c2: fp32 [C] scratch. train: bit 0 = training-mode BatchNorm (batch statistics); bit 1 = g_pool is
  * [N][D/pd][C] and broadcast over the H and W axes (the gradient of the global spatial mean of TDisc,
- * models/mygannet.py:175,189-191), only for windows (1,1,1) and (2,1,1). */
+ * models/mygannet.py:175,189-191), only for windows (1,1,1) and (2,1,1); bit 2 = add to dgamma / dbeta instead of
+ * overwriting them (a BatchNorm applied twice per step, NetD on the real and on the generated clip). */
 VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, int W, int C, int Cvalid,
                            const float* mean, const float* invstd, const float* scale,
                            const float* shift, float slope, const void* g_full, long long gf_ld,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared - {"vfd_last_error", "vfd_abi_version"} == set(_lib.SIGNATURES)
     lib.vfd_abi_version.restype = ctypes.c_int
-    assert lib.vfd_abi_version() == 1
+    assert lib.vfd_abi_version() == 2
 
 
 def test_intermediate_channels_follow_the_reference_formula():

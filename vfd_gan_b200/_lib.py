@@ -25,7 +25,7 @@ SIGNATURES = {
     "vfd_unpack_ncdhw": [_p, _i, _p, _i, _i, _ll, _ll, _p],
     "vfd_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "vfd_pack_weights_batched": [_p, _i, _ll, _p],
-    "vfd_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vfd_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "vfd_bn_stats": [_p, _ll, _i, _ll, _p, _p],
     "vfd_bn_finalize": [_p, _i, _i, _ll, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p],
     "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p, _p],

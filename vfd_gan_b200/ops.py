@@ -166,10 +166,10 @@ def _pack_weight(w, wp, mode):
     _lib.call("vfd_pack_weight", w.data_ptr(), wp.data_ptr(), cout, cin, taps, rows, ck, mode, _stream())
 
 
-def _unpack_wgrad(acc, gw):
+def _unpack_wgrad(acc, gw, accumulate=False):
     taps, ci_pad, co_pad = acc.shape
     _lib.call("vfd_unpack_wgrad", acc.data_ptr(), gw.data_ptr(), gw.shape[0], gw.shape[1], taps, co_pad, ci_pad,
-              _stream())
+              1 if accumulate else 0, _stream())
 
 
 def _bn_prepare(y, sums, cvalid, pre_bias, gamma, beta, running_mean, running_var, momentum, eps, train, mean,
@@ -191,12 +191,12 @@ def _bn_act_fwd(y, scale, shift, slope, out_full, out_pool, pd, ph, pw, drop_p, 
 
 
 def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd, ph, pw, drop_p, seed, train,
-                sums, c1, c2, dgamma, dbeta, dy, seed_dev=None, pool_bcast=False):
+                sums, c1, c2, dgamma, dbeta, dy, seed_dev=None, pool_bcast=False, accumulate=False):
     N, D, H, W, C, ld = _check_cl(y, "bn_act_bwd input")
     _lib.call("vfd_bn_act_bwd", y.data_ptr(), ld, N, D, H, W, C, cvalid, mean.data_ptr(), invstd.data_ptr(),
               scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
               _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev),
-              (1 if train else 0) | (2 if pool_bcast else 0), sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
+              (1 if train else 0) | (2 if pool_bcast else 0) | (4 if accumulate else 0), sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
               dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
 
 
@@ -332,7 +332,7 @@ conv3d_wgrad_thin = _define(
 pack_ncdhw = _define("pack_ncdhw(Tensor src, Tensor(a!) dst, int C, bool replicate) -> ()", _pack_ncdhw)
 unpack_ncdhw = _define("unpack_ncdhw(Tensor src, Tensor(a!) dst) -> ()", _unpack_ncdhw)
 pack_weight = _define("pack_weight(Tensor w, Tensor(a!) wp, int mode) -> ()", _pack_weight)
-unpack_wgrad = _define("unpack_wgrad(Tensor acc, Tensor(a!) gw) -> ()", _unpack_wgrad)
+unpack_wgrad = _define("unpack_wgrad(Tensor acc, Tensor(a!) gw, bool accumulate=False) -> ()", _unpack_wgrad)
 bn_prepare = _define(
     "bn_prepare(Tensor y, Tensor(a!) sums, int cvalid, Tensor? pre_bias, Tensor gamma, Tensor beta, "
     "Tensor(b!)? running_mean, "
@@ -345,7 +345,7 @@ bn_act_bwd = _define(
     "bn_act_bwd(Tensor y, int cvalid, Tensor mean, Tensor invstd, Tensor scale, Tensor shift, float slope, "
     "Tensor? g_full, Tensor? g_pool, int pd, int ph, int pw, float drop_p, int seed, bool train, "
     "Tensor(a!) sums, Tensor(b!) c1, Tensor(c!) c2, Tensor(d!) dgamma, Tensor(e!) dbeta, Tensor(f!) dy, "
-    "Tensor? seed_dev=None, bool pool_bcast=False) -> ()", _bn_act_bwd)
+    "Tensor? seed_dev=None, bool pool_bcast=False, bool accumulate=False) -> ()", _bn_act_bwd)
 tap_gather = _define("tap_gather(Tensor src, int cs, Tensor(a!) dst, int kd, int kh, int kw, int sign) -> ()",
                      _tap_gather)
 channel_sum = _define("channel_sum(Tensor x, Tensor(a!) out) -> ()", _channel_sum)
@@ -551,6 +551,93 @@ ARENA = StepArena()
 _const_zeros = {}
 
 
+class StepContext:
+    """State of one fused train step (GanTrainStep / StcnnTrainStep), active between begin() and end().
+
+    Inside a step the autograd functions below do not hand parameter gradients back to autograd. They write them
+    straight into the parameter's persistent ``.grad`` buffer (a slice of the GradAllReducer's flat bucket): the first
+    write of a step overwrites, later ones (NetD runs twice per step) accumulate inside the kernel -- no
+    ``AccumulateGrad`` add kernels, no per-parameter temporaries -- and tell the ``sink`` when a parameter has
+    received its last contribution (uses are counted in forward), which is what triggers a bucket's all-reduce.
+
+    Weight gradients run on a side stream: a layer's dgrad -> BatchNorm-backward chain does not depend on its
+    wgrad, so the many small, latency-bound wgrad launches of the deep layers overlap that chain. Every tensor a
+    side-stream kernel reads is kept referenced in ``held`` until ``join()`` has made the main stream wait for the
+    side stream, so the caching allocator cannot hand its memory to a main-stream kernel early."""
+
+    def __init__(self):
+        self.active, self.sink, self.wstream = False, None, None
+        self.uses, self.touched, self.held = {}, set(), []
+        self.async_wgrad = os.environ.get("VFD_ASYNC_WGRAD", "1") != "0"
+        self.forked = False
+
+    def begin(self, device, sink=None):
+        self.active, self.sink = True, sink
+        self.uses, self.touched, self.held, self.forked = {}, set(), [], False
+        if self.async_wgrad and device.type == "cuda" and self.wstream is None:
+            self.wstream = torch.cuda.Stream(device=device)
+
+    def end(self):
+        self.join()
+        self.active, self.sink = False, None
+        self.uses, self.touched, self.held = {}, set(), []
+
+    # ---- gradient sinks
+    def count_use(self, param):
+        if self.active and param is not None and param.requires_grad:
+            k = param.data_ptr()
+            self.uses[k] = self.uses.get(k, 0) + 1
+
+    def direct(self, param):
+        """The persistent gradient buffer to write into, or None when gradients go through autograd."""
+        if not self.active or param is None or param.grad is None or param.data_ptr() not in self.uses:
+            return None
+        return param.grad
+
+    def first_touch(self, param):
+        k = param.data_ptr()
+        first = k not in self.touched
+        self.touched.add(k)
+        return first
+
+    def done(self, param):
+        """One backward use of ``param`` has deposited its gradient; tells the sink after the last one."""
+        k = param.data_ptr()
+        self.uses[k] -= 1
+        if self.uses[k] == 0 and self.sink is not None:
+            self.sink(param)
+
+    # ---- side stream
+    def side(self):
+        """Context manager: run the enclosed launches on the wgrad stream, after everything enqueued so far."""
+        if not (self.active and self.async_wgrad and self.wstream is not None):
+            return _NullCtx()
+        self.wstream.wait_stream(torch.cuda.current_stream())
+        self.forked = True
+        return torch.cuda.stream(self.wstream)
+
+    def hold(self, *tensors):
+        if self.forked:
+            self.held.extend(t for t in tensors if t is not None)
+
+    def join(self):
+        if self.forked and self.wstream is not None:
+            torch.cuda.current_stream().wait_stream(self.wstream)
+            self.forked = False
+        self.held = []
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+STEP = StepContext()
+
+
 def acc_zeros(shape, device):
     """fp32 zeros for a wgrad accumulator (arena slice inside a GanTrainStep, a fresh tensor otherwise)."""
     t = ARENA.take(shape, device)
@@ -668,7 +755,7 @@ _FUSED_FOLDS = {("x", 3, 1, 1, 2)}
 
 
 def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
-    """-> fp32 weight gradient [cout, cin, taps]"""
+    """-> fp32 weight gradient as a strided [cout, cin, taps] view of the accumulator"""
     taps = kd * kh * kw
     N, D, H, W = g.shape[:4]
     cs = cin if mode == "x" else cout
@@ -694,10 +781,10 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     if mode == "x":
         acc = acc_zeros((1, cols, round_up(cout, 32)), g.device)
         _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
-        return acc[0, :taps * cin, :cout].reshape(taps, cin, cout).permute(2, 1, 0).contiguous()
+        return acc[0, :taps * cin, :cout].reshape(taps, cin, cout).permute(2, 1, 0)
     acc = acc_zeros((1, round_up(cin, 8), round_up(taps * cout, 32)), g.device)
     _timed("conv_wgrad", flops, run, 2.0 * (g.numel() + x.numel()))
-    return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1).contiguous()
+    return acc[0, :cin, :taps * cout].reshape(cin, taps, cout).permute(2, 0, 1)
 
 
 MAX_FUSED_STATS_CHANNELS = 1024   # the conv epilogue keeps per-CTA sum / sum-of-squares for at most this many columns
@@ -710,9 +797,48 @@ def conv_fuses_stats(cout, out_fp32=False):
     return (not out_fp32) and round_up(cout, 8) <= MAX_FUSED_STATS_CHANNELS
 
 
+def _put(dst3, view3, accumulate):
+    if accumulate:
+        dst3.add_(view3)
+    else:
+        dst3.copy_(view3)
+
+
+def conv_weight_grad_into(g, x, weight, dst, accumulate):
+    """Weight gradient of the stride-1 "same" conv (dy = ``g``, input ``x``, both channels-last bf16) written into
+    ``dst`` (fp32, ``weight``'s shape): overwritten, or added to when ``accumulate``."""
+    cout, cin, kd, kh, kw = _wshape(weight)
+    N, D, H, W, _, _ = _check_cl(g, "conv grad")
+    taps = kd * kh * kw
+    flops = 2.0 * N * D * H * W * cin * cout * taps
+    nbytes = 2.0 * (g.numel() + x.numel())
+    dst3 = dst.view(cout, cin, taps)
+    fold = None if CONV_IMPL_DIRECT else wgrad_fold_mode(cin, cout, kd, kh, kw)
+    if fold is not None:
+        _put(dst3, _folded_wgrad(fold, g, x, cin, cout, kd, kh, kw, flops), accumulate)
+        return
+    layout = 0 if CONV_IMPL_DIRECT else wgrad_layout(cout, cin, kd, kh, kw, H, W)
+    if taps == 1 and cout <= 32 and cin <= 32 and THIN_WGRAD and not CONV_IMPL_DIRECT:
+        acc = acc_zeros((1, round_up(cin, 8), round_up(cout, 32)), g.device)
+        _timed("conv_wgrad", flops, lambda: conv3d_wgrad_thin(g, cout, x, cin, acc), nbytes)
+        unpack_wgrad(acc, dst, accumulate)
+    elif layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
+        acc = acc_zeros((taps, round_up(cout, 8), round_up(cin, 32)), g.device)
+        _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1), nbytes)
+        _put(dst3, acc[:, :cout, :cin].permute(1, 2, 0), accumulate)
+    else:
+        acc = acc_zeros((taps, round_up(cin, 8), round_up(cout, 32)), g.device)
+        _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT), nbytes)
+        unpack_wgrad(acc, dst, accumulate)
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
-    training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean)."""
+    training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean).
+
+    Inside a fused train step (``STEP.active``) the parameter gradients are not returned to autograd: they are
+    written into the parameters' persistent ``.grad`` buffers (see StepContext), the weight gradient on the side
+    stream."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, out_fp32, bias_grad_exact_zero, fuse_stats=False):
@@ -737,8 +863,10 @@ class ConvFn(torch.autograd.Function):
                2.0 * x.numel() + out.numel() * out.element_size())
         ctx.save_for_backward(x, weight)
         ctx.w_dgrad, ctx.kc_d = pk.dgrad, pk.kc_d     # the master cannot change between forward and backward
-        ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.bias_zero = bias_grad_exact_zero
+        STEP.count_use(weight)
+        STEP.count_use(bias)
         return out
 
     @staticmethod
@@ -749,44 +877,41 @@ class ConvFn(torch.autograd.Function):
         N, D, H, W, _, _ = _check_cl(g, "conv grad")
         gx = gw = gb = None
         w_dgrad, kc_d = ctx.w_dgrad, ctx.kc_d
+        # the weight gradient first: inside a fused step it goes to the side stream, forked here -- after dy is
+        # ready, before this layer's dgrad -- so that it overlaps the dgrad -> BatchNorm-backward chain
+        if ctx.needs_input_grad[1]:
+            dst = STEP.direct(weight)
+            if dst is not None:
+                with STEP.side():
+                    conv_weight_grad_into(g, x, weight, dst, not STEP.first_touch(weight))
+                STEP.hold(g, x)
+                STEP.done(weight)
+            else:
+                gw = torch.empty_like(weight, dtype=torch.float32)
+                conv_weight_grad_into(g, x, weight, gw, False)
         if ctx.needs_input_grad[0]:
             gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
             flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
             _timed("conv_dgrad", flops,
                    lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
                                       CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
-        if ctx.needs_input_grad[1]:
-            taps = kd * kh * kw
-            flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
-            fold = None if CONV_IMPL_DIRECT else wgrad_fold_mode(cin, cout, kd, kh, kw)
-            if fold is None:
-                layout = 0 if CONV_IMPL_DIRECT else wgrad_layout(cout, cin, kd, kh, kw, H, W)
-                if taps == 1 and cout <= 32 and cin <= 32 and THIN_WGRAD and not CONV_IMPL_DIRECT:
-                    acc = acc_zeros((1, round_up(cin, 8), round_up(cout, 32)), g.device)
-                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad_thin(g, cout, x, cin, acc),
-                           2.0 * (g.numel() + x.numel()))
-                    gw = torch.empty_like(weight, dtype=torch.float32)
-                    unpack_wgrad(acc, gw)
-                elif layout == 1:   # swapped GEMM roles: acc[tap][co][ci]
-                    acc = acc_zeros((taps, round_up(cout, 8), round_up(cin, 32)), g.device)
-                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, False, 1),
-                           2.0 * (g.numel() + x.numel()))
-                    gw = acc[:, :cout, :cin].permute(1, 2, 0).contiguous().reshape(weight.shape)
-                else:
-                    acc = acc_zeros((taps, round_up(cin, 8), round_up(cout, 32)), g.device)
-                    _timed("conv_wgrad", flops, lambda: conv3d_wgrad(g, cout, x, cin, acc, kd, kh, kw, CONV_IMPL_DIRECT),
-                           2.0 * (g.numel() + x.numel()))
-                    gw = torch.empty_like(weight, dtype=torch.float32)
-                    unpack_wgrad(acc, gw)
-            else:
-                gw = _folded_wgrad(fold, g, x, cin, cout, kd, kh, kw, flops).reshape(weight.shape)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        bias = ctx.bias_param
+        if bias is not None and ctx.needs_input_grad[2]:
+            dst = STEP.direct(bias)
             if ctx.bias_zero:
-                gb = zero_grad(cout, g.device)
+                if dst is None:
+                    gb = zero_grad(cout, g.device)
+                else:                               # the buffer was zeroed at the start of the step
+                    STEP.first_touch(bias)
+                    STEP.done(bias)
             else:
-                s = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
-                channel_sum(g, s)
-                gb = s[:cout].clone()
+                sums = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
+                channel_sum(g, sums)
+                if dst is None:
+                    gb = sums[:cout].clone()
+                else:
+                    _put(dst, sums[:cout], not STEP.first_touch(bias))
+                    STEP.done(bias)
         return gx, gw, gb, None, None, None
 
 
@@ -820,7 +945,9 @@ class BnActFn(torch.autograd.Function):
         ctx.save_for_backward(y, stats)
         ctx.cfg = (cvalid, slope, pool, drop_p, seed, train)
         ctx.seed_dev = seed_dev
-        ctx.has_pre_bias = pre_bias is not None
+        ctx.params = (gamma, beta, pre_bias)
+        for prm in ctx.params:
+            STEP.count_use(prm)
         return full, pooled
 
     @staticmethod
@@ -840,15 +967,34 @@ class BnActFn(torch.autograd.Function):
         g_full, g_pool = as_cl_grad(g_full), as_cl_grad(g_pool)
         dy = cl_empty(N, D, H, W, C, dev)
         tmp = torch.empty(2, C, dtype=torch.float32, device=dev)
-        dgamma = torch.empty(cvalid, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(cvalid, dtype=torch.float32, device=dev)
+        gamma, beta, pre_bias = ctx.params
+        # inside a fused train step dgamma / dbeta land directly in the parameters' .grad buffers
+        dgamma, dbeta = STEP.direct(gamma), STEP.direct(beta)
+        direct = dgamma is not None and dbeta is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
+        accumulate = False
+        if direct:
+            accumulate = not STEP.first_touch(gamma)
+            STEP.first_touch(beta)
+        else:
+            dgamma = torch.empty(cvalid, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(cvalid, dtype=torch.float32, device=dev)
         nbytes = 2.0 * y.numel() * 3 + 2.0 * 2 * sum(g.numel() for g in (g_full, g_pool) if g is not None)
         _timed("bn_act_bwd", nbytes,
                lambda: bn_act_bwd(y, cvalid, stats[0], stats[1], stats[2], stats[3], slope, g_full, g_pool, pd, ph, pw,
                                   drop_p, seed, train, bn_scratch(dev, C), tmp[0], tmp[1], dgamma, dbeta, dy,
-                                  ctx.seed_dev, bcast))
+                                  ctx.seed_dev, bcast, accumulate))
+        if direct:
+            STEP.done(gamma)
+            STEP.done(beta)
+            dgamma = dbeta = None
         # a conv bias folded into training-mode BN has an identically zero gradient
-        gpb = zero_grad(cvalid, dev) if ctx.has_pre_bias else None
+        gpb = None
+        if pre_bias is not None and ctx.needs_input_grad[3]:
+            if STEP.direct(pre_bias) is not None:
+                STEP.first_touch(pre_bias)
+                STEP.done(pre_bias)
+            else:
+                gpb = zero_grad(cvalid, dev)
         return (dy, dgamma, dbeta, gpb) + (None,) * 14
 
 

@@ -45,20 +45,22 @@ LOSS_KEYS = ("g/err_g", "g/err_g_adv", "g/err_g_adv_s", "g/err_g_adv_t", "g/err_
 
 
 class GradAllReducer:
-    """Bucketed, backward-overlapped gradient averaging over the default process group.
+    """Persistent flat gradient buckets + bucketed, backward-overlapped averaging over the default process group.
 
-    Gradients live as views into flat fp32 bucket buffers. A bucket is all-reduced (SUM, then scaled
-    by 1/world) on ``comm_stream`` as soon as the last of its parameters has accumulated its
-    gradient; ``finish()`` makes the compute stream wait for the collectives."""
+    Every parameter's ``.grad`` is a view into a flat fp32 bucket buffer for the life of the trainer (static
+    addresses: what a captured CUDA graph and the fused Adam need). Inside a fused step the kernels write the
+    gradients straight into those views (``ops.StepContext``) and call ``ready(p)`` after a parameter's last
+    contribution; parameters whose gradient still comes from autograd (the two Linear heads) reach ``ready`` through a
+    post-accumulate-grad hook. With more than one rank a bucket is all-reduced (average) on ``comm_stream`` as soon
+    as its last parameter is ready, overlapping the rest of backward; ``finish()`` joins the side stream. With one
+    rank the same code runs without the collectives."""
 
     def __init__(self, params, bucket_mb=16.0, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.buckets, self.flat, self.pending, self.bucket_of = [], [], [], {}
-        self.comm_stream, self.handles, self.active = None, [], False
-        if self.world == 1:
-            return   # single rank: gradients stay ordinary per-parameter tensors (no flat copies, no adds)
+        self.comm_stream, self.active = None, False
         cap = int(bucket_mb * 1024 * 1024 / 4)
         cur, cur_n = [], 0
         for p in reversed(self.params):  # backward produces gradients roughly in reverse order
@@ -79,25 +81,32 @@ class GradAllReducer:
                 self.bucket_of[p] = bi
             self.flat.append(flat)
             self.pending.append(0)
-        self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        cuda = bool(self.params) and self.params[0].is_cuda
+        if self.world > 1 and cuda:
+            self.comm_stream = torch.cuda.Stream(device=self.params[0].device)
+        self.avg = dist.ReduceOp.AVG if (self.world > 1 and cuda) else None   # NCCL averages in the collective
+        self.by_ptr = {p.data_ptr(): p for p in self.params}
         for p in self.params:
-            p.register_post_accumulate_grad_hook(self._hook)
+            p.register_post_accumulate_grad_hook(self.ready)
 
     def zero(self):
-        if self.world == 1:
-            for p in self.params:
-                p.grad = None          # autograd then hands the incoming gradient over without an add kernel
-            return
-        for f in self.flat:
-            f.zero_()
+        """Clears the buckets (one multi-tensor launch): gradients that autograd accumulates (``+=``) and the
+        identically-zero conv-bias gradients rely on it; kernel-written gradients overwrite their slice anyway."""
+        for p in self.params:       # a caller may have dropped the views (optimizer.zero_grad(set_to_none=True))
+            if p.grad is None:
+                bi = self.bucket_of[p]
+                off = sum(q.numel() for q in self.buckets[bi][:self.buckets[bi].index(p)])
+                p.grad = self.flat[bi][off:off + p.numel()].view_as(p)
+        if self.flat:
+            torch._foreach_zero_(self.flat)
 
     def begin(self):
-        """Arm the hooks for one backward pass."""
+        """Arm the ready-counting for one backward pass."""
         self.pending = [len(b) for b in self.buckets]
-        self.handles = []
         self.active = True
 
-    def _hook(self, p):
+    def ready(self, p):
+        """Parameter ``p`` has received its whole gradient for this backward pass."""
         if not self.active:
             return
         bi = self.bucket_of[p]
@@ -106,18 +115,21 @@ class GradAllReducer:
             self._launch(bi)
 
     def _launch(self, bi):
+        if self.world == 1:
+            return
         flat = self.flat[bi]
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            if ops.STEP.forked:                       # weight gradients are produced on the side stream
+                self.comm_stream.wait_stream(ops.STEP.wstream)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-                flat.mul_(1.0 / self.world)
-        else:  # CPU / gloo (tests)
+                dist.all_reduce(flat, op=self.avg, group=self.group)
+        else:  # CPU / gloo (tests): no AVG in gloo
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.mul_(1.0 / self.world)
 
     def finish(self):
-        """Reduce whatever the hooks did not cover (unused parameters) and join the side stream."""
+        """Reduce whatever did not report ready (unused parameters) and join the side stream."""
         if self.world > 1:
             for bi, left in enumerate(self.pending):
                 if left > 0:
@@ -150,6 +162,7 @@ class GanTrainStep:
                                             capturable=self.use_graph)
         self.optimizer_d = torch.optim.Adam(netd.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused,
                                             capturable=self.use_graph)
+        self._g_ptrs = set(self.red_g.by_ptr)
         self.losses = torch.zeros(len(LOSS_KEYS), dtype=torch.float32, device=dev)
         self.predict = None
         self.packer = ops.WeightPacker([netg, netd]) if fused else None
@@ -215,9 +228,11 @@ class GanTrainStep:
             self.packer.pack_all()          # every conv weight's bf16 GEMM operands, one launch
         spatiotempconv.DEFER_BN_COUNTERS = counters = []
         ops.ARENA.begin(inp.device)       # one zero fill for all weight-gradient accumulators of the step
+        ops.STEP.begin(inp.device, self._grad_ready)
         try:
             return self._step_body(inp, gt, gt_flow, pre_flow, dropout_seeds, seed_dev)
         finally:
+            ops.STEP.end()
             ops.ARENA.end()
             spatiotempconv.DEFER_BN_COUNTERS = None
             if counters:   # num_batches_tracked of every BatchNorm call of the step (NetD runs twice)
@@ -227,6 +242,10 @@ class GanTrainStep:
                     ent[1] += 1
                 for n in sorted({e[1] for e in seen.values()}):
                     torch._foreach_add_([e[0] for e in seen.values() if e[1] == n], n)
+
+    def _grad_ready(self, p):
+        red = self.red_g if p.data_ptr() in self._g_ptrs else self.red_d
+        red.ready(red.by_ptr[p.data_ptr()])
 
     def _step_body(self, inp, gt, gt_flow, pre_flow, dropout_seeds, seed_dev):
         netg, netd = self.netg, self.netd
@@ -256,6 +275,7 @@ class GanTrainStep:
         self.red_g.zero()
         self.red_g.begin()
         (err_g_con * self.w_con).backward()
+        ops.STEP.join()                 # the weight gradients of the side stream
         self.red_g.finish()
         self.optimizer_g.step()
 
@@ -268,6 +288,7 @@ class GanTrainStep:
         self.red_d.zero()
         self.red_d.begin()
         err_d.backward()
+        ops.STEP.join()
         self.red_d.finish()
         self.optimizer_d.step()
 
