@@ -1088,10 +1088,11 @@ class MeanDimsFn(torch.autograd.Function):
 
 class IdentityPoolFn(torch.autograd.Function):
     """AvgPool3d (and / or Dropout) with no BatchNorm in front (the shortcut branch of C2plus1d_Block,
-    models/mystcnn.py:37-44): the fused BN+act kernel run with scale 1, shift 0 and slope 1."""
+    models/mystcnn.py:37-44): the fused BN+act kernel run with scale 1, shift 0 and slope 1. ``seed_dev``: optional
+    device counter added to the dropout seed inside the kernels (fresh masks under CUDA-graph replay)."""
 
     @staticmethod
-    def forward(ctx, x, pool, drop_p, seed):
+    def forward(ctx, x, pool, drop_p, seed, seed_dev=None):
         N, D, H, W, C, _ = _check_cl(x, "pool input")
         pd, ph, pw = pool
         dev = x.device
@@ -1099,9 +1100,11 @@ class IdentityPoolFn(torch.autograd.Function):
         k[1:3] = 1.0
         pooled = pd * ph * pw > 1
         out = cl_empty(N, D // pd, H // ph, W // pw, C, dev)
-        bn_act_fwd(x, k[2], k[3], 1.0, None if pooled else out, out if pooled else None, pd, ph, pw, drop_p, seed)
+        bn_act_fwd(x, k[2], k[3], 1.0, None if pooled else out, out if pooled else None, pd, ph, pw, drop_p, seed,
+                   seed_dev)
         ctx.save_for_backward(x, k)
         ctx.cfg = (pool, drop_p, seed, pooled)
+        ctx.seed_dev = seed_dev
         return out
 
     @staticmethod
@@ -1113,8 +1116,8 @@ class IdentityPoolFn(torch.autograd.Function):
         dx = cl_empty(N, D, H, W, C, x.device)
         tmp = torch.empty(4, C, dtype=torch.float32, device=x.device)
         bn_act_bwd(x, C, k[0], k[1], k[2], k[3], 1.0, None if pooled else g, g if pooled else None, pd, ph, pw,
-                   drop_p, seed, False, bn_scratch(x.device, C), tmp[0], tmp[1], tmp[2], tmp[3], dx)
-        return dx, None, None, None
+                   drop_p, seed, False, bn_scratch(x.device, C), tmp[0], tmp[1], tmp[2], tmp[3], dx, ctx.seed_dev)
+        return dx, None, None, None, None
 
 
 class UpsampleFn(torch.autograd.Function):

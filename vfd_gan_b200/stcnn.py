@@ -35,7 +35,7 @@ class C2plus1d_Block(nn.Module):
         self.out_ch = out_ch
         self.last_dropout_seed = None
 
-    def forward_cl(self, xc, down_samp=False, dropout_seed=None):
+    def forward_cl(self, xc, down_samp=False, dropout_seed=None, seed_dev=None):
         """channels-last bf16 -> channels-last bf16 (models/mystcnn.py:26-50)."""
         inp = xc
         tr1 = self.bn1.training or self.bn1.running_mean is None
@@ -55,7 +55,7 @@ class C2plus1d_Block(nn.Module):
             if p > 0.0:
                 seed = int(dropout_seed) if dropout_seed is not None else _draw_seed()
                 self.last_dropout_seed = seed
-                inp = ops.IdentityPoolFn.apply(inp, (1, 1, 1), float(p), seed)
+                inp = ops.IdentityPoolFn.apply(inp, (1, 1, 1), float(p), seed, seed_dev)
             inp = ops.UpsampleFn.apply(inp)
             inp = ops.ConvFn.apply(inp, self.conv.weight, self.conv.bias, False, False)
         x = torch.cat([x, inp], dim=-1)
@@ -81,8 +81,9 @@ class AutoEncoder(nn.Module):
         self.conv_last = nn.Conv3d(64, 1, 3, stride=1, padding=1, bias=False)
         self.sigmoid = nn.Sigmoid()
 
-    def forward_cl(self, xc, dropout_seeds=None):
-        """channels-last bf16 clip -> fp32 conv_last logits (models/mystcnn.py:69-88)."""
+    def forward_cl(self, xc, dropout_seeds=None, seed_dev=None):
+        """channels-last bf16 clip -> fp32 conv_last logits (models/mystcnn.py:69-88). ``seed_dev``: device counter
+        added to every dropout seed inside the kernels (a CUDA-graph-captured step draws fresh masks per replay)."""
         N, D, H, W, _ = xc.shape
         if D % 16 or H % 16 or W % 16:
             raise RuntimeError(f"AutoEncoder needs nfr and isize divisible by 16, got D={D} H={H} W={W}")
@@ -91,10 +92,10 @@ class AutoEncoder(nn.Module):
         d2 = self.down_sep2.forward_cl(d1, True)
         d3 = self.down_sep3.forward_cl(d2, True)
         d4 = self.down_sep4.forward_cl(d3, True)
-        u1 = self.up_sep1.forward_cl(d4, False, sd[0])
-        u2 = self.up_sep2.forward_cl(torch.cat([u1, d3], dim=-1), False, sd[1])
-        u3 = self.up_sep3.forward_cl(torch.cat([u2, d2], dim=-1), False, sd[2])
-        u4 = self.up_sep4.forward_cl(torch.cat([u3, d1], dim=-1), False, sd[3])
+        u1 = self.up_sep1.forward_cl(d4, False, sd[0], seed_dev)
+        u2 = self.up_sep2.forward_cl(torch.cat([u1, d3], dim=-1), False, sd[1], seed_dev)
+        u3 = self.up_sep3.forward_cl(torch.cat([u2, d2], dim=-1), False, sd[2], seed_dev)
+        u4 = self.up_sep4.forward_cl(torch.cat([u3, d1], dim=-1), False, sd[3], seed_dev)
         return ops.ConvFn.apply(u4, self.conv_last.weight, None, True, False)
 
     def forward(self, x):
@@ -103,21 +104,81 @@ class AutoEncoder(nn.Module):
 
 class StcnnTrainStep:
     """``opt.zero_grad(); predict = model(input); err = BCELoss(predict, gt); err.backward(); opt.step()``
-    (lib/train_stcnn.py:104-109) with the fused BCE reduction and Adam(lr, (beta1, 0.999)) of :91."""
+    (lib/train_stcnn.py:104-109) with the fused BCE reduction and Adam(lr, (beta1, 0.999)) of :91.
 
-    def __init__(self, model, lr=2e-5, beta1=0.5):
+    Like ``GanTrainStep``: gradients are written by the kernels into persistent flat buckets, averaged over the ranks
+    of the default process group (one process per GPU, batch sharded on dim 0, per-rank BatchNorm statistics) with
+    NCCL overlapped with backward, and after two eager steps the whole step is captured in a CUDA graph and
+    replayed (``graph=False`` or ``VFD_CUDA_GRAPH=0`` keeps it eager)."""
+
+    GRAPH_WARMUP_STEPS = 2
+
+    def __init__(self, model, lr=2e-5, beta1=0.5, bucket_mb=16.0, graph=None):
+        import os
+        from .step import GradAllReducer
         self.model = model
         dev = next(model.parameters()).device
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=(beta1, 0.999), fused=dev.type == "cuda")
+        fused = dev.type == "cuda"
+        if graph is None:
+            graph = fused and os.environ.get("VFD_CUDA_GRAPH", "1") != "0"
+        self.use_graph = bool(graph) and fused
+        self.red = GradAllReducer(list(model.parameters()), bucket_mb)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=(beta1, 0.999), fused=fused,
+                                    capturable=self.use_graph)
+        self.packer = ops.WeightPacker([model]) if fused else None
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.predict = None
+        self._graph, self._static_in, self._eager_steps = None, None, 0
+        self._step_counter = torch.zeros((), dtype=torch.int64, device=dev) if fused else None
 
     def step(self, inp, gt, dropout_seeds=None):
+        """inp (B,3,D,H,W), gt (B,1,D,H,W) on the device -> the BCE loss (device scalar, no synchronisation)."""
+        if not self.use_graph or dropout_seeds is not None:
+            return self._step_impl(inp, gt, dropout_seeds)
+        if self._graph is None:
+            if self._eager_steps < self.GRAPH_WARMUP_STEPS:
+                self._eager_steps += 1
+                return self._step_impl(inp, gt, None, self._step_counter)
+            self._static_in = [inp.detach().clone().contiguous().float(), gt.detach().clone().contiguous().float()]
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step_impl(*self._static_in, None, self._step_counter)
+            self._graph = graph
+        elif inp.shape != self._static_in[0].shape or gt.shape != self._static_in[1].shape:
+            return self._step_impl(inp, gt, None, self._step_counter)
+        self._static_in[0].copy_(inp, non_blocking=True)
+        self._static_in[1].copy_(gt, non_blocking=True)
+        self._graph.replay()
+        ops.invalidate_packed_weights()
+        return self.loss
+
+    def _step_impl(self, inp, gt, dropout_seeds=None, seed_dev=None):
+        from . import spatiotempconv
         self.model.train()
-        self.opt.zero_grad(set_to_none=True)
-        logits = self.model.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds)
-        predict = ops.SigmoidHeadFn.apply(logits)
-        err = ops.BceLossFn.apply(predict, gt)
-        err.backward()
-        self.opt.step()
-        self.predict = predict.detach()
-        return err.detach()
+        if seed_dev is not None:
+            seed_dev += 1
+        if self.packer is not None:
+            self.packer.pack_all()
+        spatiotempconv.DEFER_BN_COUNTERS = counters = []
+        ops.ARENA.begin(inp.device)
+        ops.STEP.begin(inp.device, self.red.ready_tensor)
+        try:
+            self.red.zero()
+            self.red.begin()
+            logits = self.model.forward_cl(ops.PackFn.apply(inp, 0), dropout_seeds, seed_dev)
+            predict = ops.SigmoidHeadFn.apply(logits)
+            err = ops.BceLossFn.apply(predict, gt)
+            err.backward()
+            ops.STEP.join()
+            self.red.finish()
+            self.opt.step()
+            self.predict = predict.detach()
+            self.loss.copy_(err.detach())
+        finally:
+            ops.STEP.end()
+            ops.ARENA.end()
+            spatiotempconv.DEFER_BN_COUNTERS = None
+            if counters:
+                torch._foreach_add_(list({c.data_ptr(): c for c in counters}.values()), 1)
+        return self.loss

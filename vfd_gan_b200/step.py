@@ -114,6 +114,10 @@ class GradAllReducer:
         if self.pending[bi] == 0:
             self._launch(bi)
 
+    def ready_tensor(self, t):
+        """``ready`` for a tensor that aliases one of the parameters (what the autograd functions hold)."""
+        self.ready(self.by_ptr[t.data_ptr()])
+
     def _launch(self, bi):
         if self.world == 1:
             return
