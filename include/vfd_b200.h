@@ -27,10 +27,6 @@
 
 VFD_API const char* vfd_last_error(void);
 VFD_API int vfd_abi_version(void);
-/* Diagnostics only (stage-isolation timing of the conv pipelines, tools/gpu_stage_probe.py): bit 0 skips
- * the TMA loads, bit 1 the tcgen05.mma issue, bit 2 the epilogue arithmetic/stores. Results are garbage
- * while any bit is set; 0 (the default) is the product path. */
-VFD_API int vfd_set_debug(int flags);
 
 /* ---- conv3d, stride 1, "same" zero padding, kernel extents in {1,3} ------------------------------
  * Replaces nn.Conv3d forward at models/spatiotempconv.py:49-50,59-60,63-64, conv_last at
@@ -72,15 +68,6 @@ VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, i
 VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
                                   int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
                                   int H, int W, int kd, int kh, int kw, void* stream);
-
-/* CUDA-core versions on the same operands; used by the tests to cross-check the tcgen05 kernels. */
-VFD_API int vfd_conv3d_fwd_direct(const void* x, long long x_ld, int cin, const void* w_packed,
-                                  int w_rows, int cin_k, const float* bias, void* out,
-                                  long long out_ld, int out_cols, int out_fp32, int N, int D, int H,
-                                  int W, int kd, int kh, int kw, void* stream);
-VFD_API int vfd_conv3d_wgrad_direct(const void* dy, long long dy_ld, int cout, const void* x,
-                                    long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int N,
-                                    int D, int H, int W, int kd, int kh, int kw, void* stream);
 
 /* ---- layout / weight packing -------------------------------------------------------------------
  * fp32 NCDHW [N][Csrc][S] -> bf16 channels-last [N][S][ld] (Cp channels, zero beyond C).

@@ -27,6 +27,14 @@ def test_library_exports_every_declared_symbol():
     assert declared - {"vfd_last_error", "vfd_abi_version"} == set(_lib.SIGNATURES)
     lib.vfd_abi_version.restype = ctypes.c_int
     assert lib.vfd_abi_version() == 2
+    # test-only kernels and debug switches live in the debug library, not in the product ABI
+    for name in _lib.DEBUG_SIGNATURES:
+        assert not hasattr(lib, name), name
+    dbg = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
+    dhdr = open(os.path.join(ROOT, "include", "vfd_b200_debug.h")).read()
+    assert set(re.findall(r"VFD_API\s+[\w\s\*]+?\b(vfd_\w+)\s*\(", dhdr)) == set(_lib.DEBUG_SIGNATURES)
+    for name in list(_lib.DEBUG_SIGNATURES) + list(_lib.SIGNATURES):
+        assert hasattr(dbg, name), name
 
 
 def test_intermediate_channels_follow_the_reference_formula():

@@ -21,7 +21,7 @@ FLAGS = [int(f) for f in os.environ.get("PROBE_FLAGS", "0,1,2,3,4,5,6,7").split(
 names = sys.argv[1:] or list(LAYERS)
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-L = _lib.lib()
+L = _lib.debug_lib()   # the stage switches exist only in libvfd_b200_debug.so
 L.vfd_set_debug.argtypes = [_lib._i]
 
 

@@ -19,8 +19,6 @@ SIGNATURES = {
     "vfd_conv3d_wgrad": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_layout": [_i, _i, _i, _i, _i, _i, _i],
     "vfd_conv3d_wgrad_thin": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "vfd_conv3d_fwd_direct": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "vfd_conv3d_wgrad_direct": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_pack_ncdhw": [_p, _p, _i, _i, _ll, _i, _ll, _i, _i, _p],
     "vfd_unpack_ncdhw": [_p, _i, _p, _i, _i, _ll, _ll, _p],
     "vfd_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -52,8 +50,15 @@ SIGNATURES = {
     "vfd_roc_auc": [_p, _p, _i, _p, _p],
     "vfd_video_to_flow": [_p, _i, _i, _i, _i, _p, _p, _p, _ll, _p],
     "vfd_video_to_flow_workspace": [_i, _i, _i, _i],
+}
+# test / tool-only entry points of libvfd_b200_debug.so (declared in csrc/conv_direct.cu and csrc/conv_tc.cu)
+DEBUG_SIGNATURES = {
+    "vfd_conv3d_fwd_direct": [_p, _ll, _i, _p, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_wgrad_direct": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_set_debug": [_i],
 }
+DEBUG_LIB_PATH = os.path.join(_HERE, "libvfd_b200_debug.so")
+_debug_lib = None
 
 _lib = None
 LAUNCHES = 0         # C-ABI compute calls issued by this process
@@ -89,6 +94,33 @@ def lib():
         L.vfd_video_to_flow_workspace.restype = ctypes.c_longlong
         _lib = L
     return _lib
+
+
+def debug_lib():
+    """libvfd_b200_debug.so: the product sources built with -DVFD_DEBUG plus the CUDA-core cross-check convs. Only
+    tests/ and tools/ reach it (``ops.CONV_IMPL_DIRECT``, tools/gpu_stage_probe.py)."""
+    global _debug_lib
+    if _debug_lib is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = ctypes.CDLL(DEBUG_LIB_PATH)
+        L.vfd_last_error.restype = ctypes.c_char_p
+        L.vfd_last_error.argtypes = []
+        for table in (SIGNATURES, DEBUG_SIGNATURES):
+            for name, args in table.items():
+                fn = getattr(L, name)
+                fn.argtypes = args
+                fn.restype = ctypes.c_int
+        _debug_lib = L
+    return _debug_lib
+
+
+def call_debug(name, *args):
+    """Invoke an entry point of the debug library (cross-check kernels)."""
+    L = debug_lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.vfd_last_error().decode()}")
 
 
 def call(name, *args):

@@ -17,6 +17,17 @@
 #include "ptx.cuh"
 #include "vfd_internal.h"
 
+// Stage-isolation switches of tools/gpu_stage_probe.py (skip the TMA loads / the MMA issue / the epilogue ...).
+// They exist only in the debug library (libvfd_b200_debug.so, -DVFD_DEBUG): in the product build the macros are the
+// constant 0 and the compiler removes every branch they guard; vfd_set_debug is not exported.
+#ifdef VFD_DEBUG
+#define VFD_DBG(p, bit) ((p).dbg & (bit))
+#define VFD_GDBG(bit) (g_dbg & (bit))
+#else
+#define VFD_DBG(p, bit) (0)
+#define VFD_GDBG(bit) (0)
+#endif
+
 namespace vfd {
 
 constexpr int kTileM = 128;
@@ -429,7 +440,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n = t / p.dgroups;
         for (int cb = 0; cb < p.cblocks; ++cb) {
           mbar_wait(&a_empty[sa], pha ^ 1);
-          if (p.dbg & 1) {
+          if VFD_DBG(p, 1) {
             mbar_arrive(&a_full[sa]);
           } else {
             mbar_expect_tx(&a_full[sa], p.a_box_bytes);
@@ -455,7 +466,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t alo0 = desc_lo(da0), ahi = desc_hi(da0), blo0 = desc_lo(db0), bhi = desc_hi(db0);
     const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_tile16 = p.b_tile_bytes >> 4;
     const uint32_t tap16 = static_cast<uint32_t>(p.cblocks) * b_tile16;  // next tap's weight tile (same channel block)
-    const bool issue = leader && !(p.dbg & 2);
+    const bool issue = leader && !VFD_DBG(p, 2);
     int sa = 0, as = 0;
     uint32_t pha = 0, aph = 0;
     mbar_wait(&b_full, 0);
@@ -544,13 +555,13 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool hw_ok = (w0 + (lane & 7) < p.W) && (h0 + 4 * q + (lane >> 3) < p.H);
         for (int g = (p.G > 1 ? e : 0); g < p.G; g += 2) {
           const int d = d0 + g;
-          if (d >= p.D || (p.dbg & 4)) continue;
+          if (d >= p.D || VFD_DBG(p, 4)) continue;
           const unsigned vmask = __ballot_sync(0xffffffffu, hw_ok);
           const uint32_t tacc = tmem_base + as * stage_cols + g * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
           for (int ch = 0; ch < p.nchunks; ++ch) {
             float v[32];
-            if (p.dbg & 32) {
+            if VFD_DBG(p, 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0.f;
             } else if (ch * 32 + 32 <= p.block_n) {
@@ -566,7 +577,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (ch * 32 + i < p.n_rows) v[i] += __ldg(p.bias + ch * 32 + i);
             }
             // the staging buffer may still be the source of an earlier TMA store
-            if (lane == 0 && !(p.dbg & 8)) {
+            if (lane == 0 && !VFD_DBG(p, 8)) {
               if (p.stage_bufs == 2) bulk_wait_group_read<1>();
               else bulk_wait_group_read<0>();
             }
@@ -590,9 +601,9 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 *reinterpret_cast<uint4*>(rowp + ((c ^ ((lane >> 1) & 3)) << 4)) = pk;
               }
             }
-            if (!(p.dbg & 16)) fence_proxy_async_smem();
+            if (!VFD_DBG(p, 16)) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 8)) {
+            if (lane == 0 && !VFD_DBG(p, 8)) {
               tma_store_5d(&tmC, sb, ch * 32, w0, h0 + 4 * q, d, n);
               bulk_commit_group();
             }
@@ -954,7 +965,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + static_cast<size_t>(s) * p.stage_bytes;
         uint8_t* sb = sa + 2 * kWgBoxBytes;
-        if (p.dbg & 1) {
+        if VFD_DBG(p, 1) {
           mbar_arrive(&full_bar[s]);
         } else {
           mbar_expect_tx(&full_bar[s], na * kWgBoxBytes + nbv * p.plane_bytes);
@@ -976,7 +987,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
       // warp-uniform; the (tap, K16-step) sequence is fully unrolled with immediate descriptor offsets and
       // one elected lane issues
       const bool leader = elect_one();
-      const bool issue = leader && !(p.dbg & 2);
+      const bool issue = leader && !VFD_DBG(p, 2);
       constexpr int PWk = 8 + KHW - 1;
       const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
       const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
@@ -1017,7 +1028,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int tapidx = 0; tapidx < ((p.dbg & 4) ? 0 : khw); ++tapidx) {
+    for (int tapidx = 0; tapidx < (VFD_DBG(p, 4) ? 0 : khw); ++tapidx) {
       const int tap = a * khw + tapidx;
       for (int c = 0; c < p.ci_n; c += 16) {
         float v[16];
@@ -1135,7 +1146,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sx = smem + static_cast<size_t>(s) * p.stage_bytes;
         uint8_t* sy = sx + 2 * p.plane_stride;
-        if (p.dbg & 1) {
+        if VFD_DBG(p, 1) {
           mbar_arrive(&full_bar[s]);
         } else {
           mbar_expect_tx(&full_bar[s], nx * p.plane_bytes + ny * kWgBoxBytes);
@@ -1154,7 +1165,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   } else if (warp == 1) {
     {  // warp-uniform MMA issue (see conv_wgrad2_kernel); not guarded by has_work
       const bool leader = elect_one();
-      const bool issue = leader && !(p.dbg & 2);
+      const bool issue = leader && !VFD_DBG(p, 2);
       const uint32_t idesc = idesc_bf16_m128(p.co_n, true, true);
       const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), p.plane_stride, PWk * 128);
       const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + 2 * p.plane_stride, kWgBoxBytes, 1024);
@@ -1194,7 +1205,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int t = 0; t < ((p.dbg & 4) ? 0 : ntaps); ++t) {
+    for (int t = 0; t < (VFD_DBG(p, 4) ? 0 : ntaps); ++t) {
       const int tap = a * KT + t0 + t;
       for (int c = 0; c < p.co_n; c += 16) {
         float v[16];
@@ -1296,7 +1307,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sy = smem + static_cast<size_t>(s) * p.stage_bytes;
           uint8_t* sx = sy + p.na * kWgBoxBytes;
-          if (p.dbg & 1) {
+          if VFD_DBG(p, 1) {
             mbar_arrive(&full_bar[s]);
           } else {
             mbar_expect_tx(&full_bar[s], ((j >= 1 ? nay : 0) + (j < D ? nbx : 0)) * kWgBoxBytes);
@@ -1317,7 +1328,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   } else if (warp == 1) {
     {  // warp-uniform MMA issue; not guarded by has_work (see conv_wgrad2_kernel)
       const bool leader = elect_one();
-      const bool issue = leader && !(p.dbg & 2);
+      const bool issue = leader && !VFD_DBG(p, 2);
       const uint32_t idesc = idesc_bf16_m128(p.ci_n, true, true);
       const uint64_t da0 = sdesc_mnmajor128_ex(smem_u32(smem), kWgBoxBytes, 1024);
       const uint64_t db0 = sdesc_mnmajor128_ex(smem_u32(smem) + p.na * kWgBoxBytes, kWgBoxBytes, 1024);
@@ -1384,7 +1395,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int a = 0; a < ((p.dbg & 4) ? 0 : 3); ++a) {
+    for (int a = 0; a < (VFD_DBG(p, 4) ? 0 : 3); ++a) {
       if (D == 1 && a != 1) continue;   // taps that never received a plane hold no data
       for (int c = 0; c < p.ci_n; c += 16) {
         float v[16];
@@ -1748,10 +1759,12 @@ int launch_tiny_pointwise(const void* x, long long x_ld, const void* w_packed, i
 
 using namespace vfd;
 
+#ifdef VFD_DEBUG
 VFD_API int vfd_set_debug(int flags) {
   g_dbg = flags;
   return 0;
 }
+#endif
 
 VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w_packed,
                               int w_rows, int cin_k, const float* bias, void* out,
@@ -1768,7 +1781,7 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
       (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(VFD_ERR_ARG, "conv3d_fwd: output must be 16-byte aligned");
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;  // empty batch: nothing to do
-  if (kd == 1 && kh == 1 && kw == 1 && cin <= 8 && out_cols == 8 && w_rows == 16 && !out_fp32 && !(g_dbg & 64) &&
+  if (kd == 1 && kh == 1 && kw == 1 && cin <= 8 && out_cols == 8 && w_rows == 16 && !out_fp32 && !VFD_GDBG(64) &&
       (x_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
     return launch_tiny_pointwise(x, x_ld, w_packed, cin_k, bias, out, out_ld, (long long)N * D * H * W, stats,
                                  stats_ld, stream);

@@ -109,7 +109,7 @@ def _conv3d_fwd(x, w_packed, bias, out, stats, kd, kh, kw, kc, out_cols, direct)
     head = [x.data_ptr(), ld, C, w_packed.data_ptr(), rows, cin_k, _ptr(bias), out.data_ptr(), _ld(out), out_cols,
             out_fp32]
     if direct:
-        _lib.call("vfd_conv3d_fwd_direct", *head, N, D, H, W, kd, kh, kw, _stream())
+        _lib.call_debug("vfd_conv3d_fwd_direct", *head, N, D, H, W, kd, kh, kw, _stream())
         if stats is not None:   # the CUDA-core cross-check path has no fused statistics
             _lib.call("vfd_bn_stats", out.data_ptr(), _ld(out), out.shape[-1], N * D * H * W, stats.data_ptr(),
                       _stream())
@@ -126,7 +126,7 @@ def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     else:
         taps, ci_pad, co_pad = acc.shape
     if direct:
-        _lib.call("vfd_conv3d_wgrad_direct", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(),
+        _lib.call_debug("vfd_conv3d_wgrad_direct", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(),
                   co_pad, ci_pad, N, D, H, W, kd, kh, kw, _stream())
     else:
         _lib.call("vfd_conv3d_wgrad", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
@@ -385,7 +385,7 @@ roc_auc_op = _define("roc_auc(Tensor scores, Tensor labels, Tensor(a!) out) -> (
 # ------------------------------------------------------------------------------------------------
 # helpers shared by the autograd functions
 # ------------------------------------------------------------------------------------------------
-CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core one
+CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
 
