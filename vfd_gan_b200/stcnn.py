@@ -10,7 +10,7 @@ upsample kernels of the GAN path (kernel shapes 1x3x3, 3x1x1, 1x1x1 and 3x3x3, S
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .mygannet import _draw_seed
 from .spatiotempconv import bn_apply
 
@@ -142,14 +142,19 @@ class StcnnTrainStep:
             self._static_in = [inp.detach().clone().contiguous().float(), gt.detach().clone().contiguous().float()]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            c0, k0 = _lib.LAUNCHES, _lib.KERNEL_LAUNCHES
             with torch.cuda.graph(graph):
                 self._step_impl(*self._static_in, None, self._step_counter)
+            self._graph_calls, self._graph_kernels = _lib.LAUNCHES - c0, _lib.KERNEL_LAUNCHES - k0
+            _lib.LAUNCHES, _lib.KERNEL_LAUNCHES = c0, k0        # capture records, it does not launch
             self._graph = graph
         elif inp.shape != self._static_in[0].shape or gt.shape != self._static_in[1].shape:
             return self._step_impl(inp, gt, None, self._step_counter)
         self._static_in[0].copy_(inp, non_blocking=True)
         self._static_in[1].copy_(gt, non_blocking=True)
         self._graph.replay()
+        _lib.LAUNCHES += self._graph_calls
+        _lib.KERNEL_LAUNCHES += self._graph_kernels         # kernels of ours the replay just launched
         ops.invalidate_packed_weights()
         return self.loss
 
