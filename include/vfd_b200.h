@@ -210,6 +210,14 @@ VFD_API int vfd_confusion_counts(const float* labels, const float* scores, long 
  * (lib/evaluate.py:37-38) and the precision-recall area auc(recall, precision) of precision_recall_curve
  * (lib/evaluate.py:67-68); out = device double[4]: ROC area, #positives, #negatives, PR area */
 VFD_API int vfd_roc_auc(const float* scores, const float* labels, int n, double* out, void* stream);
+/* the same four numbers for any n < 2^31 (the voxel-level evaluation of test.py:175-202 and
+ * models/mygannet.py:444-470: every voxel of the test set is a (score, label) pair): stable multi-block radix sort of
+ * (score, label) keys, negative prefix counts, one pass over the runs of equal scores. Exact integer pair counts for the
+ * ROC area, blocks summed in index order for the PR area (deterministic). workspace: 256-byte aligned device scratch
+ * of at least vfd_roc_auc_large_workspace(n) bytes (about 16 bytes per pair). */
+VFD_API long long vfd_roc_auc_large_workspace(long long n);
+VFD_API int vfd_roc_auc_large(const float* scores, const float* labels, long long n, double* out, void* workspace,
+                              long long ws_bytes, void* stream);
 
 /* ---- video_to_flow (lib/utils.py:94-129; called at models/mygannet.py:281-282,404-405) on the device -----
  * video fp32 [B][3][D][H][W] in [-1, 1] -> out fp32 [B][3][D][H][W] in [-1, 1]: per-frame-index normalize over the

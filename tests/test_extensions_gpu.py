@@ -296,7 +296,109 @@ def test_roc_auc_kernel_against_sklearn_fixture():
         assert abs(float(got[0]) - O.evaluate(lab.numpy(), sc.numpy(), "roc")) < 1e-12, n
         assert abs(float(got[3]) - O.evaluate(lab.numpy(), sc.numpy(), "pr")) < 1e-12, n
     with pytest.raises(RuntimeError):
-        V.evaluate.roc_auc(torch.zeros(20000, device=DEV), torch.zeros(20000, device=DEV))
+        V.evaluate.roc_auc(torch.zeros(20000, device=DEV), torch.zeros(19999, device=DEV))
+
+
+def _areas(lab, sc):
+    return O.evaluate(lab.numpy(), sc.numpy(), "roc"), O.evaluate(lab.numpy(), sc.numpy(), "pr")
+
+
+def test_voxel_level_roc_pr_against_sklearn_at_1e6():
+    """lib/evaluate.py's roc / pr on a million voxels (test.py:186-202 hands it every voxel of the test set): the
+    multi-block sort + run-length pass against sklearn on the same arrays. ROC pair counts are exact integers, so the
+    area differs from sklearn's trapezoid sum only by its float rounding (1e-12); the PR trapezoids are summed in a
+    different order than np.trapz (1e-10)."""
+    g = torch.Generator().manual_seed(11)
+    n = 1_000_003
+    lab = (torch.rand(n, generator=g) > 0.9).float()
+    cases = {
+        "continuous": torch.sigmoid(torch.randn(n, generator=g) + 1.5 * lab),
+        "quantised (heavy ties)": (torch.sigmoid(torch.randn(n, generator=g) + 1.5 * lab) * 255).round() / 255,
+        "signed with zeros": (torch.randn(n, generator=g) + lab).round(decimals=2) * (torch.rand(n, generator=g) > 0.2),
+    }
+    cases["signed with zeros"][::7] *= -1.0                       # -0.0 and +0.0 are one score
+    for name, sc in cases.items():
+        sc = sc.float()
+        want_roc, want_pr = _areas(lab, sc)
+        got = V.evaluate.roc_auc(lab.to(DEV), sc.to(DEV)).tolist()
+        assert abs(got[0] - want_roc) < 1e-12, (name, got[0], want_roc)
+        assert abs(got[3] - want_pr) < 1e-10, (name, got[3], want_pr)
+        assert got[1] == float(lab.sum()) and got[2] == n - float(lab.sum())
+        again = V.evaluate.roc_auc(lab.to(DEV), sc.to(DEV)).tolist()
+        assert again == got, name                                 # deterministic: no floating-point atomics
+
+
+def test_voxel_level_roc_edges_and_both_kernels_agree():
+    g = torch.Generator().manual_seed(12)
+    n = 16384                                                     # the size both kernels accept
+    lab = (torch.rand(n, generator=g) > 0.5).float()
+    sc = torch.randn(n, generator=g).round(decimals=1)
+    small = torch.empty(4, dtype=torch.float64, device=DEV)
+    large = torch.empty(4, dtype=torch.float64, device=DEV)
+    from vfd_gan_b200 import _lib
+    ws = torch.empty(int(_lib.lib().vfd_roc_auc_large_workspace(n)), dtype=torch.uint8, device=DEV)
+    ops.roc_auc_op(sc.to(DEV), lab.to(DEV), small)
+    ops.roc_auc_large_op(sc.to(DEV), lab.to(DEV), large, ws)
+    assert small[1:3].tolist() == large[1:3].tolist()
+    assert abs(float(small[0] - large[0])) < 1e-13 and abs(float(small[3] - large[3])) < 1e-12
+    for n in (16385, 2048 * 3 + 1 + 16384, 50_000):               # one past the single-block limit, ragged tiles
+        lab = (torch.rand(n, generator=g) > 0.7).float()
+        sc = torch.rand(n, generator=g).round(decimals=3)
+        want_roc, want_pr = _areas(lab, sc)
+        got = V.evaluate.roc_auc(lab.to(DEV), sc.to(DEV)).tolist()
+        assert abs(got[0] - want_roc) < 1e-12 and abs(got[3] - want_pr) < 1e-10, n
+    n = 40_000
+    lab = (torch.arange(n) % 3 == 0).float()
+    assert float(V.evaluate.roc_auc(lab.to(DEV), torch.full((n,), 0.25, device=DEV))[0]) == 0.5   # one big tie
+    sep = V.evaluate.roc_auc(lab.to(DEV), (lab * 2 - 1 + 0.1 * torch.rand(n, generator=g)).to(DEV)).tolist()
+    assert sep[0] == 1.0 and abs(sep[3] - 1.0) < 1e-12                                          # separable
+    one_class = V.evaluate.roc_auc(torch.zeros(n, device=DEV), torch.rand(n, device=DEV)).tolist()
+    assert one_class[0] != one_class[0] and one_class[1] == 0.0 and one_class[2] == float(n)   # NaN area, counts kept
+    with pytest.raises(RuntimeError):
+        ops.roc_auc_large_op(torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), large, ws[:1024])
+
+
+def test_voxel_level_roc_properties_at_1e8():
+    """Size-independent properties at the size of a whole test sweep (1e8 voxels = 62 clips of 16 x 112 x 112 x 8):
+    swapping the classes gives exactly 1 - AUC (integer pair counts), a strictly increasing map of the scores changes
+    nothing, and a subsample estimate agrees with sklearn on that subsample."""
+    g = torch.Generator(device=DEV).manual_seed(13)
+    n = 100_000_000
+    lab = (torch.rand(n, device=DEV, generator=g) > 0.95).float()
+    sc = torch.sigmoid(torch.randn(n, device=DEV, generator=g) + 2.0 * lab)
+    a = V.evaluate.roc_auc(lab, sc).tolist()
+    b = V.evaluate.roc_auc(1.0 - lab, sc).tolist()
+    assert a[1] == b[2] and a[2] == b[1] and a[1] + a[2] == n
+    assert abs(a[0] + b[0] - 1.0) < 1e-15
+    c = V.evaluate.roc_auc(lab, sc * 3.0 - 1.0).tolist()         # float rounding may merge a few neighbours into ties
+    assert abs(c[0] - a[0]) < 1e-9 and abs(c[3] - a[3]) < 1e-6
+    # analytic value: P(sigmoid(z1 + 2) > sigmoid(z0)) = Phi(2 / sqrt(2)) = 0.92135...
+    assert abs(a[0] - 0.9213503964748574) < 5e-4
+    idx = torch.randint(0, n, (2_000_000,), device=DEV, generator=g)
+    want_roc, want_pr = _areas(lab[idx].cpu(), sc[idx].cpu())
+    sub = V.evaluate.roc_auc(lab[idx], sc[idx]).tolist()
+    assert abs(sub[0] - want_roc) < 1e-12 and abs(sub[3] - want_pr) < 1e-10
+    assert abs(sub[0] - a[0]) < 2e-3
+
+
+def test_voxel_curve_accumulator_follows_test_py():
+    """test.py:175-202: per batch append gt / predict voxels, then lib/evaluate.py's roc / pr / f1_score over all."""
+    g = torch.Generator().manual_seed(14)
+    acc = V.evaluate.VoxelCurveAccumulator(DEV, capacity=1000)    # forces two growths
+    gts, predicts = [], []
+    for b in range(3):
+        gt = (torch.rand(2, 1, 4, 20, 20, generator=g) > 0.8).float()
+        predict = torch.sigmoid(torch.randn(2, 1, 4, 20, 20, generator=g) + 2 * gt)
+        acc.add(gt.to(DEV), predict.to(DEV))
+        gts.append(gt.permute(0, 2, 3, 4, 1).numpy())
+        predicts.append(predict.permute(0, 2, 3, 4, 1).numpy())
+    import numpy as np
+    gts = np.asarray(np.stack(gts), dtype=np.int32).flatten()
+    predicts = np.asarray(np.stack(predicts)).flatten()
+    got = acc.result()
+    assert abs(got["roc"] - O.evaluate(gts, predicts, "roc")) < 1e-12
+    assert abs(got["pr"] - O.evaluate(gts, predicts, "pr")) < 1e-12
+    assert abs(got["f1"] - O.evaluate(gts, predicts, "f1_score")) < 1e-12
 
 
 def test_empty_batches_are_no_ops():

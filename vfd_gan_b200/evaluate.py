@@ -69,15 +69,74 @@ def binary_metrics_from_counts(tp, fp, fn, tn):
     return {"roc": roc, "pr": pr, "f1": f1}
 
 
+ROC_SINGLE_BLOCK_MAX = 16384
+
+
 def roc_auc(labels, scores):
-    """Exact ROC area of up to 16384 (score, label) pairs on the device (the per-clip anomaly-score sweep);
-    equals ``lib/evaluate.py``'s ``roc`` = ``auc(*roc_curve(labels, scores)[:2])``. Returns a device double[4]:
-    ROC area, #positives, #negatives, PR area (``lib/evaluate.py``'s ``pr``) -- no host synchronisation."""
+    """Exact ROC and precision-recall areas of (score, label) pairs on the device; equals ``lib/evaluate.py``'s
+    ``roc`` = ``auc(*roc_curve(labels, scores)[:2])`` and ``pr`` = ``auc(recall, precision)``. Returns a device
+    double[4]: ROC area, #positives, #negatives, PR area -- no host synchronisation.
+
+    Up to 16384 pairs (the per-clip anomaly-score sweep) run in one block; anything larger (the voxel-level evaluation
+    of test.py:175-202: every voxel of the test set) goes through the multi-block radix sort of ``csrc/roc_large.cu``
+    (about 16 bytes of scratch per pair, n < 2^31)."""
     if not scores.is_cuda:
         raise RuntimeError("roc_auc: vfd_gan_b200 has no CPU path")
     out = torch.empty(4, dtype=torch.float64, device=scores.device)
-    ops.roc_auc_op(scores.contiguous().float().view(-1), labels.contiguous().float().view(-1), out)
+    s, l = scores.contiguous().float().view(-1), labels.contiguous().float().view(-1)
+    if s.numel() != l.numel():
+        raise RuntimeError(f"roc_auc: {s.numel()} scores but {l.numel()} labels")
+    if s.numel() <= ROC_SINGLE_BLOCK_MAX:
+        ops.roc_auc_op(s, l, out)
+    else:
+        from . import _lib
+        need = int(_lib.lib().vfd_roc_auc_large_workspace(s.numel()))
+        ws = torch.empty(need, dtype=torch.uint8, device=s.device)
+        ops.roc_auc_large_op(s, l, out, ws)
     return out
+
+
+class VoxelCurveAccumulator:
+    """The evaluation loop of test.py:175-202 without the host arrays: per batch ``add(gt, predict)`` keeps the
+    flattened voxels of the raw prediction and of the ground truth on the device (the reference appends
+    ``predict.permute(0,2,3,4,1).cpu().numpy()`` to a list and stacks it) and folds them into the confusion counts of
+    the F1 branch (threshold 0.20, lib/evaluate.py:20-24); ``result()`` runs the device ROC / PR areas over all voxels
+    seen and does the one device->host read. The order of the voxels does not enter any of the three metrics, so no
+    permute is needed. ``capacity`` voxels are allocated up front (two fp32 arrays) and doubled on demand."""
+
+    def __init__(self, device, capacity=1 << 24):
+        self.scores = torch.empty(int(capacity), dtype=torch.float32, device=device)
+        self.labels = torch.empty(int(capacity), dtype=torch.float32, device=device)
+        self.counts = torch.zeros(4, dtype=torch.int64, device=device)
+        self.n = 0
+
+    def add(self, gt, predict):
+        if not predict.is_cuda:
+            raise RuntimeError("VoxelCurveAccumulator: vfd_gan_b200 has no CPU path")
+        p, g = predict.detach().reshape(-1).float(), gt.detach().reshape(-1).float()
+        if p.numel() != g.numel():
+            raise RuntimeError(f"VoxelCurveAccumulator.add: {p.numel()} predictions but {g.numel()} labels")
+        m = p.numel()
+        if self.n + m > self.scores.numel():
+            cap = max(2 * self.scores.numel(), self.n + m)
+            for name in ("scores", "labels"):
+                grown = torch.empty(cap, dtype=torch.float32, device=self.scores.device)
+                grown[:self.n].copy_(getattr(self, name)[:self.n])
+                setattr(self, name, grown)
+        self.scores[self.n:self.n + m].copy_(p)
+        self.labels[self.n:self.n + m].copy_(g)
+        if m:
+            confusion_counts(g, p, 0.20, self.counts)
+        self.n += m
+
+    def result(self):
+        """-> {"roc", "pr", "f1"} as lib/evaluate.py's three metrics return them for (gts, predicts)."""
+        if self.n == 0:
+            raise RuntimeError("VoxelCurveAccumulator.result() before any add()")
+        area = roc_auc(self.labels[:self.n], self.scores[:self.n]).tolist()
+        tp, fp, fn, _ = self.counts.tolist()
+        f1 = 2.0 * tp / (2.0 * tp + fp + fn) if (2.0 * tp + fp + fn) > 0 else 0.0
+        return {"roc": area[0], "pr": area[3], "f1": f1}
 
 
 TEST_KEYS = ("d/err_d_real_s/test", "d/err_d_real_t/test", "d/err_d_fake_s/test", "d/err_d_fake_t/test",

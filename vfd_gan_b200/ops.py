@@ -320,6 +320,11 @@ def _roc_auc(scores, labels, out):
     _lib.call("vfd_roc_auc", scores.data_ptr(), labels.data_ptr(), scores.numel(), out.data_ptr(), _stream())
 
 
+def _roc_auc_large(scores, labels, out, ws):
+    _lib.call("vfd_roc_auc_large", scores.data_ptr(), labels.data_ptr(), scores.numel(), out.data_ptr(),
+              ws.data_ptr(), ws.numel(), _stream())
+
+
 conv3d_fwd = _define(
     "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
@@ -380,6 +385,8 @@ confusion_counts_op = _define("confusion_counts(Tensor labels, Tensor scores, fl
 video_to_flow_op = _define("video_to_flow(Tensor video, Tensor(a!) out, Tensor(b!)? raw, Tensor(c!) ws) -> ()",
                            _video_to_flow)
 roc_auc_op = _define("roc_auc(Tensor scores, Tensor labels, Tensor(a!) out) -> ()", _roc_auc)
+roc_auc_large_op = _define("roc_auc_large(Tensor scores, Tensor labels, Tensor(a!) out, Tensor(b!) ws) -> ()",
+                           _roc_auc_large)
 
 
 # ------------------------------------------------------------------------------------------------
