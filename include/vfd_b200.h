@@ -229,4 +229,18 @@ VFD_API long long vfd_video_to_flow_workspace(int B, int D, int H, int W);
 VFD_API int vfd_video_to_flow(const float* video, int B, int D, int H, int W, float* out, float* raw_flow,
                               void* workspace, long long ws_bytes, void* stream);
 
+/* ---- clip pipeline from decoded uint8 frames (lib/data.py:14-161) --------------------------------------------
+ * vfd_resize_frames_u8: Resize((isize, isize)) of the test transform (test.py:150-153, lib/data.py:143-146; the
+ * reference's videotransforms/functional.py:54-58 selects PIL.Image.BILINEAR): Pillow's antialiased two-pass
+ * resample on 8-bit channels, bit-exact. src uint8 [n][Hin][Win][C] -> dst uint8 [n][Hout][Wout][C], C in {1, 3}.
+ * workspace: 256-byte aligned device scratch of at least vfd_resize_frames_u8_workspace(...) bytes.
+ * vfd_frames_to_clip: ClipToTensor (videotransforms/volume_transforms.py:17-58) and the `*2-1` of lib/data.py:78:
+ * frames uint8 [B][T][H][W][C] -> out float32 [B][Cout][T][H][W] = x / 255 (pm1 = 1: then 2x - 1); C == Cout, or
+ * C == 1 broadcast over Cout channels (an 'L' mask through ClipToTensor(channel_nb=3)). */
+VFD_API long long vfd_resize_frames_u8_workspace(long long n, int Hin, int Win, int C, int Hout, int Wout);
+VFD_API int vfd_resize_frames_u8(const void* src, long long n, int Hin, int Win, int C, void* dst, int Hout,
+                                 int Wout, void* workspace, long long ws_bytes, void* stream);
+VFD_API int vfd_frames_to_clip(const void* frames, long long B, int T, int H, int W, int C, int Cout, int pm1,
+                               float* out, void* stream);
+
 #endif /* VFD_B200_H */

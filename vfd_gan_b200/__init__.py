@@ -12,11 +12,12 @@ from .convlstm import ConvLSTMCell, ConvLSTM  # noqa: F401
 from .losses import weights_init, l2_loss, weighted_bce, gray2rgb, strip_module_prefix  # noqa: F401
 from .composed import NetGLstm, Encoder, EncDecEncG, AnomalyScorer, anomaly_scores, latent_l2_and_scores  # noqa: F401
 from .stcnn import C2plus1d_Block, AutoEncoder, StcnnTrainStep  # noqa: F401
-from . import evaluate  # noqa: F401
+from . import evaluate, data, checkpoint  # noqa: F401
+from .data import ClipPrefetcher, DeviceTestTransform  # noqa: F401
 from .flow import video_to_flow  # noqa: F401
 from .step import GanTrainStep, HostBatchStep, GradAllReducer, LOSS_KEYS  # noqa: F401
 
 __all__ = ["SpatioTemporalConv", "NetgConv", "NetG", "NetdConv", "SDisc", "TDisc", "NetD", "ConvLSTMCell",
            "ConvLSTM", "weights_init", "l2_loss", "weighted_bce", "gray2rgb", "strip_module_prefix", "GanTrainStep", "HostBatchStep",
            "GradAllReducer", "LOSS_KEYS", "NetGLstm", "Encoder", "EncDecEncG", "AnomalyScorer", "anomaly_scores",
-           "latent_l2_and_scores", "C2plus1d_Block", "AutoEncoder", "StcnnTrainStep", "evaluate", "video_to_flow"]
+           "latent_l2_and_scores", "C2plus1d_Block", "AutoEncoder", "StcnnTrainStep", "evaluate", "video_to_flow", "data", "checkpoint", "ClipPrefetcher", "DeviceTestTransform"]

@@ -50,6 +50,9 @@ SIGNATURES = {
     "vfd_roc_auc": [_p, _p, _i, _p, _p],
     "vfd_roc_auc_large": [_p, _p, _ll, _p, _p, _ll, _p],
     "vfd_roc_auc_large_workspace": [_ll],
+    "vfd_resize_frames_u8_workspace": [_ll, _i, _i, _i, _i, _i],
+    "vfd_resize_frames_u8": [_p, _ll, _i, _i, _i, _p, _i, _i, _p, _ll, _p],
+    "vfd_frames_to_clip": [_p, _ll, _i, _i, _i, _i, _i, _i, _p, _p],
     "vfd_video_to_flow": [_p, _i, _i, _i, _i, _p, _p, _p, _ll, _p],
     "vfd_video_to_flow_workspace": [_i, _i, _i, _i],
 }
@@ -65,7 +68,7 @@ _debug_lib = None
 _lib = None
 LAUNCHES = 0         # C-ABI compute calls issued by this process
 KERNEL_LAUNCHES = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18}
+_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18, "vfd_resize_frames_u8": 4}
 
 
 def build(force=False):
@@ -95,6 +98,7 @@ def lib():
             fn.restype = ctypes.c_int
         L.vfd_video_to_flow_workspace.restype = ctypes.c_longlong
         L.vfd_roc_auc_large_workspace.restype = ctypes.c_longlong
+        L.vfd_resize_frames_u8_workspace.restype = ctypes.c_longlong
         _lib = L
     return _lib
 

@@ -325,6 +325,18 @@ def _roc_auc_large(scores, labels, out, ws):
               ws.data_ptr(), ws.numel(), _stream())
 
 
+def _resize_frames_u8(src, dst, ws):
+    n, hin, win, c = src.shape
+    _lib.call("vfd_resize_frames_u8", src.data_ptr(), n, hin, win, c, dst.data_ptr(), dst.shape[1], dst.shape[2],
+              ws.data_ptr(), ws.numel(), _stream())
+
+
+def _frames_to_clip(frames, out, pm1):
+    b, t, h, w, c = frames.shape
+    _lib.call("vfd_frames_to_clip", frames.data_ptr(), b, t, h, w, c, out.shape[1], int(pm1), out.data_ptr(),
+              _stream())
+
+
 conv3d_fwd = _define(
     "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
@@ -385,6 +397,8 @@ confusion_counts_op = _define("confusion_counts(Tensor labels, Tensor scores, fl
 video_to_flow_op = _define("video_to_flow(Tensor video, Tensor(a!) out, Tensor(b!)? raw, Tensor(c!) ws) -> ()",
                            _video_to_flow)
 roc_auc_op = _define("roc_auc(Tensor scores, Tensor labels, Tensor(a!) out) -> ()", _roc_auc)
+resize_frames_u8_op = _define("resize_frames_u8(Tensor src, Tensor(a!) dst, Tensor(b!) ws) -> ()", _resize_frames_u8)
+frames_to_clip_op = _define("frames_to_clip(Tensor frames, Tensor(a!) out, bool pm1) -> ()", _frames_to_clip)
 roc_auc_large_op = _define("roc_auc_large(Tensor scores, Tensor labels, Tensor(a!) out, Tensor(b!) ws) -> ()",
                            _roc_auc_large)
 
