@@ -135,8 +135,9 @@ def test_training_state_resume_continues_the_trajectory(tmp_path):
         for i, w in zip((3, 4), want):
             tr2.step(*batches[i])
             got = tr2.losses_dict()
-            for k in w:
-                assert abs(got[k] - w[k]) <= 2e-3 * abs(w[k]) + 1e-5, (graph, i, k, got[k], w[k])
+            for k in w:     # the logged-only adversarial terms carry the run-to-run atomics noise
+                tol = 2e-2 if "adv" in k or k == "g/err_g" else 2e-3
+                assert abs(got[k] - w[k]) <= tol * abs(w[k]) + 1e-5, (graph, i, k, got[k], w[k])
         netg3, netd3 = build(2)
         tr3 = V.GanTrainStep(netg3, netd3, graph=False, lr=2e-3)
         V.checkpoint.load_weights(str(tmp_path / "w" / "mygan_ep0007_netG.pth"), netg3, netd3)
