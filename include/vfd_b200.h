@@ -69,6 +69,22 @@ VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, con
                                   int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
                                   int H, int W, int kd, int kh, int kw, void* stream);
 
+/* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
+ * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
+ * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =
+ * 16-byte aligned device scratch of at least the matching *_workspace(...) bytes. */
+VFD_API long long vfd_conv3d_wgrad_det_workspace(int cout, int cin, int co_pad, int ci_pad, int layout, int N, int D,
+                                                 int H, int W, int kd, int kh, int kw);
+VFD_API int vfd_conv3d_wgrad_det(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin,
+                                 float* acc, int co_pad, int ci_pad, int layout, int N, int D, int H, int W, int kd,
+                                 int kh, int kw, void* workspace, long long ws_bytes, void* stream);
+VFD_API long long vfd_conv3d_wgrad_thin_det_workspace(int cout, int cin, int fold, int cs, int N, int D, int H, int W,
+                                                      int kd, int kh, int kw);
+VFD_API int vfd_conv3d_wgrad_thin_det(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
+                                      int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
+                                      int H, int W, int kd, int kh, int kw, void* workspace, long long ws_bytes,
+                                      void* stream);
+
 /* ---- layout / weight packing -------------------------------------------------------------------
  * fp32 NCDHW [N][Csrc][S] -> bf16 channels-last [N][S][ld] (Cp channels, zero beyond C).
  * replicate = 1 repeats the source channels (gray2rgb, lib/utils.py:91-92). */

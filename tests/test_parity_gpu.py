@@ -308,6 +308,54 @@ def test_graph_step_equals_eager_step():
     assert all(float((pb[k] - pa[k]).abs().max()) <= 5 * 3 * 2e-5 for k in pa)
 
 
+DET_CASES = [c for c in CONV_CASES if c[:3] in {(96, 86, (1, 3, 3)), (64, 64, (3, 1, 1)), (3, 21, (1, 3, 3)),
+                                               (32, 1, (3, 3, 3)), (2, 32, (3, 1, 1)), (256, 72, (3, 3, 3)),
+                                               (192, 172, (1, 3, 3)), (14, 32, (1, 1, 1)), (24, 40, (1, 3, 3))}]
+
+
+@pytest.mark.parametrize("cin,cout,k,N,D,H,W", DET_CASES + [(3, 2, (1, 1, 1), 4, 16, 32, 32)])
+def test_deterministic_weight_gradient_mode(cin, cout, k, N, D, H, W):
+    """VFD_DETERMINISTIC / ops.set_deterministic: every weight-gradient kernel (the four tcgen05 variants, the thin
+    mma.sync kernel with and without tap folding, the one-thread-per-voxel kernel) writes per-split partials and an
+    ordered pass sums them -- repeated calls give identical bits, and the values are those of the atomic path up to
+    the summation order."""
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(N * 4, cin, D, H, W, generator=g).to(DEV)       # enough voxels for many splits
+    w = (torch.randn(cout, cin, *k, generator=g) * 0.1).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    gy = torch.randn(N * 4, cout, D, H, W, generator=g).to(DEV)
+    plain = _conv_all(x, w, b, gy, direct=False)[2]
+    ops.set_deterministic(True)
+    try:
+        runs = [_conv_all(x, w, b, gy, direct=False)[2] for _ in range(4)]
+    finally:
+        ops.set_deterministic(False)
+    assert all(torch.equal(runs[0], r) for r in runs[1:])
+    assert rel(runs[0], plain) < 1e-5
+
+
+def test_deterministic_mode_step_is_reproducible():
+    """Two independent runs of three eager train steps, and a CUDA-graph run, from the same weights and batches with
+    the deterministic weight gradients on. What is left to reorder are fp64 atomics of float partial sums
+    (BatchNorm statistics, loss sums), which are exact unless a sum needs more than 53 bits."""
+    ops.set_deterministic(True)
+    try:
+        results = []
+        for graph in (False, False, True):
+            netg, netd = build_cfg1_nets()
+            netg, netd = netg.to(DEV), netd.to(DEV)
+            tr = V.GanTrainStep(netg, netd, graph=graph)
+            for it in range(4):
+                tr.step(*[t.to(DEV) for t in O.synthetic_batch(2, 16, 64, seed=it)])
+            results.append((tr.losses.clone(), [p.detach().clone() for p in list(netg.parameters()) + list(netd.parameters())]))
+    finally:
+        ops.set_deterministic(False)
+    for other in results[1:]:
+        worst = max(float((a - b).abs().max()) for a, b in zip(results[0][1], other[1]))
+        assert rel(other[0], results[0][0]) < 1e-6, (results[0][0], other[0])
+        assert worst <= 1e-7, worst       # parameters: identical up to (at most) a last-bit difference
+
+
 def test_losses_match_reference_fixture():
     f = golden("losses.pt")
     p, t = f["p"].to(DEV).requires_grad_(True), f["t"].to(DEV)

@@ -1,14 +1,6 @@
-python -m pytest tests/test_data_gpu.py -x -q -m gpu -k training_state 2>&1 | tail -15 > gpurun_out/r2o_state_test.log
-B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile --no-flow"
-for cfg in "default" "VFD_BN_WAVES=1" "VFD_BN_WAVES=2" "VFD_ASYNC_WGRAD=0" "VFD_BN_WAVES=1 VFD_ASYNC_WGRAD=0"; do
-  if [ "$cfg" = "default" ]; then env $B > gpurun_out/r2o_tmp.json 2>gpurun_out/r2o_tmp.err; else env $cfg $B > gpurun_out/r2o_tmp.json 2>gpurun_out/r2o_tmp.err; fi
-  python - "$cfg" <<'PY' >> gpurun_out/r2o_overlap_experiment.txt
-import json,sys
-try:
-    d=json.loads(open('gpurun_out/r2o_tmp.json').read().strip().splitlines()[-1])
-    print(sys.argv[1], 'ms_per_step', round(d['ms_per_step'],3), 'e2e_ms', round(d['e2e']['ms_per_step'],3))
-except Exception as e:
-    print(sys.argv[1], 'FAILED', e)
-PY
-done
-cat gpurun_out/r2o_overlap_experiment.txt; tail -3 gpurun_out/r2o_state_test.log
+python -m pytest tests/test_data_gpu.py -x -q -m gpu -k training_state 2>&1 | tail -5 > gpurun_out/r2p_state_test.log
+python bench.py --steps 1 --warmup 3 --no-profile --no-cpu-baseline --no-flow > gpurun_out/r2p_b.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2p_launches_raw.csv python bench.py --steps 1 --warmup 3 --no-profile --no-cpu-baseline --no-flow > gpurun_out/r2p_ncu.log 2>&1
+python tools/launch_summary.py gpurun_out/r2p_launches_raw.csv gpurun_out/r2p > gpurun_out/r2p_summary.log 2>&1
+python tools/gpu_glue_trace.py > gpurun_out/r2p_glue.log 2>&1
+tail -3 gpurun_out/r2p_state_test.log; head -40 gpurun_out/r2p_step_kernel_summary.csv

@@ -19,6 +19,10 @@ SIGNATURES = {
     "vfd_conv3d_wgrad": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_layout": [_i, _i, _i, _i, _i, _i, _i],
     "vfd_conv3d_wgrad_thin": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_wgrad_det_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "vfd_conv3d_wgrad_det": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
+    "vfd_conv3d_wgrad_thin_det_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "vfd_conv3d_wgrad_thin_det": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
     "vfd_pack_ncdhw": [_p, _p, _i, _i, _ll, _i, _ll, _i, _i, _p],
     "vfd_unpack_ncdhw": [_p, _i, _p, _i, _i, _ll, _ll, _p],
     "vfd_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -68,7 +72,7 @@ _debug_lib = None
 _lib = None
 LAUNCHES = 0         # C-ABI compute calls issued by this process
 KERNEL_LAUNCHES = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18, "vfd_resize_frames_u8": 4}
+_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18, "vfd_conv3d_wgrad_det": 3, "vfd_conv3d_wgrad_thin_det": 2, "vfd_resize_frames_u8": 4}
 
 
 def build(force=False):
@@ -98,6 +102,8 @@ def lib():
             fn.restype = ctypes.c_int
         L.vfd_video_to_flow_workspace.restype = ctypes.c_longlong
         L.vfd_roc_auc_large_workspace.restype = ctypes.c_longlong
+        L.vfd_conv3d_wgrad_det_workspace.restype = ctypes.c_longlong
+        L.vfd_conv3d_wgrad_thin_det_workspace.restype = ctypes.c_longlong
         L.vfd_resize_frames_u8_workspace.restype = ctypes.c_longlong
         _lib = L
     return _lib

@@ -744,6 +744,7 @@ struct WgradParams {
   int co_pad;           // leading dimension of the accumulation buffer
   int ci_pad;
   float* acc;           // [ntaps][ci_pad][co_pad] fp32, accumulated with red.add
+  long long det_stride; // deterministic mode: split s adds into acc + s * det_stride (0 = all splits into acc)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -866,7 +867,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         for (int i = 0; i < 16; ++i) {
           const int ci = ci0 + c + i;
           if (ci < p.cin)
-            atomicAdd(p.acc + (static_cast<size_t>(tap) * p.ci_pad + ci) * p.co_pad + co, v[i]);
+            atomicAdd(p.acc + static_cast<size_t>(split) * p.det_stride + (static_cast<size_t>(tap) * p.ci_pad + ci) * p.co_pad + co, v[i]);
         }
       }
     }
@@ -897,6 +898,7 @@ struct Wg2Params {
   int co_pad, ci_pad;
   int dbg;
   float* acc;
+  long long det_stride;   // deterministic mode: split s adds into acc + s * det_stride (0 = off)
 };
 
 template <int KHW>
@@ -1037,7 +1039,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int ci = ci0 + c + i;
-            if (ci < p.cin) atomicAdd(p.acc + (static_cast<size_t>(tap) * p.ci_pad + ci) * p.co_pad + co, v[i]);
+            if (ci < p.cin) atomicAdd(p.acc + static_cast<size_t>(split) * p.det_stride + (static_cast<size_t>(tap) * p.ci_pad + ci) * p.co_pad + co, v[i]);
           }
         }
       }
@@ -1072,6 +1074,7 @@ struct Wg3Params {
   int co_pad, ci_pad;
   int dbg;
   float* acc;
+  long long det_stride;   // deterministic mode: split s adds into acc + s * det_stride (0 = off)
 };
 
 template <int KHW>
@@ -1214,7 +1217,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int co = co0 + c + i;
-            if (co < p.cout) atomicAdd(p.acc + (static_cast<size_t>(tap) * p.co_pad + co) * p.ci_pad + ci, v[i]);
+            if (co < p.cout) atomicAdd(p.acc + static_cast<size_t>(split) * p.det_stride + (static_cast<size_t>(tap) * p.co_pad + co) * p.ci_pad + ci, v[i]);
           }
         }
       }
@@ -1244,6 +1247,7 @@ struct WgtParams {
   int co_pad, ci_pad;
   int dbg;
   float* acc;            // [3][ci_pad][co_pad]
+  long long det_stride;  // deterministic mode: split s adds into acc + s * det_stride (0 = off)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -1404,7 +1408,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int ci = ci0 + c + i;
-            if (ci < p.cin) atomicAdd(p.acc + (static_cast<size_t>(a) * p.ci_pad + ci) * p.co_pad + co, v[i]);
+            if (ci < p.cin) atomicAdd(p.acc + static_cast<size_t>(split) * p.det_stride + (static_cast<size_t>(a) * p.ci_pad + ci) * p.co_pad + co, v[i]);
           }
         }
       }
@@ -1845,7 +1849,7 @@ VFD_API int vfd_conv3d_wgrad_layout(int cout, int cin, int kd, int kh, int kw, i
 
 static int launch_wgrad3(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin,
                          float* acc, int co_pad, int ci_pad, int N, int D, int H, int W, int kd, int kh,
-                         const WgradPlan& w, cudaStream_t stream) {
+                         const WgradPlan& w, cudaStream_t stream, long long det_stride, int* splits_out) {
   Wg3Params q;
   q.N = N; q.D = D; q.H = H; q.W = W;
   q.tilesW = (W + 7) / 8; q.tilesH = (H + 15) / 16;
@@ -1869,7 +1873,8 @@ static int launch_wgrad3(const void* dy, long long dy_ld, int cout, const void* 
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
   q.splits = (int)splits;
-  q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+  if (splits_out != nullptr) { *splits_out = q.splits; return 0; }
+  q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg; q.det_stride = det_stride;
   const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
   CUtensorMap tmDY, tmX;
   if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
@@ -1887,11 +1892,16 @@ static int launch_wgrad3(const void* dy, long long dy_ld, int cout, const void* 
   return check_launch("conv_wgrad3");
 }
 
-VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const void* x,
-                                long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int layout, int N,
-                                int D, int H, int W, int kd, int kh, int kw, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+// One body for the three entry points: the plain launch (det_stride = 0, splits_out = nullptr), the split-count
+// query of the deterministic variant (splits_out != nullptr: nothing is launched) and its launch (acc = the partial
+// buffers, det_stride = elements per partial).
+static int wgrad_dispatch(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin,
+                          float* acc, int co_pad, int ci_pad, int layout, int N, int D, int H, int W, int kd, int kh,
+                          int kw, cudaStream_t stream, long long det_stride, int* splits_out) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) {
+    if (splits_out != nullptr) *splits_out = 0;
+    return 0;
+  }
   if (co_pad < cout || ci_pad < cin) return set_error(VFD_ERR_ARG, "conv3d_wgrad: bad acc padding");
   if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
     return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
@@ -1899,7 +1909,7 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
     if (!vfd_conv3d_wgrad_layout(cout, cin, kd, kh, kw, H, W))
       return set_error(VFD_ERR_ARG, "conv3d_wgrad: layout 1 ([tap][co][ci]) only as reported by vfd_conv3d_wgrad_layout");
     return launch_wgrad3(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, N, D, H, W, kd, kh,
-                         plan_wgrad(cout, cin, kh), stream);
+                         plan_wgrad(cout, cin, kh), stream, det_stride, splits_out);
   }
   if (layout != 0) return set_error(VFD_ERR_ARG, "conv3d_wgrad: layout must be 0 or 1");
   if (kd == 3 && kh == 1 && kw == 1 && wgrad_t_enabled() && wgrad_halo_ok(H, W, 1, 1) && D >= 2) {
@@ -1928,7 +1938,8 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
       if (splits > columns) splits = columns;
       if (splits < 1) splits = 1;
       q.splits = (int)splits;
-      q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+      if (splits_out != nullptr) { *splits_out = q.splits; return 0; }
+      q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg; q.det_stride = det_stride;
       const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
       CUtensorMap tmDY, tmX;
       if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
@@ -1978,7 +1989,8 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
         if (splits > chunks) splits = chunks;
         if (splits < 1) splits = 1;
         q.splits = (int)splits;
-        q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg;
+        if (splits_out != nullptr) { *splits_out = q.splits; return 0; }
+        q.co_pad = co_pad; q.ci_pad = ci_pad; q.acc = acc; q.dbg = g_dbg; q.det_stride = det_stride;
         const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
         CUtensorMap tmDY, tmX;
         if (int e = make_act_map(&tmDY, dy, dy_ld, dy_ch, N, D, H, W, 64, 8, 16, 1, 1)) return e;
@@ -2010,6 +2022,7 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   p.co_pad = co_pad;
   p.ci_pad = ci_pad;
   p.acc = acc;
+  p.det_stride = det_stride;
   const int nb_slots = (p.block_n + 63) / 64;
   const int stage_bytes = (2 + nb_slots) * kWgBoxBytes;
   int stages = kSmemBudget / stage_bytes;
@@ -2022,6 +2035,7 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
+  if (splits_out != nullptr) { *splits_out = p.splits; return 0; }
   // cin/cout here are the valid counts; the TMA maps expose the channel-padded widths
   const int dy_ch = (cout + 7) & ~7, x_ch = (cin + 7) & ~7;
   CUtensorMap tmDY, tmX;
@@ -2040,4 +2054,58 @@ VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const vo
   const long long grid = base * p.splits;
   conv_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, smem, stream>>>(tmDY, tmX, p);
   return check_launch("conv_wgrad_tc");
+}
+
+VFD_API int vfd_conv3d_wgrad(const void* dy, long long dy_ld, int cout, const void* x,
+                                long long x_ld, int cin, float* acc, int co_pad, int ci_pad, int layout, int N,
+                                int D, int H, int W, int kd, int kh, int kw, void* stream_) {
+  return wgrad_dispatch(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, layout, N, D, H, W, kd, kh, kw,
+                        reinterpret_cast<cudaStream_t>(stream_), 0, nullptr);
+}
+
+// ---- deterministic variant: per-split partial accumulators + an ordered second pass -------------------------------
+namespace vfd {
+namespace {
+// acc[i] += partial[0][i] + partial[1][i] + ... in split order (one thread per element, coalesced over i)
+__global__ void __launch_bounds__(256)
+wgrad_ordered_reduce_kernel(const float* __restrict__ partial, long long elems, int splits, float* __restrict__ acc) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < elems; i += gridDim.x * 256ll) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[static_cast<size_t>(k) * elems + i];
+    acc[i] += s;
+  }
+}
+}  // namespace
+}  // namespace vfd
+
+VFD_API long long vfd_conv3d_wgrad_det_workspace(int cout, int cin, int co_pad, int ci_pad, int layout, int N, int D,
+                                                 int H, int W, int kd, int kh, int kw) {
+  int splits = 0;
+  if (wgrad_dispatch(nullptr, 0, cout, nullptr, 0, cin, nullptr, co_pad, ci_pad, layout, N, D, H, W, kd, kh, kw,
+                     nullptr, 0, &splits))
+    return -1;
+  return 4ll * splits * kd * kh * kw * co_pad * ci_pad;
+}
+
+VFD_API int vfd_conv3d_wgrad_det(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin,
+                                 float* acc, int co_pad, int ci_pad, int layout, int N, int D, int H, int W, int kd,
+                                 int kh, int kw, void* workspace, long long ws_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int splits = 0;
+  if (int e = wgrad_dispatch(nullptr, 0, cout, nullptr, 0, cin, nullptr, co_pad, ci_pad, layout, N, D, H, W, kd, kh,
+                             kw, nullptr, 0, &splits))
+    return e;
+  if (splits == 0) return 0;
+  const long long elems = (long long)kd * kh * kw * co_pad * ci_pad;
+  if (workspace == nullptr || ws_bytes < 4ll * splits * elems || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_det: workspace too small (vfd_conv3d_wgrad_det_workspace)");
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, 4ull * splits * elems, stream);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "conv3d_wgrad_det: memset");
+  if (int e = wgrad_dispatch(dy, dy_ld, cout, x, x_ld, cin, static_cast<float*>(workspace), co_pad, ci_pad, layout, N,
+                             D, H, W, kd, kh, kw, stream, elems, nullptr))
+    return e;
+  long long blocks = (elems + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_ordered_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), elems, splits, acc);
+  return check_launch("wgrad_ordered_reduce");
 }

@@ -76,7 +76,8 @@ struct Fold {
 template <int MT, int NT, typename FX = NoFold, typename FY = NoFold>
 __global__ void __launch_bounds__(kThinThreads)
 thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const bf16* __restrict__ x,
-                  long long x_ld, int cin, float* __restrict__ acc, int co_pad, long long V, FoldGeom fg) {
+                  long long x_ld, int cin, float* __restrict__ acc, int co_pad, long long V, FoldGeom fg,
+                  float* __restrict__ partial) {
   const int xchunks = (cin + 7) >> 3;   // 16-byte chunks that exist in a (folded) row of x (dy has exactly NT)
   __shared__ __align__(16) uint8_t tiles[kThinThreads / 32][2][16 * kThinRowBytes];
   __shared__ float red[32 * 32];
@@ -169,22 +170,28 @@ thin_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
     }
   }
 
-  // block reduction, then one atomic per valid element
+  // block reduction in warp order (every lane of a warp owns distinct elements, so the sum does not depend on
+  // timing), then one atomic per valid element -- or, in deterministic mode, the block's own partial slot
   const int g = lane >> 2, t = lane & 3;
+  for (int w = 0; w < kThinThreads / 32; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int ci = 16 * m + g, co = 8 * n + 2 * t;
-      atomicAdd(&red[ci * 32 + co], c[m][n][0]);
-      atomicAdd(&red[ci * 32 + co + 1], c[m][n][1]);
-      atomicAdd(&red[(ci + 8) * 32 + co], c[m][n][2]);
-      atomicAdd(&red[(ci + 8) * 32 + co + 1], c[m][n][3]);
+        for (int n = 0; n < NT; ++n) {
+          const int ci = 16 * m + g, co = 8 * n + 2 * t;
+          red[ci * 32 + co] += c[m][n][0];
+          red[ci * 32 + co + 1] += c[m][n][1];
+          red[(ci + 8) * 32 + co] += c[m][n][2];
+          red[(ci + 8) * 32 + co + 1] += c[m][n][3];
+        }
     }
-  __syncthreads();
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < 32 * 32; i += kThinThreads) {
     const int ci = i >> 5, co = i & 31;
-    if (ci < cin && co < cout) atomicAdd(acc + static_cast<size_t>(ci) * co_pad + co, red[i]);
+    if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * 1024 + i] = red[i];
+    else if (ci < cin && co < cout) atomicAdd(acc + static_cast<size_t>(ci) * co_pad + co, red[i]);
   }
 }
 
@@ -280,8 +287,9 @@ tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __
 // lanes loading on such rows and ran at 1.5 TB/s.
 __global__ void __launch_bounds__(256)
 tiny_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const bf16* __restrict__ x, long long x_ld,
-                  int cin, float* __restrict__ acc, int co_pad, long long V) {
+                  int cin, float* __restrict__ acc, int co_pad, long long V, float* __restrict__ partial) {
   __shared__ float red[64];
+  __shared__ float wred[8][64];
   float p[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -326,12 +334,16 @@ tiny_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const 
       float a = p[i][j];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&red[i * 8 + j], a);
+      if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5][i * 8 + j] = a;
     }
   __syncthreads();
   if (threadIdx.x < 64) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += wred[w][threadIdx.x];      // warp order: independent of timing
     const int ci = threadIdx.x >> 3, co = threadIdx.x & 7;
-    if (ci < cin && co < cout) atomicAdd(acc + (size_t)ci * co_pad + co, red[threadIdx.x]);
+    if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * 64 + threadIdx.x] = a;
+    else if (ci < cin && co < cout) atomicAdd(acc + (size_t)ci * co_pad + co, a);
   }
 }
 
@@ -356,18 +368,20 @@ static FastDivT make_fastdivt(uint32_t d) {
 
 // fold: 0 = none; 1 = x is folded on the fly (x holds cs channels per voxel, cin = taps * cs);
 //       2 = dy is folded on the fly (dy holds cs channels per voxel, cout = taps * cs)
-VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
-                                     int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
-                                     int H, int W, int kd, int kh, int kw, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// partial == nullptr: blocks add into acc with atomics. Otherwise every block writes its 32 x 32 (tiny kernel: 8 x 8)
+// result into its own slot of `partial` and *blocks_out / *slot_out tell the caller how many slots of which size.
+static int thin_dispatch(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, int cin, float* acc,
+                         int co_pad, int ci_pad, int fold, int cs, int N, int D, int H, int W, int kd, int kh, int kw,
+                         cudaStream_t stream, float* partial, int* blocks_out, int* slot_out, bool query) {
   const long long V = (long long)N * D * H * W;
+  if (blocks_out != nullptr) *blocks_out = 0;
   if (V <= 0) return 0;
   if (V >= (1LL << 31)) return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: more than 2^31 voxels");
   if (cout < 1 || cout > 32 || cin < 1 || cin > 32 || co_pad < cout || ci_pad < cin)
     return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: needs 1 <= cin, cout <= 32 and a large enough accumulator");
   const int x_need = fold == 1 ? ((cs + 7) & ~7) : ((cin + 7) & ~7), y_need = fold == 2 ? ((cs + 7) & ~7) : ((cout + 7) & ~7);
-  if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (dy_ld % 8) || (x_ld % 8) ||
-      dy_ld < y_need || x_ld < x_need)
+  if (!query && ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (dy_ld % 8) || (x_ld % 8) ||
+      dy_ld < y_need || x_ld < x_need))
     return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: tensors must be 16-byte aligned channels-last bf16");
   const int taps = kd * kh * kw;
   if ((fold == 1 && cin != taps * cs) || (fold == 2 && cout != taps * cs) || fold < 0 || fold > 2)
@@ -378,13 +392,17 @@ VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, con
   if (fold == 0 && cin <= 8 && cout <= 8) {   // 32 bytes per voxel: the one-thread-per-voxel kernel
     long long blocks = (V + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks_out != nullptr) { *blocks_out = (int)blocks; *slot_out = 64; }
+    if (query) return 0;
     tiny_wgrad_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)dy, dy_ld, cout, (const bf16*)x, x_ld, cin, acc,
-                                                       co_pad, V);
+                                                       co_pad, V, partial);
     return check_launch("tiny_wgrad");
   }
   const int mt = (cin + 15) / 16, nt = (cout + 7) / 8;
   const int grid = 148 * 4;
-#define VFD_THIN_ARGS (const bf16*)dy, dy_ld, cout, (const bf16*)x, x_ld, cin, acc, co_pad, V, fg
+  if (blocks_out != nullptr) { *blocks_out = grid; *slot_out = 1024; }
+  if (query) return 0;
+#define VFD_THIN_ARGS (const bf16*)dy, dy_ld, cout, (const bf16*)x, x_ld, cin, acc, co_pad, V, fg, partial
 #define VFD_THIN(MT, NT, FX, FY)                                                                  \
   if (mt == MT && nt == NT) {                                                                     \
     thin_wgrad_kernel<MT, NT, FX, FY><<<grid, kThinThreads, 0, stream>>>(VFD_THIN_ARGS);           \
@@ -409,6 +427,59 @@ VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, con
 #undef VFD_THIN
 #undef VFD_THIN_ARGS
   return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin: unsupported tile shape / fold combination");
+}
+
+VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
+                                     int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
+                                     int H, int W, int kd, int kh, int kw, void* stream_) {
+  return thin_dispatch(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, fold, cs, N, D, H, W, kd, kh, kw,
+                       reinterpret_cast<cudaStream_t>(stream_), nullptr, nullptr, nullptr, false);
+}
+
+namespace vfd {
+namespace {
+// acc[ci][co] += slot 0 + slot 1 + ... in block order; slot = `side` x `side` row-major
+__global__ void thin_ordered_reduce_kernel(const float* __restrict__ partial, int blocks, int side, int cin, int cout,
+                                           float* __restrict__ acc, int co_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= side * side) return;
+  const int ci = i / side, co = i % side;
+  if (ci >= cin || co >= cout) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partial[static_cast<size_t>(b) * side * side + i];
+  acc[static_cast<size_t>(ci) * co_pad + co] += s;
+}
+}  // namespace
+}  // namespace vfd
+
+VFD_API long long vfd_conv3d_wgrad_thin_det_workspace(int cout, int cin, int fold, int cs, int N, int D, int H, int W,
+                                                      int kd, int kh, int kw) {
+  int blocks = 0, slot = 0;
+  if (thin_dispatch(nullptr, 0, cout, nullptr, 0, cin, nullptr, 32, 32, fold, cs, N, D, H, W, kd, kh, kw, nullptr,
+                    nullptr, &blocks, &slot, true))
+    return -1;
+  return 4ll * blocks * slot;
+}
+
+VFD_API int vfd_conv3d_wgrad_thin_det(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld,
+                                      int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
+                                      int H, int W, int kd, int kh, int kw, void* workspace, long long ws_bytes,
+                                      void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int blocks = 0, slot = 0;
+  if (int e = thin_dispatch(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, fold, cs, N, D, H, W, kd, kh, kw,
+                            stream, nullptr, &blocks, &slot, true))
+    return e;
+  if (blocks == 0) return 0;
+  if (workspace == nullptr || ws_bytes < 4ll * blocks * slot || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_thin_det: workspace too small (vfd_conv3d_wgrad_thin_det_workspace)");
+  if (int e = thin_dispatch(dy, dy_ld, cout, x, x_ld, cin, acc, co_pad, ci_pad, fold, cs, N, D, H, W, kd, kh, kw,
+                            stream, static_cast<float*>(workspace), &blocks, &slot, false))
+    return e;
+  const int side = slot == 64 ? 8 : 32;
+  thin_ordered_reduce_kernel<<<(side * side + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(workspace), blocks,
+                                                                          side, cin, cout, acc, co_pad);
+  return check_launch("thin_ordered_reduce");
 }
 
 // Internal (called from vfd_conv3d_fwd): 1x1x1, <= 8 input and <= 8 output channels, bf16 output.

@@ -128,6 +128,13 @@ def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     if direct:
         _lib.call_debug("vfd_conv3d_wgrad_direct", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(),
                   co_pad, ci_pad, N, D, H, W, kd, kh, kw, _stream())
+    elif DETERMINISTIC:
+        need = int(_lib.lib().vfd_conv3d_wgrad_det_workspace(cout, cin, co_pad, ci_pad, layout, N, D, H, W, kd, kh, kw))
+        if need < 0:
+            raise RuntimeError("conv3d_wgrad_det: " + _lib.lib().vfd_last_error().decode())
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dy.device)
+        _lib.call("vfd_conv3d_wgrad_det", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
+                  ci_pad, layout, N, D, H, W, kd, kh, kw, ws.data_ptr(), ws.numel(), _stream())
     else:
         _lib.call("vfd_conv3d_wgrad", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
                   ci_pad, layout, N, D, H, W, kd, kh, kw, _stream())
@@ -137,6 +144,14 @@ def _conv3d_wgrad_thin(dy, cout, x, cin, acc, fold=0, cs=0, kd=1, kh=1, kw=1):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad_thin dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad_thin x")
     _, ci_pad, co_pad = acc.shape
+    if DETERMINISTIC:
+        need = int(_lib.lib().vfd_conv3d_wgrad_thin_det_workspace(cout, cin, fold, cs, N, D, H, W, kd, kh, kw))
+        if need < 0:
+            raise RuntimeError("conv3d_wgrad_thin_det: " + _lib.lib().vfd_last_error().decode())
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dy.device)
+        _lib.call("vfd_conv3d_wgrad_thin_det", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(),
+                  co_pad, ci_pad, fold, cs, N, D, H, W, kd, kh, kw, ws.data_ptr(), ws.numel(), _stream())
+        return
     _lib.call("vfd_conv3d_wgrad_thin", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, cin, acc.data_ptr(), co_pad,
               ci_pad, fold, cs, N, D, H, W, kd, kh, kw, _stream())
 
@@ -406,6 +421,16 @@ roc_auc_large_op = _define("roc_auc_large(Tensor scores, Tensor labels, Tensor(a
 # ------------------------------------------------------------------------------------------------
 # helpers shared by the autograd functions
 # ------------------------------------------------------------------------------------------------
+# Weight gradients through per-split partial accumulators and an ordered second pass instead of fp32 atomics
+# (vfd_conv3d_wgrad_det / vfd_conv3d_wgrad_thin_det): run-to-run identical bits, a few percent slower.
+DETERMINISTIC = os.environ.get("VFD_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic(on=True):
+    global DETERMINISTIC
+    DETERMINISTIC = bool(on)
+
+
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
