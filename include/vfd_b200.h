@@ -151,8 +151,9 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
  * yields every tap's gradient from dense MMAs. */
 VFD_API int vfd_tap_gather(const void* src, long long src_ld, int cs, void* dst, long long dst_ld, int dst_cols,
                            int N, int D, int H, int W, int kd, int kh, int kw, int sign, void* stream);
-/* out[c] += sum_v x[v][c]  (conv bias gradient when no BatchNorm follows) */
-VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream);
+/* out[c] += sum_v x[v][c]  (conv bias gradient when no BatchNorm follows); double accumulators: the blocks' fp32
+ * partial sums add up exactly, so the result does not depend on the order of the atomics */
+VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, double* out, void* stream);
 
 /* ---- nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) + torch.cat -------------------
  * (models/mygannet.py:50,77-94). Forward writes straight into a channel slice of the concat

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared - {"vfd_last_error", "vfd_abi_version"} == set(_lib.SIGNATURES)
     lib.vfd_abi_version.restype = ctypes.c_int
-    assert lib.vfd_abi_version() == 2
+    assert lib.vfd_abi_version() == 3
     # test-only kernels and debug switches live in the debug library, not in the product ABI
     for name in _lib.DEBUG_SIGNATURES:
         assert not hasattr(lib, name), name
@@ -194,3 +194,18 @@ def test_public_header_is_plain_c(tmp_path):
         assert r.returncode == 0, r.stderr
     text = open(os.path.join(root, "include", "vfd_b200.h")).read()
     assert "at::" not in text and "c10::" not in text and "#include <torch" not in text
+
+
+def test_step_context_refuses_a_second_concurrent_step():
+    """The per-step state (gradient sinks, arena) is process-wide because autograd runs backward nodes on its own
+    threads; starting a second fused step while one is active must fail loudly, not interleave."""
+    import torch
+    from vfd_gan_b200 import ops
+    ops.STEP.begin(torch.device("cpu"))
+    try:
+        with pytest.raises(RuntimeError, match="not re-entrant"):
+            ops.STEP.begin(torch.device("cpu"))
+    finally:
+        ops.STEP.end()
+    ops.STEP.begin(torch.device("cpu"))
+    ops.STEP.end()

@@ -1,6 +1,8 @@
-python -m pytest tests/test_data_gpu.py -x -q -m gpu -k training_state 2>&1 | tail -5 > gpurun_out/r2p_state_test.log
-python bench.py --steps 1 --warmup 3 --no-profile --no-cpu-baseline --no-flow > gpurun_out/r2p_b.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2p_launches_raw.csv python bench.py --steps 1 --warmup 3 --no-profile --no-cpu-baseline --no-flow > gpurun_out/r2p_ncu.log 2>&1
-python tools/launch_summary.py gpurun_out/r2p_launches_raw.csv gpurun_out/r2p > gpurun_out/r2p_summary.log 2>&1
-python tools/gpu_glue_trace.py > gpurun_out/r2p_glue.log 2>&1
-tail -3 gpurun_out/r2p_state_test.log; head -40 gpurun_out/r2p_step_kernel_summary.csv
+python -m pytest tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -40 > gpurun_out/r2r_parity.log
+tail -30 gpurun_out/r2r_parity.log
+for cfg in "VFD_DETERMINISTIC=0" "VFD_DETERMINISTIC=1"; do
+env $cfg python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile --no-flow > gpurun_out/r2r_bench_$cfg.json 2> gpurun_out/r2r_bench.err
+python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2r_bench_$cfg.json').read().strip().splitlines()[-1]); print('$cfg ms_per_step', d['ms_per_step'])"
+done

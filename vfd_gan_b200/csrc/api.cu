@@ -23,4 +23,4 @@ int check_launch(const char* kernel_name) {
 }  // namespace vfd
 
 VFD_API const char* vfd_last_error(void) { return vfd::g_err; }
-VFD_API int vfd_abi_version(void) { return 2; }
+VFD_API int vfd_abi_version(void) { return 3; }

@@ -74,8 +74,8 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
 // One accumulator tile (this warp's 32 TMEM lanes x block_n columns) -> bias, convert, store, and
 // optionally per-channel statistics into the CTA's shared accumulators. Warp-collective.
 __device__ __forceinline__ void epilogue_tile(const Epilogue& e, uint32_t tacc, int block_n, int col0,
-                                              bool valid, long long vox, int lane, float* s_sum,
-                                              float* s_sq) {
+                                              bool valid, long long vox, int lane, double* s_sum,
+                                              double* s_sq) {
   for (int c = 0; c < block_n; c += 32) {
     float v[32];
     if (c + 32 <= block_n) {
@@ -131,22 +131,24 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& e, uint32_t tacc, 
       const float cs = warp_colsum32(v, lane);
       const float cq = warp_colsum32(sq, lane);
       if (c + lane < block_n && col + lane < 1024) {
-        atomicAdd(&s_sum[col + lane], cs);
-        atomicAdd(&s_sq[col + lane], cq);
+        // double accumulators: sums of fp32 partials are exact there (24-bit mantissas, a few thousand summands), so
+        // the result does not depend on the order in which the epilogue warps arrive
+        atomicAdd(&s_sum[col + lane], static_cast<double>(cs));
+        atomicAdd(&s_sq[col + lane], static_cast<double>(cq));
       }
     }
   }
 }
 
 // After the last tile: the four epilogue warps publish the CTA's statistics.
-__device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_thread, const float* s_sum,
-                                                     const float* s_sq) {
+__device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_thread, const double* s_sum,
+                                                     const double* s_sq) {
   if (e.stats == nullptr) return;
   asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
   for (int j = epi_thread; j < e.stats_ld && j < 1024; j += 128) {
-    if (s_sum[j] != 0.f || s_sq[j] != 0.f) {
-      atomicAdd(e.stats + j, (double)s_sum[j]);
-      atomicAdd(e.stats + e.stats_ld + j, (double)s_sq[j]);
+    if (s_sum[j] != 0.0 || s_sq[j] != 0.0) {
+      atomicAdd(e.stats + j, s_sum[j]);
+      atomicAdd(e.stats + e.stats_ld + j, s_sq[j]);
     }
   }
 }
@@ -180,13 +182,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_sum[1024], s_sq[1024];
+  __shared__ double s_sum[1024], s_sq[1024];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
   if (p.epi.stats != nullptr)
-    for (int i = threadIdx.x; i < 1024; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.f;
+    for (int i = threadIdx.x; i < 1024; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.0;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -384,7 +386,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ uint64_t a_full[kResMaxASlots], a_empty[kResMaxASlots];
   __shared__ uint64_t b_full, acc_full[4], acc_empty[4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_sum[256], s_sq[256];
+  __shared__ double s_sum[256], s_sq[256];   // double: exact sums of the warps' fp32 partials, order-independent
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -410,7 +412,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 256; i += kRes2Threads) s_sum[i] = s_sq[i] = 0.f;
+  for (int i = threadIdx.x; i < 256; i += kRes2Threads) s_sum[i] = s_sq[i] = 0.0;
   if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -688,8 +690,8 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane < 4) {   // every accumulator row holds the same column sums: lanes 0-3 own columns 8n + 2t, +1
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
-            atomicAdd(&s_sum[8 * n + 2 * lane], msum[n][0]);
-            atomicAdd(&s_sum[8 * n + 2 * lane + 1], msum[n][1]);
+            atomicAdd(&s_sum[8 * n + 2 * lane], static_cast<double>(msum[n][0]));
+            atomicAdd(&s_sum[8 * n + 2 * lane + 1], static_cast<double>(msum[n][1]));
           }
         }
         // Gram diagonals: accumulator element (row g [+8], column 2t + j) is on the diagonal when g == 2t + j
@@ -697,25 +699,25 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (dj == 0 || dj == 1) {
 #pragma unroll
           for (int np = 0; np < 2; ++np) {
-            atomicAdd(&s_sq[16 * np + gq], dj ? msq[2 * np][1] : msq[2 * np][0]);
-            atomicAdd(&s_sq[16 * np + 8 + gq], dj ? msq[2 * np + 1][3] : msq[2 * np + 1][2]);
+            atomicAdd(&s_sq[16 * np + gq], static_cast<double>(dj ? msq[2 * np][1] : msq[2 * np][0]));
+            atomicAdd(&s_sq[16 * np + 8 + gq], static_cast<double>(dj ? msq[2 * np + 1][3] : msq[2 * np + 1][2]));
           }
         }
       } else {
 #pragma unroll
         for (int i = 0; i < kMaxChunks; ++i)
           if (i < p.nchunks) {
-            atomicAdd(&s_sum[i * 32 + 2 * cp], ssum[i][0]);
-            atomicAdd(&s_sum[i * 32 + 2 * cp + 1], ssum[i][1]);
-            atomicAdd(&s_sq[i * 32 + 2 * cp], ssq[i][0]);
-            atomicAdd(&s_sq[i * 32 + 2 * cp + 1], ssq[i][1]);
+            atomicAdd(&s_sum[i * 32 + 2 * cp], static_cast<double>(ssum[i][0]));
+            atomicAdd(&s_sum[i * 32 + 2 * cp + 1], static_cast<double>(ssum[i][1]));
+            atomicAdd(&s_sq[i * 32 + 2 * cp], static_cast<double>(ssq[i][0]));
+            atomicAdd(&s_sq[i * 32 + 2 * cp + 1], static_cast<double>(ssq[i][1]));
           }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       const int j = ew * 32 + lane;
-      if (j < p.stats_ld && j < p.nchunks * 32 && (s_sum[j] != 0.f || s_sq[j] != 0.f)) {
-        atomicAdd(p.stats + j, (double)s_sum[j]);
-        atomicAdd(p.stats + p.stats_ld + j, (double)s_sq[j]);
+      if (j < p.stats_ld && j < p.nchunks * 32 && (s_sum[j] != 0.0 || s_sq[j] != 0.0)) {
+        atomicAdd(p.stats + j, s_sum[j]);
+        atomicAdd(p.stats + p.stats_ld + j, s_sq[j]);
       }
     }
   }
@@ -1569,7 +1571,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel<KC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024);   // + 16.2 KB static
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_tc)");
     attr_set = true;
   }
@@ -1580,7 +1582,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   return check_launch("conv_fwd_tc");
 }
 
-constexpr int kResBudget = 223 * 1024;
+constexpr int kResBudget = 221 * 1024;   // + 1 KB alignment slack + ~4.3 KB static (fp64 statistics) <= 227 KB
 
 // 5-D map over the conv output for the epilogue's TMA stores: box = 32 channels x 8 (w) x 4 (h) voxels,
 // i.e. the 32 accumulator rows one epilogue warp owns.
@@ -1679,7 +1681,7 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC, KHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         224 * 1024);
+                                         222 * 1024);
     if (e != cudaSuccess) {
       *err = set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_res)");
       return 0;

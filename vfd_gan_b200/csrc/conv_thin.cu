@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256)
 tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __restrict__ w_packed, int cin_k,
                       const float* __restrict__ bias, bf16* __restrict__ out, long long out_ld, long long V,
                       double* __restrict__ stats, int stats_ld) {
-  __shared__ float s_stat[16];
+  __shared__ double s_stat[16];   // exact sums of the warps' fp32 partials: order-independent
   float w[8][8], b[8], ssum[8], ssq[8];
 #pragma unroll
   for (int co = 0; co < 8; ++co) {
@@ -214,7 +214,7 @@ tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) w[co][ci] = __bfloat162float(w_packed[co * cin_k + ci]);
   }
-  if (threadIdx.x < 16) s_stat[threadIdx.x] = 0.f;
+  if (threadIdx.x < 16) s_stat[threadIdx.x] = 0.0;
   __syncthreads();
   // 32 bytes per voxel: four voxels per iteration with their loads issued together, or a thread has a single
   // 16-byte load in flight and the kernel is latency bound (2.7 TB/s measured with one voxel per iteration)
@@ -268,15 +268,15 @@ tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __
         q += __shfl_xor_sync(0xffffffffu, q, off);
       }
       if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_stat[c], a);
-        atomicAdd(&s_stat[8 + c], q);
+        atomicAdd(&s_stat[c], static_cast<double>(a));
+        atomicAdd(&s_stat[8 + c], static_cast<double>(q));
       }
     }
     __syncthreads();
     if (threadIdx.x < 16) {
       const int c = threadIdx.x & 7;
-      const float val = s_stat[threadIdx.x];
-      if (c < stats_ld && val != 0.f) atomicAdd(stats + (threadIdx.x < 8 ? 0 : stats_ld) + c, (double)val);
+      const double val = s_stat[threadIdx.x];
+      if (c < stats_ld && val != 0.0) atomicAdd(stats + (threadIdx.x < 8 ? 0 : stats_ld) + c, val);
     }
   }
 }

@@ -197,11 +197,11 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __rest
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
                 double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ double sh[];  // [2][C]; double: exact sums of the threads' fp32 partials, order-independent
   const int CG = C / 8;
   const int rows_per_iter = 256 / CG;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.0;
   __syncthreads();
   const bool active = tid < rows_per_iter * CG;
   const int cg = tid % CG;
@@ -238,12 +238,12 @@ bn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], s[j]);
-      atomicAdd(&sh[C + cg * 8 + j], ss[j]);
+      atomicAdd(&sh[cg * 8 + j], static_cast<double>(s[j]));
+      atomicAdd(&sh[C + cg * 8 + j], static_cast<double>(ss[j]));
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&sums[i], sh[i]);
 }
 
 // sums -> (mean, invstd, scale, shift), running-stat update, and clears the accumulator.
@@ -904,12 +904,12 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
 // Per-channel sum over voxels of a channels-last bf16 tensor (conv bias gradient).
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
-                   float* __restrict__ out) {
-  extern __shared__ float sh[];  // [C]
+                   double* __restrict__ out) {
+  extern __shared__ double sh[];  // [C]; double (shared and global): exact, order-independent sums of fp32 partials
   const int CG = C / 8;
   const int rows_per_iter = 256 / CG;
   const int tid = threadIdx.x;
-  for (int i = tid; i < C; i += 256) sh[i] = 0.f;
+  for (int i = tid; i < C; i += 256) sh[i] = 0.0;
   __syncthreads();
   const int cg = tid % CG;
   const int rl = tid / CG;
@@ -927,7 +927,7 @@ channel_sum_kernel(const bf16* __restrict__ x, long long ld, int C, long long V,
       for (int j = 0; j < 8; ++j) s[j] += v[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cg * 8 + j], s[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cg * 8 + j], static_cast<double>(s[j]));
   }
   __syncthreads();
   for (int i = tid; i < C; i += 256) atomicAdd(&out[i], sh[i]);
@@ -1611,7 +1611,7 @@ static int stats_grid(long long V, int C) {
 VFD_API int vfd_bn_stats(const void* x, long long ld, int C, long long V, double* sums, void* stream_) {
   if (int e = check_cl(x, ld, C, "bn_stats: bad tensor")) return e;
   if (V <= 0) return 0;
-  bn_stats_kernel<<<stats_grid(V, C), 256, 2 * C * sizeof(float), STREAM>>>((const bf16*)x, ld, C, V, sums);
+  bn_stats_kernel<<<stats_grid(V, C), 256, 2 * C * sizeof(double), STREAM>>>((const bf16*)x, ld, C, V, sums);
   return check_launch("bn_stats");
 }
 
@@ -1841,10 +1841,10 @@ VFD_API int vfd_tap_gather(const void* src, long long src_ld, int cs, void* dst,
   return set_error(VFD_ERR_ARG, "tap_gather: unsupported (kernel, channels-per-tap) combination");
 }
 
-VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, float* out, void* stream_) {
+VFD_API int vfd_channel_sum(const void* x, long long ld, int C, long long V, double* out, void* stream_) {
   if (int e = check_cl(x, ld, C, "channel_sum: bad tensor")) return e;
   if (V <= 0) return 0;
-  channel_sum_kernel<<<stats_grid(V, C), 256, C * sizeof(float), STREAM>>>((const bf16*)x, ld, C, V, out);
+  channel_sum_kernel<<<stats_grid(V, C), 256, C * sizeof(double), STREAM>>>((const bf16*)x, ld, C, V, out);
   return check_launch("channel_sum");
 }
 

@@ -223,6 +223,8 @@ def _tap_gather(src, cs, dst, kd, kh, kw, sign):
 
 def _channel_sum(x, out):
     N, D, H, W, C, ld = _check_cl(x, "channel_sum input")
+    if out.dtype != torch.float64:
+        raise RuntimeError("channel_sum accumulates in float64")
     _lib.call("vfd_channel_sum", x.data_ptr(), ld, C, N * D * H * W, out.data_ptr(), _stream())
 
 
@@ -618,6 +620,11 @@ class StepContext:
         self.forked = False
 
     def begin(self, device, sink=None):
+        if self.active:
+            # autograd runs backward nodes on its own worker threads, so this state cannot be thread-local; the design
+            # is one process per GPU and one fused step at a time -- fail loudly instead of mixing two steps' sinks
+            raise RuntimeError("a fused train step is already running in this process: GanTrainStep / StcnnTrainStep "
+                               "are not re-entrant (one process per GPU)")
         self.active, self.sink = True, sink
         self.uses, self.touched, self.held, self.forked = {}, set(), [], False
         if self.async_wgrad and device.type == "cuda" and self.wstream is None:
@@ -951,8 +958,9 @@ class ConvFn(torch.autograd.Function):
                     STEP.first_touch(bias)
                     STEP.done(bias)
             else:
-                sums = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
+                sums = torch.zeros(g.shape[-1], dtype=torch.float64, device=g.device)
                 channel_sum(g, sums)
+                sums = sums.float()
                 if dst is None:
                     gb = sums[:cout].clone()
                 else:
