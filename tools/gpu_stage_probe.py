@@ -2,7 +2,9 @@
 (with / without fused BN statistics), dgrad and wgrad kernels with the TMA loads, the MMA issue and the
 epilogue switched off in turn. Diagnostics only; prints one table.
     python tools/gpu_stage_probe.py [layer ...]      layer = cin,cout,kd,kh,kw,N,D,H,W"""
+import os
 import sys
+os.environ["VFD_DEBUG_LIB"] = "1"   # route every op through libvfd_b200_debug.so: the switches act on what it launches
 import torch
 sys.path.insert(0, ".")
 from vfd_gan_b200 import ops, _lib
@@ -15,6 +17,10 @@ LAYERS = {
     "conv_last": (32, 1, 3, 3, 3, 32, 16, 112, 112),
     "T.dconv3.t": (54, 128, 3, 1, 1, 32, 4, 112, 112),
     "uconv2.s": (192, 172, 1, 3, 3, 32, 8, 56, 56),
+    "G.dconv1.s": (3, 21, 1, 3, 3, 32, 16, 112, 112),
+    "S.dconv1.s": (3, 14, 1, 3, 3, 32, 16, 112, 112),
+    "S.dconv2.s": (32, 43, 1, 3, 3, 32, 16, 56, 56),
+    "G.dconv1.t": (21, 32, 3, 1, 1, 32, 16, 112, 112),
 }
 import os
 FLAGS = [int(f) for f in os.environ.get("PROBE_FLAGS", "0,1,2,3,4,5,6,7").split(",")]

@@ -92,7 +92,9 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(vfd_gan_b200 has no CPU fallback)")
-        L = ctypes.CDLL(LIB_PATH)
+        # tools/gpu_stage_probe.py sets VFD_DEBUG_LIB=1: every entry point then comes from libvfd_b200_debug.so (a
+        # superset of the product library), whose stage-isolation switches act on the kernels it launches
+        L = ctypes.CDLL(DEBUG_LIB_PATH if os.environ.get("VFD_DEBUG_LIB") == "1" else LIB_PATH)
         L.vfd_last_error.restype = ctypes.c_char_p
         L.vfd_last_error.argtypes = []
         L.vfd_abi_version.restype = ctypes.c_int
@@ -113,6 +115,8 @@ def debug_lib():
     """libvfd_b200_debug.so: the product sources built with -DVFD_DEBUG plus the CUDA-core cross-check convs. Only
     tests/ and tools/ reach it (``ops.CONV_IMPL_DIRECT``, tools/gpu_stage_probe.py)."""
     global _debug_lib
+    if _debug_lib is None and os.environ.get("VFD_DEBUG_LIB") == "1":
+        _debug_lib = lib()     # one image, one set of switches
     if _debug_lib is None:
         if not os.path.exists(DEBUG_LIB_PATH):
             raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
