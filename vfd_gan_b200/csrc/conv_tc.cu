@@ -361,7 +361,7 @@ struct Res2Params {
   int a_slots, a_slot_bytes, a_box_bytes, b_tile_bytes;
   int acc_stages, acc_stride;  // TMEM columns per sub-tile accumulator; one stage = G * acc_stride columns
   int nchunks;                 // 32-column output chunks
-  int stage_bufs;              // staging buffers per epilogue warp (1 or 2)
+  int stage_bufs;              // staging buffers per epilogue warp (1, 2 or 4)
   int out_fp32;
   int n_rows;                  // valid bias entries
   int dbg;
@@ -369,6 +369,13 @@ struct Res2Params {
   double* stats;
   int stats_ld;
   int stage_bytes;             // bytes of one epilogue staging buffer (32 rows x 64 or 128 B)
+  // thin bf16 outputs (one 32-column chunk): the epilogue warps store their rows straight from registers (64 bytes per
+  // voxel, whole 32-byte sectors) instead of staging them for a TMA store -- a 2 KB box of 64-byte rows costs the TMA
+  // unit ~3 cycles per row, which made the store the slowest stage of the HBM-bound layers (profiles/r2_thin_epilogue.txt)
+  int direct_out;
+  void* out;
+  long long out_ld;            // elements
+  int out_cols;                // channels of the output tensor (multiple of 8)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -578,13 +585,39 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i)
                 if (ch * 32 + i < p.n_rows) v[i] += __ldg(p.bias + ch * 32 + i);
             }
+            uint8_t* sb = stg + buf * p.stage_bytes;
+            if (p.direct_out) {
+              uint4 pk[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                pk[c].x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+                pk[c].y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                pk[c].z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+                pk[c].w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+              }
+              if (hw_ok && !VFD_DBG(p, 8)) {
+                const long long vox = ((static_cast<long long>(n) * p.D + d) * p.H + (h0 + 4 * q + (lane >> 3))) * p.W +
+                                      (w0 + (lane & 7));
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (8 * c < p.out_cols) *reinterpret_cast<uint4*>(op + 8 * c) = pk[c];
+              }
+              if (mma_stats) {   // the statistics fragments come from the staged copy
+                __syncwarp();
+                uint8_t* rowp = sb + lane * 64;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(rowp + ((c ^ ((lane >> 1) & 3)) << 4)) = pk[c];
+                __syncwarp();
+              }
+            } else {
             // the staging buffer may still be the source of an earlier TMA store
             if (lane == 0 && !VFD_DBG(p, 8)) {
-              if (p.stage_bufs == 2) bulk_wait_group_read<1>();
+              if (p.stage_bufs == 4) bulk_wait_group_read<3>();
+              else if (p.stage_bufs == 2) bulk_wait_group_read<1>();
               else bulk_wait_group_read<0>();
             }
             __syncwarp();
-            uint8_t* sb = stg + buf * p.stage_bytes;
             if (p.out_fp32) {
               uint8_t* rowp = sb + lane * 128;
 #pragma unroll
@@ -608,6 +641,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0 && !VFD_DBG(p, 8)) {
               tma_store_5d(&tmC, sb, ch * 32, w0, h0 + 4 * q, d, n);
               bulk_commit_group();
+            }
             }
             if (mma_stats) {
               const uint32_t sb_s = smem_u32(sb);
@@ -672,7 +706,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   ssq[i][1] += q1;
                 }
             }
-            if (p.stage_bufs == 2) buf ^= 1;
+            buf = (buf + 1) & (p.stage_bufs - 1);
           }
         }
         tc_fence_before();
@@ -1642,9 +1676,14 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   const int stage_bytes = epi.out_fp32 ? 4096 : 2048;  // 32 rows x 128 / 64 B
   // pick (G, staging buffers): first choice with >= 3 input slots, else the first with >= 2
   int bestG = 0, bestBufs = 0, bestSlots = 0;
+  int max_bufs = 2;
+  if (const char* e = getenv("VFD_RES_BUFS")) {   // diagnostics: staging buffers per epilogue warp
+    const int f = atoi(e);
+    if (f == 1 || f == 2 || f == 4) max_bufs = f;
+  }
   for (int pass = 0; pass < 2 && !bestG; ++pass)
     for (int G = g0; G >= 1 && !bestG; G >>= 1)
-      for (int bufs = 2; bufs >= 1 && !bestG; --bufs) {
+      for (int bufs = max_bufs; bufs >= 1 && !bestG; bufs >>= 1) {
         if (G * p.acc_stride * 2 > 512) continue;
         const long long box = (long long)(G + kd - 1) * PWc * PHc * KC * 2;
         const long long slot = (box + 1023) & ~1023LL;
@@ -1672,6 +1711,14 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   p.stats = epi.stats;
   p.stats_ld = epi.stats_ld;
   p.stage_bytes = stage_bytes;
+  // measured (profiles/r2_thin_epilogue.txt): rows of <= 48 bytes gain 15-25 % from the direct store, full 64-byte
+  // rows lose 10-18 % (the TMA store is asynchronous, the register store holds the epilogue warp)
+  static const int direct_env = getenv("VFD_RES_DIRECT") ? atoi(getenv("VFD_RES_DIRECT")) : -1;
+  p.direct_out = p.nchunks == 1 && !epi.out_fp32 &&
+                 (direct_env == 1 || (direct_env != 0 && epi.out_cols <= 24));
+  p.out = epi.out;
+  p.out_ld = epi.out_ld;
+  p.out_cols = epi.out_cols;
   CUtensorMap tmA, tmB, tmC;
   if ((*err = make_act_map(&tmA, x, x_ld, cin, N, D, H, W, KC, PWc, PHc, p.G + kd - 1, 1))) return 0;
   if ((*err = make_weight_map(&tmB, w_packed, w_rows, (long long)ntaps * cin_k, KC, p.block_n))) return 0;
