@@ -1739,7 +1739,8 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   static const int force4 = getenv("VFD_BN_BWD4") ? atoi(getenv("VFD_BN_BWD4")) : 0;
   static const int gather = getenv("VFD_BN_GATHER") ? atoi(getenv("VFD_BN_GATHER")) : 0;
   const bool use_gather = gather && pd * ph * pw > 1 && !drop;
-  if ((ph == 1 && !force4) || use_gather) {
+  static const int pool8 = getenv("VFD_BN_BWD8_POOL") ? atoi(getenv("VFD_BN_BWD8_POOL")) : 0;   // experiment switch
+  if ((ph == 1 && !force4) || use_gather || (pool8 && ph == 2 && !drop && !pool_bcast)) {
     // un-pooled / depth-pooled: 8-channel window-per-thread kernels
     ActGeom g;
     if (use_gather) {
@@ -1754,7 +1755,11 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
     const int grid = win_grid(g, pd, ph, pw, nvi, 2);
 #define VFD_BWD8_LAUNCH(KERNEL, SMEM, ...)                                                             \
     do {                                                                                                \
-      if (pd == 1) {                                                                                    \
+      if (ph == 2 && pd == 1) {                                                                         \
+        KERNEL<1, 2, 2, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                               \
+      } else if (ph == 2) {                                                                             \
+        KERNEL<2, 2, 2, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                               \
+      } else if (pd == 1) {                                                                             \
         if (drop) KERNEL<1, 1, 1, true><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                      \
         else KERNEL<1, 1, 1, false><<<grid, 256, SMEM, STREAM>>>(__VA_ARGS__);                          \
       } else {                                                                                          \
