@@ -1739,8 +1739,12 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   static const int force4 = getenv("VFD_BN_BWD4") ? atoi(getenv("VFD_BN_BWD4")) : 0;
   static const int gather = getenv("VFD_BN_GATHER") ? atoi(getenv("VFD_BN_GATHER")) : 0;
   const bool use_gather = gather && pd * ph * pw > 1 && !drop;
-  static const int pool8 = getenv("VFD_BN_BWD8_POOL") ? atoi(getenv("VFD_BN_BWD8_POOL")) : 0;   // experiment switch
-  if ((ph == 1 && !force4) || use_gather || (pool8 && ph == 2 && !drop && !pool_bcast)) {
+  // (1,2,2) windows (SDisc) also take the 8-channel kernels: 0.435 -> 0.347 ms on the first SDisc block, step -0.5 ms
+  // (profiles/r2_negative_overlap_and_bn_mapping.txt); (2,2,2) windows measured equal and stay on the 4-channel ones
+  // (8 voxels x 16 bytes per thread spill). VFD_BN_BWD8_POOL = 0 / 2 forces neither / both.
+  static const int pool8 = getenv("VFD_BN_BWD8_POOL") ? atoi(getenv("VFD_BN_BWD8_POOL")) : 1;
+  const bool pooled8 = ph == 2 && !drop && !pool_bcast && ((pool8 == 1 && pd == 1) || pool8 == 2);
+  if ((ph == 1 && !force4) || use_gather || pooled8) {
     // un-pooled / depth-pooled: 8-channel window-per-thread kernels
     ActGeom g;
     if (use_gather) {
