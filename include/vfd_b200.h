@@ -136,14 +136,17 @@ VFD_API int vfd_bn_act_fwd(const void* y, long long y_ld, int N, int D, int H, i
  * c1 / c2: fp32 [C] scratch. train: bit 0 = training-mode BatchNorm (batch statistics); bit 1 = g_pool is
  * [N][D/pd][C] and broadcast over the H and W axes (the gradient of the global spatial mean of TDisc,
  * models/mygannet.py:175,189-191), only for windows (1,1,1) and (2,1,1); bit 2 = add to dgamma / dbeta instead of
- * overwriting them (a BatchNorm applied twice per step, NetD on the real and on the generated clip). */
+ * overwriting them (a BatchNorm applied twice per step, NetD on the real and on the generated clip).
+ * ticket (optional): a zeroed device counter; with it the reduce pass's last block derives dgamma / dbeta / c1 / c2
+ * itself (and leaves sums and the counter zero again) instead of a separate finalize launch. One counter must not be
+ * shared by calls that may run concurrently on different streams. */
 VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, int W, int C, int Cvalid,
                            const float* mean, const float* invstd, const float* scale,
                            const float* shift, float slope, const void* g_full, long long gf_ld,
                            const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
                            unsigned long long seed, const unsigned long long* seed_dev, int train,
                            double* sums, float* c1, float* c2, float* dgamma, float* dbeta, void* dy,
-                           long long dy_ld, void* stream);
+                           long long dy_ld, unsigned int* ticket, void* stream);
 /* Tap folding for the weight gradient of thin convs (autograd of nn.Conv3d, models/mygannet.py:311,344):
  * dst[v][t*cs + c] = src[v + sign*offset(t)][c] for the kd*kh*kw taps t and c < cs (zero outside the volume,
  * remaining columns zero; dst_cols = taps*cs rounded up to 8, <= 32). With taps folded into channels,

@@ -32,7 +32,7 @@ SIGNATURES = {
     "vfd_bn_finalize": [_p, _i, _i, _ll, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p],
     "vfd_bn_act_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i, _f, _ull, _p, _p],
     "vfd_bn_act_bwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _i, _i,
-                       _f, _ull, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p],
+                       _f, _ull, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _p],
     "vfd_tap_gather": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vfd_channel_sum": [_p, _ll, _i, _ll, _p, _p],
     "vfd_upsample2x_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p],
@@ -72,7 +72,7 @@ _debug_lib = None
 _lib = None
 LAUNCHES = 0         # C-ABI compute calls issued by this process
 KERNEL_LAUNCHES = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 3, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18, "vfd_conv3d_wgrad_det": 3, "vfd_conv3d_wgrad_thin_det": 2, "vfd_resize_frames_u8": 4}
+_KERNELS_PER_CALL = {"vfd_bn_act_bwd": 2, "vfd_upsample2x_bwd": 3, "vfd_roc_auc_large": 18, "vfd_conv3d_wgrad_det": 3, "vfd_conv3d_wgrad_thin_det": 2, "vfd_resize_frames_u8": 4}
 
 
 def build(force=False):

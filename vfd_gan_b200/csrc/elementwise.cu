@@ -524,6 +524,39 @@ struct BwdWindow8 {
   }
 };
 
+// Tail of both reduce kernels when a ticket counter is supplied: the block that finishes last (every block adds its
+// partials to `sums` with atomics, fences, then takes a ticket) turns the complete sums into dgamma / dbeta and the two
+// per-channel means of pass 2 and clears the accumulator and the ticket -- what bn_bwd_finalize_kernel does as a separate
+// launch otherwise (56 launches of ~3 us per train step on the critical path).
+struct BwdFinalize {
+  unsigned int* ticket;   // nullptr: the caller launches bn_bwd_finalize_kernel
+  int Cvalid, train, accumulate;
+  long long V;
+  float *dgamma, *dbeta, *c1, *c2;
+};
+__device__ __forceinline__ void bwd_finalize_by_last_block(const BwdFinalize& f, double* sums, int C) {
+  if (f.ticket == nullptr) return;
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sg = __ldcg(sums + c), sgx = __ldcg(sums + C + c);
+    if (c < f.Cvalid) {
+      f.dbeta[c] = f.accumulate ? f.dbeta[c] + (float)sg : (float)sg;
+      f.dgamma[c] = f.accumulate ? f.dgamma[c] + (float)sgx : (float)sgx;
+    }
+    f.c1[c] = f.train ? (float)(sg / (double)f.V) : 0.f;
+    f.c2[c] = f.train ? (float)(sgx / (double)f.V) : 0.f;
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+  }
+  if (threadIdx.x == 0) *f.ticket = 0u;
+}
+
 // Pass 1 of BN backward: per-channel sum(g) and sum(g * xhat).
 template <int PD, int PH, int PW, bool DROP>
 __global__ void __launch_bounds__(256, 2)
@@ -533,7 +566,7 @@ bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
                          float slope, const bf16* __restrict__ g_full, long long gf_ld,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                          unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
-                         double* __restrict__ sums) {
+                         double* __restrict__ sums, BwdFinalize fin) {
   __shared__ float part[16 * 256];  // [sum | sum*xhat][channel in group][thread]
   constexpr int NV = PD * PH * PW;
   constexpr int U = NV >= 4 ? 1 : 4 / NV;
@@ -596,6 +629,7 @@ bn_act_bwd8_reduce_kernel(const bf16* __restrict__ y, long long y_ld, ActGeom g,
     for (int wl = 0; wl < rpi; ++wl) acc += src[wl * CG];
     atomicAdd(&sums[i], (double)acc);
   }
+  bwd_finalize_by_last_block(fin, sums, C);
 }
 
 // Pass 2 of BN backward: dy = scale * (g - c1 - xhat * c2) = scale * g + (kb + kc * xhat)
@@ -764,7 +798,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
                          float slope, const bf16* __restrict__ g_full, long long gf_ld,
                          const bf16* __restrict__ g_pool, long long gp_ld, float drop_p,
                          unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
-                         double* __restrict__ sums) {
+                         double* __restrict__ sums, BwdFinalize fin) {
   __shared__ float part[8 * 256];  // [sum | sum*xhat][channel in group][thread]
   constexpr int NV = PH * PW;
   constexpr int U = 8 / NV;
@@ -824,6 +858,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, long long y_ld, BwdGeom g,
     for (int wl = 0; wl < rpi; ++wl) acc += src[wl * CG];
     atomicAdd(&sums[i], (double)acc);
   }
+  bwd_finalize_by_last_block(fin, sums, C);
 }
 
 // sums -> dgamma, dbeta and the two per-channel means used by pass 2; clears the accumulator.
@@ -1718,7 +1753,7 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
                               const void* g_pool, long long gp_ld, int pd, int ph, int pw, float drop_p,
                               unsigned long long seed, const unsigned long long* seed_dev, int train,
                               double* sums, float* c1, float* c2, float* dgamma, float* dbeta, void* dy,
-                              long long dy_ld, void* stream_) {
+                              long long dy_ld, unsigned int* ticket, void* stream_) {
   if (int e = check_cl(y, y_ld, C, "bn_act_bwd: bad input")) return e;
   if (int e = check_cl(dy, dy_ld, C, "bn_act_bwd: bad output")) return e;
   if (g_full && check_cl(g_full, gf_ld, C, "bn_act_bwd: bad full-resolution gradient")) return VFD_ERR_ARG;
@@ -1744,6 +1779,9 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
   // (8 voxels x 16 bytes per thread spill). VFD_BN_BWD8_POOL = 0 / 2 forces neither / both.
   static const int pool8 = getenv("VFD_BN_BWD8_POOL") ? atoi(getenv("VFD_BN_BWD8_POOL")) : 1;
   const bool pooled8 = ph == 2 && !drop && !pool_bcast && ((pool8 == 1 && pd == 1) || pool8 == 2);
+  BwdFinalize fin;
+  fin.ticket = ticket; fin.Cvalid = Cvalid; fin.train = train; fin.accumulate = accumulate; fin.V = V;
+  fin.dgamma = dgamma; fin.dbeta = dbeta; fin.c1 = c1; fin.c2 = c2;
   if ((ph == 1 && !force4) || use_gather || pooled8) {
     // un-pooled / depth-pooled: 8-channel window-per-thread kernels
     ActGeom g;
@@ -1771,10 +1809,12 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
       }                                                                                                 \
     } while (0)
     VFD_BWD8_LAUNCH(bn_act_bwd8_reduce_kernel, 2 * C * sizeof(float), (const bf16*)y, y_ld, g, mean, invstd, scale,
-                    shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums);
+                    shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums, fin);
     if (int e = check_launch("bn_act_bwd_reduce")) return e;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, accumulate, dgamma, dbeta, c1, c2);
-    if (int e = check_launch("bn_bwd_finalize")) return e;
+    if (ticket == nullptr) {
+      bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, accumulate, dgamma, dbeta, c1, c2);
+      if (int e = check_launch("bn_bwd_finalize")) return e;
+    }
     VFD_BWD8_LAUNCH(bn_act_bwd8_apply_kernel, 0, (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
                     (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, c1, c2, (bf16*)dy,
                     dy_ld);
@@ -1806,10 +1846,12 @@ VFD_API int vfd_bn_act_bwd(const void* y, long long y_ld, int N, int D, int H, i
       }                                                                                                 \
     } while (0)
     VFD_BWD_LAUNCH(bn_act_bwd_reduce_kernel, 2 * C * sizeof(float), (const bf16*)y, y_ld, g, mean, invstd, scale,
-                   shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums);
+                   shift, slope, (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, sums, fin);
     if (int e = check_launch("bn_act_bwd_reduce")) return e;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, accumulate, dgamma, dbeta, c1, c2);
-    if (int e = check_launch("bn_bwd_finalize")) return e;
+    if (ticket == nullptr) {
+      bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, C, Cvalid, V, train, accumulate, dgamma, dbeta, c1, c2);
+      if (int e = check_launch("bn_bwd_finalize")) return e;
+    }
     VFD_BWD_LAUNCH(bn_act_bwd_apply_kernel, 0, (const bf16*)y, y_ld, g, mean, invstd, scale, shift, slope,
                    (const bf16*)g_full, gf_ld, (const bf16*)g_pool, gp_ld, drop_p, seed, seed_dev, c1, c2, (bf16*)dy,
                    dy_ld);

@@ -212,7 +212,7 @@ def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd
               scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
               _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev),
               (1 if train else 0) | (2 if pool_bcast else 0) | (4 if accumulate else 0), sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
-              dbeta.data_ptr(), dy.data_ptr(), _ld(dy), _stream())
+              dbeta.data_ptr(), dy.data_ptr(), _ld(dy), bn_ticket(y.device).data_ptr(), _stream())
 
 
 def _tap_gather(src, cs, dst, kd, kh, kw, sign):
@@ -446,6 +446,19 @@ def _timed(kind, work, thunk, nbytes=0.0):
         PROFILER.run(kind, work, thunk, nbytes)
 
 _scratch = {}
+
+
+_tickets = {}
+
+
+def bn_ticket(device):
+    """A zeroed device counter for vfd_bn_act_bwd's last-block finalize. The kernels leave it zero again; calls rotate
+    over 64 of them so that BatchNorm backward passes on different streams never share one."""
+    ent = _tickets.get(device)
+    if ent is None:
+        ent = _tickets[device] = [torch.zeros(64 * 32, dtype=torch.int32, device=device), 0]
+    ent[1] = (ent[1] + 1) % 64
+    return ent[0][ent[1] * 32:ent[1] * 32 + 1]       # 128 bytes apart
 
 
 def bn_scratch(device, C):
