@@ -69,6 +69,14 @@ VFD_API int vfd_conv3d_wgrad_thin(const void* dy, long long dy_ld, int cout, con
                                   int cin, float* acc, int co_pad, int ci_pad, int fold, int cs, int N, int D,
                                   int H, int W, int kd, int kh, int kw, void* stream);
 
+/* Forward of a 3x3x3 conv from 32 input channels to ONE output channel with fp32 output (NetG's conv_last,
+ * models/mygannet.py:52,97): same operands and result as vfd_conv3d_fwd (row 0 of the packed weights, packed K = 32;
+ * out column 0 = the logit, the remaining out_cols - 1 columns 0), but the 27 taps are the GEMM's N dimension and the
+ * neighbourhood sum runs over fp32 partial products in shared memory (csrc/conv_narrow.cu). */
+VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const void* w_packed, int cin_k,
+                                  const float* bias, float* out, long long out_ld, int out_cols, int N, int D, int H,
+                                  int W, void* stream);
+
 /* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
  * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
  * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =

@@ -99,9 +99,9 @@ def test_clip_prefetcher_yields_the_loader_batches_in_order(depth, pin):
 
 
 def test_training_state_resume_continues_the_trajectory(tmp_path):
-    """2 steps + save + 2 steps against load + 2 steps: the same losses (the only difference between the two runs is
-    the order of the fp32 atomics), with and without the captured graph. A weights-only resume (what the reference
-    saves) restarts Adam's moments and must NOT give the same third step."""
+    """3 steps + save + 2 steps against load + 2 steps, in deterministic mode: the same losses to 1e-6, with and without
+    the captured graph (the load must drop a graph captured earlier). A weights-only resume (what the reference saves)
+    restarts Adam's moments and must NOT give the same second step."""
     B, D, S = 2, 16, 64                                             # SDisc pools 64 -> 1
     args = types.SimpleNamespace(nfr=D, isize=S)
 
@@ -114,6 +114,15 @@ def test_training_state_resume_continues_the_trajectory(tmp_path):
         return netg.to(DEV), netd.to(DEV)
 
     batches = [tuple(t.to(DEV) for t in O.synthetic_batch(B, D, S, seed=i)) for i in range(5)]
+    from vfd_gan_b200 import ops
+    ops.set_deterministic(True)      # bit-reproducible steps: the comparison below is exact, not a noise envelope
+    try:
+        _resume_cases(tmp_path, build, batches)
+    finally:
+        ops.set_deterministic(False)
+
+
+def _resume_cases(tmp_path, build, batches):
     for graph in (False, True):
         netg, netd = build(0)
         tr = V.GanTrainStep(netg, netd, graph=graph, lr=2e-3)       # a large lr makes the optimizer state matter
@@ -135,9 +144,8 @@ def test_training_state_resume_continues_the_trajectory(tmp_path):
         for i, w in zip((3, 4), want):
             tr2.step(*batches[i])
             got = tr2.losses_dict()
-            for k in w:     # the logged-only adversarial terms carry the run-to-run atomics noise
-                tol = 2e-2 if "adv" in k or k == "g/err_g" else 2e-3
-                assert abs(got[k] - w[k]) <= tol * abs(w[k]) + 1e-5, (graph, i, k, got[k], w[k])
+            for k in w:
+                assert abs(got[k] - w[k]) <= 1e-6 * abs(w[k]) + 1e-9, (graph, i, k, got[k], w[k])
         netg3, netd3 = build(2)
         tr3 = V.GanTrainStep(netg3, netd3, graph=False, lr=2e-3)
         V.checkpoint.load_weights(str(tmp_path / "w" / "mygan_ep0007_netG.pth"), netg3, netd3)

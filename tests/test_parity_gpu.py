@@ -28,6 +28,23 @@ CONV_CASES = [
 ]
 
 
+_CALLS = {}
+
+
+def _lib_calls(name=None):
+    """Counts C-ABI calls by entry point (wraps vfd_gan_b200._lib.call once)."""
+    from vfd_gan_b200 import _lib
+    if not getattr(_lib.call, "_counting", False):
+        inner = _lib.call
+
+        def counting(nm, *a):
+            _CALLS[nm] = _CALLS.get(nm, 0) + 1
+            return inner(nm, *a)
+        counting._counting = True
+        _lib.call = counting
+    return _CALLS.get(name, 0) if name else dict(_CALLS)
+
+
 def _conv_all(x, w, b, gy, direct):
     ops.CONV_IMPL_DIRECT = direct
     try:
@@ -61,6 +78,36 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, N, D, H, W):
     assert rel(tc[1], xr.grad) < 3e-3 and rel(tc[1], di[1]) < 1e-3     # bf16-stored dgrad
     assert rel(tc[2], wr.grad) < 1e-4 and rel(tc[2], di[2]) < 1e-4     # fp32 wgrad
     assert rel(tc[3], gyr.sum((0, 2, 3, 4))) < 1e-4
+
+
+@pytest.mark.parametrize("N,D,H,W", [(1, 4, 16, 16), (2, 3, 20, 12), (3, 1, 7, 33), (1, 5, 9, 50), (2, 16, 112, 112)])
+def test_narrow_conv_last_forward(N, D, H, W):
+    """conv_last (32 -> 1 channels, 3x3x3, fp32 logits) through csrc/conv_narrow.cu (taps as the GEMM's N dimension, ring of
+    three partial-product planes) against F.conv3d on the bf16-rounded operands and against the tcgen05 path it replaces,
+    on ragged windows, single planes and the bench geometry."""
+    g = torch.Generator().manual_seed(N * 1000 + D * 100 + H)
+    x = torch.randn(N, 32, D, H, W, generator=g).to(DEV)
+    w = (torch.randn(1, 32, 3, 3, 3, generator=g) * 0.1).to(DEV)
+    b = torch.randn(1, generator=g).to(DEV)
+
+    def run():
+        xc = ops.PackFn.apply(x, 0)
+        yc = ops.ConvFn.apply(xc, w, b, True, False)
+        assert yc.dtype == torch.float32 and float(yc[..., 1:].abs().max()) == 0.0     # padded columns stay zero
+        return ops.UnpackFn.apply(yc, 1)
+
+    assert ops.NARROW_CONV
+    calls = _lib_calls()
+    got = run()
+    assert _lib_calls("vfd_conv3d_fwd_narrow") == calls.get("vfd_conv3d_fwd_narrow", 0) + 1
+    ops.NARROW_CONV = False
+    try:
+        tc = run()
+    finally:
+        ops.NARROW_CONV = True
+    want = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    assert rel(got, want) < 1e-5 and rel(got, tc) < 1e-5
+    assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
 
 
 @pytest.mark.parametrize("cin,cout,N,D,H,W,bias", [(3, 2, 2, 5, 9, 11, False), (8, 8, 1, 3, 7, 5, True), (3, 2, 4, 16, 32, 32, False)])

@@ -1,0 +1,215 @@
+// Forward of a 3x3x3 conv with 32 input channels and ONE output channel -- NetG's conv_last
+// (models/mygannet.py:52,97: nn.Conv3d(ngf, 1, 3, padding=1) before the sigmoid), fp32 logits out.
+//
+// On the 128-row tcgen05 tile this layer is 27 taps x 2 K16 steps, each re-reading its A tile from shared memory for
+// 16 output columns of which one is used: MMA-issue bound at 0.20 of the HBM rate (profiles/r2_thin_epilogue.txt).
+// Here the taps become the GEMM's N dimension instead:
+//     P[u][tap] = sum_c x[u][c] * w[tap][c]          one m16n8k16 mma.sync chain per 16 INPUT voxels (N = 27 -> 32)
+//     out[v]    = bias + sum_tap P[v + off(tap)][tap]  27 shared-memory reads per output voxel
+// i.e. every input voxel is multiplied with all 27 filter rows once (8 MMAs per 16 voxels instead of 54 per 16
+// outputs), and the 3x3x3 neighbourhood sum runs over the fp32 partial products. A CTA owns an 8 x 16 (h, w) window and
+// walks along d: input plane j's partial products go into slot j % 3 of a three-plane ring, so each input plane is
+// loaded and multiplied once per window (halo overhead 180 / 128 in h, w only).
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "vfd_internal.h"
+
+namespace vfd {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kNarrowThreads = 128;
+constexpr int kTH = 8, kTW = 16;                 // output window of one CTA (one d-plane at a time)
+constexpr int kPH = kTH + 2, kPW = kTW + 2;      // haloed input window
+constexpr int kPV = kPH * kPW;                   // 180 input voxels per plane
+constexpr int kPVpad = 192;                      // 12 m16 tiles
+constexpr int kXRow = 80;                        // bytes per staged voxel row: 64 B data + 16 B pad (conflict-free ldmatrix)
+constexpr int kTaps = 27;
+constexpr int kXBytes = kPVpad * kXRow;          // 15360
+constexpr int kPSlot = kTaps * kPV;              // floats per ring slot
+constexpr int kNarrowSmem = kXBytes + 3 * kPSlot * 4;   // 73680
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct NarrowParams {
+  const bf16* x;        // channels-last [N][D][H][W][x_ld], 32 valid channels
+  long long x_ld;
+  const bf16* w;        // packed forward weights, row 0: [27 taps][cin_k = 32]
+  int cin_k;
+  const float* bias;    // 1 entry or nullptr
+  float* out;           // fp32 [N][D][H][W][out_ld], out_cols columns written (column 0 = logit, the rest 0)
+  long long out_ld;
+  int out_cols;
+  int N, D, H, W, tilesH, tilesW;
+};
+
+constexpr int kChunks = kPV * 4;                                   // 16-byte chunks of one input plane window
+constexpr int kChunksPerThread = (kChunks + kNarrowThreads - 1) / kNarrowThreads;   // 6
+
+__global__ void __launch_bounds__(kNarrowThreads)
+conv_narrow_fwd_kernel(const NarrowParams p) {
+  extern __shared__ __align__(16) uint8_t nsm[];
+  uint8_t* xs = nsm;
+  float* P = reinterpret_cast<float*>(nsm + kXBytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int t = blockIdx.x;
+  const int w0 = (t % p.tilesW) * kTW;
+  t /= p.tilesW;
+  const int h0 = (t % p.tilesH) * kTH;
+  const int n = t / p.tilesH;
+
+  // B fragments (the 27 x 32 filter, zero rows for taps 27..31) stay in registers: [n-tile][k-step][2]
+  uint32_t bfr[4][2][2];
+  {
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int tap = 8 * nt + g;
+        uint32_t b0 = 0u, b1 = 0u;
+        if (tap < kTaps) {
+          const bf16* row = p.w + static_cast<size_t>(tap) * p.cin_k + ks * 16 + 2 * tq;
+          b0 = *reinterpret_cast<const uint32_t*>(row);
+          b1 = *reinterpret_cast<const uint32_t*>(row + 8);
+        }
+        bfr[nt][ks][0] = b0;
+        bfr[nt][ks][1] = b1;
+      }
+  }
+  // rows 180..191 of the staged window are never loaded: keep them zero
+  for (int i = tid; i < (kPVpad - kPV) * kXRow / 4; i += kNarrowThreads)
+    reinterpret_cast<uint32_t*>(xs + kPV * kXRow)[i] = 0u;
+  const float bias = p.bias != nullptr ? __ldg(p.bias) : 0.f;
+
+  uint4 pre[kChunksPerThread];
+  auto load_plane = [&](int d) {
+#pragma unroll
+    for (int k = 0; k < kChunksPerThread; ++k) {
+      const int c = tid + k * kNarrowThreads;
+      pre[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < kChunks && d >= 0 && d < p.D) {
+        const int pv = c >> 2, part = c & 3;
+        const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
+        if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {
+          const long long vox = ((static_cast<long long>(n) * p.D + d) * p.H + hh) * p.W + ww;
+          pre[k] = __ldg(reinterpret_cast<const uint4*>(p.x + vox * p.x_ld + part * 8));
+        }
+      }
+    }
+  };
+
+  const uint32_t xs_s = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
+  const int oh = tid / kTW, ow = tid % kTW;
+  const bool out_ok = h0 + oh < p.H && w0 + ow < p.W;
+  load_plane(-1);
+  for (int s = 0; s <= p.D + 1; ++s) {          // input plane d_in = s - 1 (planes -1 and D are the zero padding)
+    const int d_in = s - 1;
+#pragma unroll
+    for (int k = 0; k < kChunksPerThread; ++k) {
+      const int c = tid + k * kNarrowThreads;
+      if (c < kChunks) *reinterpret_cast<uint4*>(xs + (c >> 2) * kXRow + (c & 3) * 16) = pre[k];
+    }
+    __syncthreads();
+    if (s <= p.D) load_plane(d_in + 1);         // in flight while this plane is multiplied
+    float* Ps = P + (s % 3) * kPSlot;
+    if (d_in >= 0 && d_in < p.D) {
+      const int g = lane >> 2, tq = lane & 3;
+#pragma unroll 1
+      for (int mt = warp; mt < kPVpad / 16; mt += kNarrowThreads / 32) {
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(xs_s + (mt * 16 + (lane & 15)) * kXRow + ks * 32 + (lane >> 4) * 16, a0, a1, a2, a3);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma16816(acc[nt], a0, a1, a2, a3, bfr[nt][ks][0], bfr[nt][ks][1]);
+        }
+        const int v0 = mt * 16 + g, v1 = v0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int tap = 8 * nt + 2 * tq;
+          if (tap < kTaps) {
+            if (v0 < kPV) Ps[tap * kPV + v0] = acc[nt][0];
+            if (v1 < kPV) Ps[tap * kPV + v1] = acc[nt][2];
+          }
+          if (tap + 1 < kTaps) {
+            if (v0 < kPV) Ps[(tap + 1) * kPV + v0] = acc[nt][1];
+            if (v1 < kPV) Ps[(tap + 1) * kPV + v1] = acc[nt][3];
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < kPSlot; i += kNarrowThreads) Ps[i] = 0.f;
+    }
+    __syncthreads();
+    const int d_out = d_in - 1;                  // planes d_out - 1, d_out, d_out + 1 are in the ring now
+    if (d_out >= 0 && d_out < p.D && out_ok) {
+      float sum = bias;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float* Pa = P + ((d_out + a) % 3) * kPSlot;   // plane d_out - 1 + a sits in slot (d_out + a) % 3
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            sum += Pa[((a * 3 + b) * 3 + c) * kPV + (oh + b) * kPW + (ow + c)];
+      }
+      const long long vox = ((static_cast<long long>(n) * p.D + d_out) * p.H + (h0 + oh)) * p.W + (w0 + ow);
+      float* o = p.out + vox * p.out_ld;
+      *reinterpret_cast<float4*>(o) = make_float4(sum, 0.f, 0.f, 0.f);
+      for (int c4 = 4; c4 < p.out_cols; c4 += 4) *reinterpret_cast<float4*>(o + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace vfd
+
+using namespace vfd;
+
+VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const void* w_packed, int cin_k,
+                                  const float* bias, float* out, long long out_ld, int out_cols, int N, int D, int H,
+                                  int W, void* stream_) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  if (x == nullptr || w_packed == nullptr || out == nullptr) return set_error(VFD_ERR_ARG, "conv3d_fwd_narrow: null pointer");
+  if (cin != 32 || cin_k != 32)
+    return set_error(VFD_ERR_ARG, "conv3d_fwd_narrow: serves 32 input channels (packed K = 32) only");
+  if (out_cols < 4 || out_cols % 4 || out_ld < out_cols || out_ld % 4 || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      x_ld < 32 || x_ld % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 3))
+    return set_error(VFD_ERR_ARG, "conv3d_fwd_narrow: tensors must be 16-byte aligned channels-last");
+  if (static_cast<long long>(N) * D * H * W >= (1LL << 31))
+    return set_error(VFD_ERR_ARG, "conv3d_fwd_narrow: more than 2^31 voxels");
+  NarrowParams p;
+  p.x = static_cast<const bf16*>(x); p.x_ld = x_ld; p.w = static_cast<const bf16*>(w_packed); p.cin_k = cin_k;
+  p.bias = bias; p.out = out; p.out_ld = out_ld; p.out_cols = out_cols;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.tilesH = (H + kTH - 1) / kTH; p.tilesW = (W + kTW - 1) / kTW;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_narrow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNarrowSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_narrow_fwd)");
+    attr = true;
+  }
+  const long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
+  conv_narrow_fwd_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, kNarrowSmem, static_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("conv_narrow_fwd");
+}

@@ -288,15 +288,12 @@ tiny_pointwise_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __
 __global__ void __launch_bounds__(256)
 tiny_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, int cout, const bf16* __restrict__ x, long long x_ld,
                   int cin, float* __restrict__ acc, int co_pad, long long V, float* __restrict__ partial) {
-  __shared__ float red[64];
-  __shared__ float wred[8][64];
+  __shared__ float wred[8][64];   // per-warp partials, summed in warp order
   float p[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) p[i][j] = 0.f;
-  if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
-  __syncthreads();
   constexpr int U = 4;
   const long long tstride = (long long)gridDim.x * blockDim.x;
   for (long long v0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; v0 < V; v0 += tstride * U) {

@@ -118,6 +118,12 @@ def _conv3d_fwd(x, w_packed, bias, out, stats, kd, kh, kw, kc, out_cols, direct)
                   kh, kw, kc, _stream())
 
 
+def _conv3d_fwd_narrow(x, w_packed, bias, out):
+    N, D, H, W, C, ld = _check_cl(x, "conv3d_fwd_narrow input")
+    _lib.call("vfd_conv3d_fwd_narrow", x.data_ptr(), ld, C, w_packed.data_ptr(), w_packed.shape[2], _ptr(bias),
+              out.data_ptr(), _ld(out), out.shape[-1], N, D, H, W, _stream())
+
+
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
@@ -357,6 +363,8 @@ def _frames_to_clip(frames, out, pm1):
 conv3d_fwd = _define(
     "conv3d_fwd(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats, int kd, int kh, int kw, "
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
+conv3d_fwd_narrow = _define("conv3d_fwd_narrow(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out) -> ()",
+                            _conv3d_fwd_narrow)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
@@ -433,6 +441,7 @@ def set_deterministic(on=True):
     DETERMINISTIC = bool(on)
 
 
+NARROW_CONV = os.environ.get("VFD_NARROW_CONV", "1") != "0"   # conv_last forward through csrc/conv_narrow.cu
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
@@ -924,9 +933,16 @@ class ConvFn(torch.autograd.Function):
         # into the shared self-clearing scratch (the caller passes stats_ready=True to BnActFn)
         st = bn_scratch(x.device, cout_p) if (fuse_stats and conv_fuses_stats(cout, out_fp32)) else None
         ctx.stats_fused = st is not None
-        _timed("conv_fwd", flops,
-               lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT),
-               2.0 * x.numel() + out.numel() * out.element_size())
+        # one output channel from 32 inputs through 27 taps (conv_last): taps as the GEMM's N dimension (conv_narrow.cu)
+        narrow = (NARROW_CONV and cout == 1 and (kd, kh, kw) == (3, 3, 3) and Cin_p == 32 and out_fp32 and st is None
+                  and not CONV_IMPL_DIRECT and pk.fwd.shape[2] == 32)
+        if narrow:
+            _timed("conv_fwd", flops, lambda: conv3d_fwd_narrow(x, pk.fwd, b, out),
+                   2.0 * x.numel() + out.numel() * out.element_size())
+        else:
+            _timed("conv_fwd", flops,
+                   lambda: conv3d_fwd(x, pk.fwd, b, out, st, kd, kh, kw, pk.kc_f, cout_p, CONV_IMPL_DIRECT),
+                   2.0 * x.numel() + out.numel() * out.element_size())
         ctx.save_for_backward(x, weight)
         ctx.w_dgrad, ctx.kc_d = pk.dgrad, pk.kc_d     # the master cannot change between forward and backward
         ctx.bias_param = bias
