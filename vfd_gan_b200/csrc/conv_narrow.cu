@@ -12,7 +12,17 @@
 // loaded and multiplied once per window (halo overhead 180 / 128 in h, w only).
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include "vfd_internal.h"
+
+// stage-isolation switches (debug library only; tools/gpu_time_conv_last.py): 1 = no global loads, 2 = no MMAs / partial
+// product stores, 4 = no neighbourhood sum, 8 = no output store
+#ifdef VFD_DEBUG
+#define VFD_NDBG(p, bit) ((p).dbg & (bit))
+#else
+#define VFD_NDBG(p, bit) (0)
+#endif
 
 namespace vfd {
 namespace {
@@ -44,6 +54,16 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// first K step: D = A * B (+ 0), no accumulator registers to clear
+__device__ __forceinline__ void mma16816_zero(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                              uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 struct NarrowParams {
   const bf16* x;        // channels-last [N][D][H][W][x_ld], 32 valid channels
   long long x_ld;
@@ -54,6 +74,7 @@ struct NarrowParams {
   long long out_ld;
   int out_cols;
   int N, D, H, W, tilesH, tilesW;
+  int dbg;
 };
 
 constexpr int kChunks = kPV * 4;                                   // 16-byte chunks of one input plane window
@@ -95,28 +116,44 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
     reinterpret_cast<uint32_t*>(xs + kPV * kXRow)[i] = 0u;
   const float bias = p.bias != nullptr ? __ldg(p.bias) : 0.f;
 
-  uint4 pre[kChunksPerThread];
-  auto load_plane = [&](int d) {
+  // two input planes in flight per thread (registers): one plane ahead left the memory system idle for most of a step
+  uint4 pre_a[kChunksPerThread], pre_b[kChunksPerThread];
+  // the kernel is instruction-issue bound, so everything that does not depend on the plane is computed once: element
+  // offsets of this thread's 16-byte chunks inside a plane (-1 = outside the image or past the window)
+  int coff[kChunksPerThread];
+#pragma unroll
+  for (int k = 0; k < kChunksPerThread; ++k) {
+    const int c = tid + k * kNarrowThreads;
+    const int pv = c >> 2, part = c & 3;
+    const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
+    coff[k] = (c < kChunks && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                  ? static_cast<int>((static_cast<long long>(hh) * p.W + ww) * p.x_ld + part * 8) : -1;
+  }
+  const long long plane_elems = static_cast<long long>(p.H) * p.W * p.x_ld;
+  auto load_plane = [&](int d, uint4 (&pre)[kChunksPerThread]) {
+    const bool plane_ok = d >= 0 && d < p.D && !VFD_NDBG(p, 1);
+    const bf16* base = p.x + (static_cast<long long>(n) * p.D + (plane_ok ? d : 0)) * plane_elems;
 #pragma unroll
     for (int k = 0; k < kChunksPerThread; ++k) {
-      const int c = tid + k * kNarrowThreads;
       pre[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (c < kChunks && d >= 0 && d < p.D) {
-        const int pv = c >> 2, part = c & 3;
-        const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
-        if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {
-          const long long vox = ((static_cast<long long>(n) * p.D + d) * p.H + hh) * p.W + ww;
-          pre[k] = __ldg(reinterpret_cast<const uint4*>(p.x + vox * p.x_ld + part * 8));
-        }
-      }
+      if (plane_ok && coff[k] >= 0) pre[k] = __ldg(reinterpret_cast<const uint4*>(base + coff[k]));
     }
   };
+  // float offsets of this lane's accumulator columns inside a ring slot (-1: tap 27..31, not stored)
+  int poff[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tap = 8 * nt + 2 * (lane & 3) + j;
+      poff[nt][j] = tap < kTaps ? tap * kPV : -1;
+    }
 
   const uint32_t xs_s = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
   const int oh = tid / kTW, ow = tid % kTW;
   const bool out_ok = h0 + oh < p.H && w0 + ow < p.W;
-  load_plane(-1);
-  for (int s = 0; s <= p.D + 1; ++s) {          // input plane d_in = s - 1 (planes -1 and D are the zero padding)
+  // one step: input plane d_in = s - 1 (planes -1 and D are the zero padding) arrives in `pre`
+  auto step = [&](int s, uint4 (&pre)[kChunksPerThread]) {
     const int d_in = s - 1;
 #pragma unroll
     for (int k = 0; k < kChunksPerThread; ++k) {
@@ -124,59 +161,60 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
       if (c < kChunks) *reinterpret_cast<uint4*>(xs + (c >> 2) * kXRow + (c & 3) * 16) = pre[k];
     }
     __syncthreads();
-    if (s <= p.D) load_plane(d_in + 1);         // in flight while this plane is multiplied
+    if (s + 2 <= p.D + 1) load_plane(d_in + 2, pre);   // this buffer is free again: fetch the plane after next
     float* Ps = P + (s % 3) * kPSlot;
-    if (d_in >= 0 && d_in < p.D) {
-      const int g = lane >> 2, tq = lane & 3;
+    if (d_in >= 0 && d_in < p.D && !VFD_NDBG(p, 2)) {
+      const int g = lane >> 2;
 #pragma unroll 1
       for (int mt = warp; mt < kPVpad / 16; mt += kNarrowThreads / 32) {
         float acc[4][4];
+        uint32_t a0, a1, a2, a3;
+        ldmatrix_x4(xs_s + (mt * 16 + (lane & 15)) * kXRow + (lane >> 4) * 16, a0, a1, a2, a3);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816_zero(acc[nt], a0, a1, a2, a3, bfr[nt][0][0], bfr[nt][0][1]);
+        ldmatrix_x4(xs_s + (mt * 16 + (lane & 15)) * kXRow + 32 + (lane >> 4) * 16, a0, a1, a2, a3);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(acc[nt], a0, a1, a2, a3, bfr[nt][1][0], bfr[nt][1][1]);
+        const int v0 = mt * 16 + g;
+        const bool ok0 = v0 < kPV, ok1 = v0 + 8 < kPV;
+        float* pv0 = Ps + v0;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t a0, a1, a2, a3;
-          ldmatrix_x4(xs_s + (mt * 16 + (lane & 15)) * kXRow + ks * 32 + (lane >> 4) * 16, a0, a1, a2, a3);
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma16816(acc[nt], a0, a1, a2, a3, bfr[nt][ks][0], bfr[nt][ks][1]);
-        }
-        const int v0 = mt * 16 + g, v1 = v0 + 8;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int tap = 8 * nt + 2 * tq;
-          if (tap < kTaps) {
-            if (v0 < kPV) Ps[tap * kPV + v0] = acc[nt][0];
-            if (v1 < kPV) Ps[tap * kPV + v1] = acc[nt][2];
-          }
-          if (tap + 1 < kTaps) {
-            if (v0 < kPV) Ps[(tap + 1) * kPV + v0] = acc[nt][1];
-            if (v1 < kPV) Ps[(tap + 1) * kPV + v1] = acc[nt][3];
-          }
-        }
+          for (int j = 0; j < 2; ++j)
+            if (poff[nt][j] >= 0) {
+              if (ok0) pv0[poff[nt][j]] = acc[nt][j];
+              if (ok1) pv0[poff[nt][j] + 8] = acc[nt][2 + j];
+            }
       }
-    } else {
+    } else if (!VFD_NDBG(p, 2)) {
       for (int i = tid; i < kPSlot; i += kNarrowThreads) Ps[i] = 0.f;
     }
     __syncthreads();
     const int d_out = d_in - 1;                  // planes d_out - 1, d_out, d_out + 1 are in the ring now
     if (d_out >= 0 && d_out < p.D && out_ok) {
-      float sum = bias;
+      float sum[3] = {bias, 0.f, 0.f};           // three independent chains
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
+      for (int a = 0; a < (VFD_NDBG(p, 4) ? 0 : 3); ++a) {
         const float* Pa = P + ((d_out + a) % 3) * kPSlot;   // plane d_out - 1 + a sits in slot (d_out + a) % 3
 #pragma unroll
         for (int b = 0; b < 3; ++b)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            sum += Pa[((a * 3 + b) * 3 + c) * kPV + (oh + b) * kPW + (ow + c)];
+            sum[a] += Pa[((a * 3 + b) * 3 + c) * kPV + (oh + b) * kPW + (ow + c)];
       }
       const long long vox = ((static_cast<long long>(n) * p.D + d_out) * p.H + (h0 + oh)) * p.W + (w0 + ow);
       float* o = p.out + vox * p.out_ld;
-      *reinterpret_cast<float4*>(o) = make_float4(sum, 0.f, 0.f, 0.f);
+      if (!VFD_NDBG(p, 8) || sum[0] == 12345.f)
+      *reinterpret_cast<float4*>(o) = make_float4((sum[0] + sum[1]) + sum[2], 0.f, 0.f, 0.f);
       for (int c4 = 4; c4 < p.out_cols; c4 += 4) *reinterpret_cast<float4*>(o + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  load_plane(-1, pre_a);
+  load_plane(0, pre_b);
+  for (int s = 0; s <= p.D + 1; s += 2) {
+    step(s, pre_a);
+    if (s + 1 <= p.D + 1) step(s + 1, pre_b);
   }
 }
 
@@ -203,11 +241,24 @@ VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const 
   p.bias = bias; p.out = out; p.out_ld = out_ld; p.out_cols = out_cols;
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.tilesH = (H + kTH - 1) / kTH; p.tilesW = (W + kTW - 1) / kTW;
+  p.dbg = 0;
+#ifdef VFD_DEBUG
+  if (const char* e = getenv("VFD_NARROW_DBG")) p.dbg = atoi(e);
+#endif
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_narrow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNarrowSmem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_narrow_fwd)");
+    // three CTAs per SM need 3 x 73 KB of shared memory: ask for the largest carveout instead of the driver's default
+    e = cudaFuncSetAttribute(conv_narrow_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_narrow_fwd, carveout)");
     attr = true;
+#ifdef VFD_DEBUG
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_narrow_fwd_kernel, kNarrowThreads, kNarrowSmem);
+    fprintf(stderr, "conv_narrow_fwd: %d resident CTAs per SM\n", occ);
+#endif
   }
   const long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
   conv_narrow_fwd_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, kNarrowSmem, static_cast<cudaStream_t>(stream_)>>>(p);
