@@ -86,11 +86,6 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
   uint8_t* xs = nsm;
   float* P = reinterpret_cast<float*>(nsm + kXBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int t = blockIdx.x;
-  const int w0 = (t % p.tilesW) * kTW;
-  t /= p.tilesW;
-  const int h0 = (t % p.tilesH) * kTH;
-  const int n = t / p.tilesH;
 
   // B fragments (the 27 x 32 filter, zero rows for taps 27..31) stay in registers: [n-tile][k-step][2]
   uint32_t bfr[4][2][2];
@@ -117,6 +112,15 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
   const float bias = p.bias != nullptr ? __ldg(p.bias) : 0.f;
 
   // two input planes in flight per thread (registers): one plane ahead left the memory system idle for most of a step
+  // persistent: a CTA takes (n, h-window, w-window) columns round-robin; the filter fragments are loaded once
+  const int ncols = p.N * p.tilesH * p.tilesW;
+#pragma unroll 1
+  for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+  int t = col;
+  const int w0 = (t % p.tilesW) * kTW;
+  t /= p.tilesW;
+  const int h0 = (t % p.tilesH) * kTH;
+  const int n = t / p.tilesH;
   uint4 pre_a[kChunksPerThread], pre_b[kChunksPerThread];
   // the kernel is instruction-issue bound, so everything that does not depend on the plane is computed once: element
   // offsets of this thread's 16-byte chunks inside a plane (-1 = outside the image or past the window)
@@ -216,6 +220,7 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
     step(s, pre_a);
     if (s + 1 <= p.D + 1) step(s + 1, pre_b);
   }
+  }
 }
 
 }  // namespace
@@ -260,7 +265,13 @@ VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const 
     fprintf(stderr, "conv_narrow_fwd: %d resident CTAs per SM\n", occ);
 #endif
   }
-  const long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
+  long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (grid > 3LL * sms) grid = 3LL * sms;       // three resident CTAs per SM, each walks several columns
   conv_narrow_fwd_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, kNarrowSmem, static_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("conv_narrow_fwd");
 }
