@@ -26,7 +26,7 @@ for r in csv.DictReader(lines):
 rows = list(per_id.values())
 marks = [i for i, r in enumerate(rows) if "pack_weights_batched" in r["name"]]
 step = rows[marks[-1]:]
-short = lambda n: re.sub(r"<.*", "", re.sub(r"\(.*", "", n).replace("void ", ""))
+short = lambda n: re.sub(r"<.*", "", re.sub(r"\(.*", "", n.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")).replace("void ", ""))
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for r in step:
     a = agg[short(r["name"])]
@@ -38,7 +38,7 @@ with open(out_prefix + "_dram_per_kernel.csv", "w") as f:
     f.write("kernel,launches,total_ms,dram_read_MB,dram_write_MB,GBps\n")
     for k, (c, us, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k},{c},{us / 1e3:.3f},{rd / 1e6:.1f},{wr / 1e6:.1f},{(rd + wr) / max(us, 1e-9) / 1e3:.0f}\n")
-kinds = {"conv_fwd+dgrad": ("conv_fwd_res_kernel", "conv_fwd_tc_kernel", "tiny_pointwise_kernel"),
+kinds = {"conv_fwd+dgrad": ("conv_fwd_res_kernel", "conv_fwd_tc_kernel", "tiny_pointwise_kernel", "conv_narrow_fwd_kernel"),
          "conv_wgrad": ("conv_wgrad", "thin_wgrad_kernel", "tiny_wgrad_kernel", "tap_gather_kernel"),
          "bn_act_fwd": ("bn_act_fwd_kernel",), "bn_act_bwd": ("bn_act_bwd",)}
 tot = {}
