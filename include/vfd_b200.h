@@ -77,6 +77,18 @@ VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const 
                                   const float* bias, float* out, long long out_ld, int out_cols, int N, int D, int H,
                                   int W, void* stream);
 
+/* One ConvLSTM step (models/convlstm.py:46-58) in one launch: the gate conv (nn.Conv2d over cat[x, h], kd = 1) on
+ * tcgen05 with sigmoid / tanh and c' = f*c + i*g, h' = o*tanh(c') in its epilogue; the gates never reach HBM.
+ * comb: bf16 channels-last [N][H][W][comb_ld] (cin = in + hid channels); w_packed_perm: forward-packed gate weights
+ * [4*hid][taps][cin_k] with the rows re-ordered [hid/64][gate i,f,o,g][64] (so one 256-column accumulator tile holds the
+ * four gates of 64 hidden channels), bias_perm in the same order (or NULL); c_cur / c_next fp32 [N][H][W][hid]; h_out
+ * bf16 [N][H][W][h_ld] (may be a channel slice of the next step's concat buffer); act (optional) fp32 [N][H][W][4*hid]
+ * gate-major post-activation values for vfd_convlstm_cell_bwd. hid must be a multiple of 64. */
+VFD_API int vfd_convlstm_step_fwd(const void* comb, long long comb_ld, int cin, const void* w_packed_perm, int cin_k,
+                                  const float* bias_perm, const float* c_cur, int hid, float* c_next, void* h_out,
+                                  long long h_ld, float* act, int N, int H, int W, int kh, int kw, int kc,
+                                  void* stream);
+
 /* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
  * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
  * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =

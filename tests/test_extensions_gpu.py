@@ -109,6 +109,35 @@ def test_netg_lstm_against_reference_fixture_and_oracle():
         assert rel(got[::4], f[key]) <= max(2.0 * rel(res[True][0][name].grad[::4], f[key]), 2e-2), name
 
 
+def test_fused_convlstm_step_equals_the_two_kernel_path():
+    """models/convlstm.py:46-58 with the cell update in the gate conv's epilogue (vfd_convlstm_step_fwd, hidden sizes
+    that are multiples of 64) against the gate conv + cell kernel pair that the reference fixture pins: hidden states,
+    and the gradients of the input and of the gate weights / bias through a 3-step unroll."""
+    torch.manual_seed(4)
+    N, T, H, W, cin, hid = 2, 3, 8, 8, 64, 64
+    lstm = V.ConvLSTM((H, W), cin, hid, (3, 3), 1, batch_first=True, bias=True).to(DEV)
+    x = (torch.randn(N, T, H, W, cin, device=DEV) * 0.5).bfloat16()
+    gout = torch.randn(N, T, H, W, hid, device=DEV).bfloat16()
+    res = {}
+    for fused in (True, False):
+        ops.LSTM_FUSED = fused
+        try:
+            xin = x.clone().requires_grad_(True)
+            lstm.zero_grad()
+            calls = ops._lib.LAUNCHES
+            out = lstm.forward_cl(xin)
+            out.backward(gout)
+            res[fused] = (out.detach().float(), xin.grad.float(), lstm.cell_list[0].conv.weight.grad.clone(),
+                          lstm.cell_list[0].conv.bias.grad.clone())
+        finally:
+            ops.LSTM_FUSED = True
+    for a, b, tol in zip(res[True], res[False], (4e-3, 1e-2, 3e-3, 3e-3)):
+        assert a.shape == b.shape and rel(a, b) < tol, (rel(a, b), tol)
+    assert ops.lstm_step_fusable(lstm.cell_list[0].conv.weight, cin + hid)
+    small = V.ConvLSTM((H, W), 8, 8, (3, 3), 1, batch_first=True, bias=True).to(DEV)
+    assert not ops.lstm_step_fusable(small.cell_list[0].conv.weight, 16)        # falls back to the two-kernel path
+
+
 def test_gan_step_with_convlstm_bottleneck_tracks_oracle():
     """BASELINE config 3 in miniature: 32-frame clips, NetG + ConvLSTM bottleneck (T = 2), full GAN step."""
     B, D, S = 2, 32, 64

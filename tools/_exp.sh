@@ -1,6 +1,12 @@
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2f_dram_raw.csv python tools/gpu_one_step.py 2 > gpurun_out/r2f_ncu.log 2>&1
-python tools/dram_summary.py gpurun_out/r2f_dram_raw.csv gpurun_out/r2f > gpurun_out/r2f_kind.log
-head -24 gpurun_out/r2f_dram_per_kernel.csv
-ncu --set full --clock-control none --import-source on -k regex:conv_narrow_fwd -c 1 -s 2 -o gpurun_out/r2f_narrow python tools/gpu_time_conv_last.py > gpurun_out/r2f_ncu2.log 2>&1
-ncu -i gpurun_out/r2f_narrow.ncu-rep --page raw --csv > gpurun_out/r2f_narrow_raw.csv 2>/dev/null
-ls -la gpurun_out/r2f_narrow*
+python -m pytest tests/test_extensions_gpu.py -x -q -m gpu -k "convlstm or lstm" 2>&1 | grep -E "^E  |passed|failed|Error" | head -20
+python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "convlstm or conv_fwd_dgrad" 2>&1 | grep -E "^E  |passed|failed|Error" | head
+for f in 0 1; do
+VFD_LSTM_FUSED=$f python bench.py --workload cfg3 --steps 10 --warmup 3 --no-cpu-baseline --no-profile --no-flow > gpurun_out/r2ag_cfg3_$f.json 2> gpurun_out/r2ag_cfg3.err
+python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2ag_cfg3_$f.json').read().strip().splitlines()[-1]); print('cfg3 LSTM_FUSED=$f ms_per_step', d['ms_per_step'])"
+done
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile --no-flow > gpurun_out/r2ag_cfg2.json 2> gpurun_out/r2ag_cfg2.err
+python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2ag_cfg2.json').read().strip().splitlines()[-1]); print('cfg2 ms_per_step', d['ms_per_step'])"

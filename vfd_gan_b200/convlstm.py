@@ -134,10 +134,16 @@ class ConvLSTM(nn.Module):
             h = torch.zeros(N, 1, H, W, cell.hidden_dim, dtype=torch.bfloat16, device=x_cl.device)
             c = torch.zeros(N, H, W, cell.hidden_dim, dtype=torch.float32, device=x_cl.device)
             outs = []
+            fused = ops.lstm_step_fusable(cell.conv.weight, cin + cell.hidden_dim)
+            if fused:   # gate conv + cell update in one kernel; the permuted gate operands are shared by the T steps
+                w_perm, b_perm, kc = ops.lstm_gate_operands(cell.conv.weight, cell.conv.bias)
             for t in range(T):
                 comb = torch.cat([cur[:, t:t + 1], h], dim=-1)        # models/convlstm.py:46
-                h32, c = cell.forward_cl(comb, c)
-                h = h32.to(torch.bfloat16).unsqueeze(1)
+                if fused:
+                    h, c = ops.LstmStepFn.apply(comb, c, cell.conv.weight, cell.conv.bias, w_perm, b_perm, kc)
+                else:
+                    h32, c = cell.forward_cl(comb, c)
+                    h = h32.to(torch.bfloat16).unsqueeze(1)
                 outs.append(h)
             cur = torch.cat(outs, dim=1)
         return cur

@@ -53,6 +53,15 @@ struct Epilogue {
   void* out;
   double* stats;     // optional [2][stats_ld]: per-channel sum / sum of squares of the stored bf16 values
   int stats_ld;
+  // ConvLSTM step (models/convlstm.py:46-58) fused into the gate conv's epilogue: lstm_j > 0 means the packed weight
+  // rows are ordered [n-tile][gate i,f,o,g][lstm_j hidden channels], so one 4*lstm_j-column accumulator tile holds all
+  // four gates of hidden channels [nt*lstm_j, (nt+1)*lstm_j); bias is in the same (permuted) order
+  int lstm_j, lstm_hid;
+  const float* lstm_c_cur;   // [V][hid] fp32
+  float* lstm_c_next;        // [V][hid] fp32
+  float* lstm_act;           // [V][4*hid] fp32, gate-major (i | f | o | g) post-activation values for the backward pass
+  void* lstm_h;              // bf16 [V][lstm_h_ld]: h' straight into the next step's [x, h] concat slice
+  long long lstm_h_ld;
 };
 
 // column sums of a 32-row x 32-column register tile spread over a warp (row = lane): after the
@@ -149,6 +158,75 @@ __device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_
     if (s_sum[j] != 0.0 || s_sq[j] != 0.0) {
       atomicAdd(e.stats + j, s_sum[j]);
       atomicAdd(e.stats + e.stats_ld + j, s_sq[j]);
+    }
+  }
+}
+
+// ConvLSTM epilogue: this warp's 32 voxel rows x one n-tile = the four gates of lstm_j hidden channels.
+//   i, f, o = sigmoid, g = tanh; c' = f * c + i * g; h' = o * tanh(c')      (models/convlstm.py:49-58)
+// 16 channels at a time: four tcgen05.ld of 16 columns (one per gate), c read and c' written as fp32, h' written as
+// bf16 into the next step's concat slice, activations saved gate-major for the cell backward kernel. The gates never
+// go to HBM.
+__device__ __forceinline__ void epilogue_tile_lstm(const Epilogue& e, uint32_t tacc, int nt, bool valid, long long vox) {
+  const int J = e.lstm_j, hid = e.lstm_hid;
+  for (int jb = 0; jb < J; jb += 16) {
+    float gi[16], gf[16], go[16], gg[16];
+    tmem_ld16(tacc + jb, gi);
+    tmem_ld16(tacc + J + jb, gf);
+    tmem_ld16(tacc + 2 * J + jb, go);
+    tmem_ld16(tacc + 3 * J + jb, gg);
+    if (!valid) continue;
+    const int ch0 = nt * J + jb;
+    if (e.bias != nullptr) {
+      const float* b = e.bias + nt * 4 * J + jb;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        gi[i] += __ldg(b + i);
+        gf[i] += __ldg(b + J + i);
+        go[i] += __ldg(b + 2 * J + i);
+        gg[i] += __ldg(b + 3 * J + i);
+      }
+    }
+    const float* cc = e.lstm_c_cur + vox * hid + ch0;
+    float c[16], h[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(cc + i);
+      c[i] = t.x; c[i + 1] = t.y; c[i + 2] = t.z; c[i + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      gi[i] = 1.f / (1.f + expf(-gi[i]));
+      gf[i] = 1.f / (1.f + expf(-gf[i]));
+      go[i] = 1.f / (1.f + expf(-go[i]));
+      gg[i] = tanhf(gg[i]);
+      c[i] = gf[i] * c[i] + gi[i] * gg[i];
+      h[i] = go[i] * tanhf(c[i]);
+    }
+    float* cn = e.lstm_c_next + vox * hid + ch0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cn + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
+    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(e.lstm_h) + vox * e.lstm_h_ld + ch0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 8) {
+      uint4 pk;
+      const __nv_bfloat162 t0 = __floats2bfloat162_rn(h[i], h[i + 1]), t1 = __floats2bfloat162_rn(h[i + 2], h[i + 3]);
+      const __nv_bfloat162 t2 = __floats2bfloat162_rn(h[i + 4], h[i + 5]), t3 = __floats2bfloat162_rn(h[i + 6], h[i + 7]);
+      pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<const uint32_t*>(&t2);
+      pk.w = *reinterpret_cast<const uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(hp + i) = pk;
+    }
+    if (e.lstm_act != nullptr) {
+      float* ap = e.lstm_act + vox * 4 * hid + ch0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        *reinterpret_cast<float4*>(ap + i) = make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]);
+        *reinterpret_cast<float4*>(ap + hid + i) = make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]);
+        *reinterpret_cast<float4*>(ap + 2 * hid + i) = make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]);
+        *reinterpret_cast<float4*>(ap + 3 * hid + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
+      }
     }
   }
 }
@@ -313,7 +391,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
+      if (p.epi.lstm_j > 0) epilogue_tile_lstm(p.epi, tacc, nt, valid, vox);
+      else epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -1847,6 +1926,8 @@ VFD_API int vfd_conv3d_fwd(const void* x, long long x_ld, int cin, const void* w
   epi.out = out;
   epi.stats = stats;
   epi.stats_ld = stats_ld;
+  epi.lstm_j = 0; epi.lstm_hid = 0; epi.lstm_c_cur = nullptr; epi.lstm_c_next = nullptr; epi.lstm_act = nullptr;
+  epi.lstm_h = nullptr; epi.lstm_h_ld = 0;
   if ((kd != 1 && kd != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
     return set_error(VFD_ERR_ARG, "kernel extents must be 1 or 3");
   if (res_enabled() && w_rows <= 256 && (stats == nullptr || stats_ld <= 256)) {
@@ -2157,4 +2238,40 @@ VFD_API int vfd_conv3d_wgrad_det(const void* dy, long long dy_ld, int cout, cons
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_ordered_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), elems, splits, acc);
   return check_launch("wgrad_ordered_reduce");
+}
+
+// ---- ConvLSTM step: gate conv (Conv2d == kd 1) with the cell update in its epilogue --------------------------------
+VFD_API int vfd_convlstm_step_fwd(const void* comb, long long comb_ld, int cin, const void* w_packed_perm, int cin_k,
+                                  const float* bias_perm, const float* c_cur, int hid, float* c_next, void* h_out,
+                                  long long h_ld, float* act, int N, int H, int W, int kh, int kw, int kc,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  if (comb == nullptr || w_packed_perm == nullptr || c_cur == nullptr || c_next == nullptr || h_out == nullptr)
+    return set_error(VFD_ERR_ARG, "convlstm_step_fwd: null pointer");
+  if (hid <= 0 || hid % 64) return set_error(VFD_ERR_ARG, "convlstm_step_fwd: hidden_dim must be a multiple of 64");
+  if ((kh != 1 && kh != 3) || kh != kw) return set_error(VFD_ERR_ARG, "convlstm_step_fwd: kernel must be 1x1 or 3x3");
+  if (kc != 16 && kc != 32 && kc != 64) return set_error(VFD_ERR_ARG, "kc must be 16, 32 or 64");
+  if (cin_k % kc || comb_ld % 8 || h_ld % 8 || h_ld < hid || (reinterpret_cast<uintptr_t>(comb) & 15) ||
+      (reinterpret_cast<uintptr_t>(h_out) & 15) || (reinterpret_cast<uintptr_t>(c_cur) & 15) ||
+      (reinterpret_cast<uintptr_t>(c_next) & 15) || (reinterpret_cast<uintptr_t>(act) & 15))
+    return set_error(VFD_ERR_ARG, "convlstm_step_fwd: tensors must be 16-byte aligned, channel strides multiples of 8");
+  const int w_rows = 4 * hid;
+  FwdParams p;
+  if (int e = fill_geom(p.g, N, 1, H, W, 1, kh, kw)) return e;
+  p.cblocks = cin_k / kc;
+  p.block_n = 256;                    // four gates x 64 hidden channels per accumulator tile
+  p.n_tiles = w_rows / 256;
+  Epilogue epi;
+  epi.n_rows = w_rows; epi.out_cols = 0; epi.out_ld = 0; epi.out_fp32 = 1; epi.bias = bias_perm; epi.out = nullptr;
+  epi.stats = nullptr; epi.stats_ld = 0;
+  epi.lstm_j = 64; epi.lstm_hid = hid; epi.lstm_c_cur = c_cur; epi.lstm_c_next = c_next; epi.lstm_act = act;
+  epi.lstm_h = h_out; epi.lstm_h_ld = h_ld;
+  p.epi = epi;
+  CUtensorMap tmA, tmB;
+  if (int e = make_act_map(&tmA, comb, comb_ld, cin, N, 1, H, W, kc, p.g.TW, p.g.TH, p.g.TD, p.g.TN)) return e;
+  if (int e = make_weight_map(&tmB, w_packed_perm, w_rows, (long long)p.g.ntaps * cin_k, kc, p.block_n)) return e;
+  if (kc == 64) return launch_fwd<64>(tmA, tmB, p, stream);
+  if (kc == 32) return launch_fwd<32>(tmA, tmB, p, stream);
+  return launch_fwd<16>(tmA, tmB, p, stream);
 }

@@ -124,6 +124,14 @@ def _conv3d_fwd_narrow(x, w_packed, bias, out):
               out.data_ptr(), _ld(out), out.shape[-1], N, D, H, W, _stream())
 
 
+def _convlstm_step_fwd(comb, w_perm, bias_perm, c_cur, c_next, h_out, act, kh, kw, kc):
+    N, D, H, W, C, ld = _check_cl(comb, "convlstm_step_fwd input")
+    hid = c_cur.shape[-1]
+    _lib.call("vfd_convlstm_step_fwd", comb.data_ptr(), ld, C, w_perm.data_ptr(), w_perm.shape[2], _ptr(bias_perm),
+              c_cur.data_ptr(), hid, c_next.data_ptr(), h_out.data_ptr(), _ld(h_out), _ptr(act), N, H, W, kh, kw, kc,
+              _stream())
+
+
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
@@ -365,6 +373,9 @@ conv3d_fwd = _define(
     "int kc, int out_cols, bool direct) -> ()", _conv3d_fwd)
 conv3d_fwd_narrow = _define("conv3d_fwd_narrow(Tensor x, Tensor w_packed, Tensor? bias, Tensor(a!) out) -> ()",
                             _conv3d_fwd_narrow)
+convlstm_step_fwd = _define(
+    "convlstm_step_fwd(Tensor comb, Tensor w_perm, Tensor? bias_perm, Tensor c_cur, Tensor(a!) c_next, Tensor(b!) h_out, "
+    "Tensor(c!)? act, int kh, int kw, int kc) -> ()", _convlstm_step_fwd)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
@@ -442,6 +453,7 @@ def set_deterministic(on=True):
 
 
 NARROW_CONV = os.environ.get("VFD_NARROW_CONV", "1") != "0"   # conv_last forward through csrc/conv_narrow.cu
+LSTM_FUSED = os.environ.get("VFD_LSTM_FUSED", "1") != "0"     # ConvLSTM step with the cell update in the gate conv's epilogue
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
@@ -907,6 +919,52 @@ def conv_weight_grad_into(g, x, weight, dst, accumulate):
         unpack_wgrad(acc, dst, accumulate)
 
 
+def conv_backward(x, weight, w_dgrad, kc_d, g, bias, bias_zero, need_x, need_w, need_b):
+    """Backward of a stride-1 'same' conv given the gradient of its output: (dx, dW, db), each None when not needed or
+    when it was written into the parameter's persistent gradient buffer (inside a fused train step). Shared by ConvFn
+    and the fused ConvLSTM step."""
+    cout, cin, kd, kh, kw = _wshape(weight)
+    g = as_cl_grad(g)
+    N, D, H, W, _, _ = _check_cl(g, "conv grad")
+    gx = gw = gb = None
+    # the weight gradient first: inside a fused step it goes to the side stream, forked here -- after dy is
+    # ready, before this layer's dgrad -- so that it overlaps the dgrad -> BatchNorm-backward chain
+    if need_w:
+        dst = STEP.direct(weight)
+        if dst is not None:
+            with STEP.side():
+                conv_weight_grad_into(g, x, weight, dst, not STEP.first_touch(weight))
+            STEP.hold(g, x)
+            STEP.done(weight)
+        else:
+            gw = torch.empty_like(weight, dtype=torch.float32)
+            conv_weight_grad_into(g, x, weight, gw, False)
+    if need_x:
+        gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
+        flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
+        _timed("conv_dgrad", flops,
+               lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
+                                  CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
+    if bias is not None and need_b:
+        dst = STEP.direct(bias)
+        if bias_zero:
+            if dst is None:
+                gb = zero_grad(cout, g.device)
+            else:                               # the buffer was zeroed at the start of the step
+                STEP.first_touch(bias)
+                STEP.done(bias)
+        else:
+            sums = torch.zeros(g.shape[-1], dtype=torch.float64, device=g.device)
+            channel_sum(g, sums)
+            sums = sums.float()
+            if dst is None:
+                gb = sums[:cout].clone()
+            else:
+                _put(dst, sums[:cout], not STEP.first_touch(bias))
+                STEP.done(bias)
+    return gx, gw, gb
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 "same" conv3d on channels-last bf16. `bias_grad_exact_zero` marks convs that feed a
     training-mode BatchNorm: there d loss / d bias is identically zero (BN removes the mean).
@@ -954,48 +1012,73 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        cout, cin, kd, kh, kw = _wshape(weight)
-        g = as_cl_grad(g)
-        N, D, H, W, _, _ = _check_cl(g, "conv grad")
-        gx = gw = gb = None
-        w_dgrad, kc_d = ctx.w_dgrad, ctx.kc_d
-        # the weight gradient first: inside a fused step it goes to the side stream, forked here -- after dy is
-        # ready, before this layer's dgrad -- so that it overlaps the dgrad -> BatchNorm-backward chain
-        if ctx.needs_input_grad[1]:
-            dst = STEP.direct(weight)
-            if dst is not None:
-                with STEP.side():
-                    conv_weight_grad_into(g, x, weight, dst, not STEP.first_touch(weight))
-                STEP.hold(g, x)
-                STEP.done(weight)
-            else:
-                gw = torch.empty_like(weight, dtype=torch.float32)
-                conv_weight_grad_into(g, x, weight, gw, False)
-        if ctx.needs_input_grad[0]:
-            gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
-            flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
-            _timed("conv_dgrad", flops,
-                   lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
-                                      CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
-        bias = ctx.bias_param
-        if bias is not None and ctx.needs_input_grad[2]:
-            dst = STEP.direct(bias)
-            if ctx.bias_zero:
-                if dst is None:
-                    gb = zero_grad(cout, g.device)
-                else:                               # the buffer was zeroed at the start of the step
-                    STEP.first_touch(bias)
-                    STEP.done(bias)
-            else:
-                sums = torch.zeros(g.shape[-1], dtype=torch.float64, device=g.device)
-                channel_sum(g, sums)
-                sums = sums.float()
-                if dst is None:
-                    gb = sums[:cout].clone()
-                else:
-                    _put(dst, sums[:cout], not STEP.first_touch(bias))
-                    STEP.done(bias)
+        gx, gw, gb = conv_backward(x, weight, ctx.w_dgrad, ctx.kc_d, g, ctx.bias_param, ctx.bias_zero,
+                                   ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None, None
+
+
+def lstm_gate_operands(weight, bias):
+    """Packed forward weights / bias of a ConvLSTM gate conv with the rows re-ordered for the fused step kernel:
+    [n-tile][gate i, f, o, g][64 hidden channels] instead of [gate][hidden channel] (models/convlstm.py:49 splits the
+    4*hid output channels gate-major), so that one 256-column accumulator tile holds all four gates of 64 channels."""
+    pk = _packed(weight)
+    hid = weight.shape[0] // 4
+    rows, taps, ck = pk.fwd.shape
+    w_perm = pk.fwd[:4 * hid].view(4, hid // 64, 64, taps, ck).permute(1, 0, 2, 3, 4).contiguous().view(4 * hid, taps, ck)
+    b_perm = None
+    if bias is not None:
+        b_perm = bias.detach().float().view(4, hid // 64, 64).permute(1, 0, 2).contiguous().view(-1)
+    return w_perm, b_perm, pk.kc_f
+
+
+def lstm_step_fusable(weight, cin_p):
+    """The fused ConvLSTM step serves hidden sizes that are multiples of 64 (one accumulator tile = 4 gates x 64
+    channels) with square 1x1 / 3x3 gate kernels."""
+    if weight.dim() != 4:
+        return False
+    rows, cin, kh, kw = weight.shape
+    return (LSTM_FUSED and rows % 256 == 0 and kh == kw and kh in (1, 3) and round_up(cin, 8) == cin_p
+            and not CONV_IMPL_DIRECT)
+
+
+class LstmStepFn(torch.autograd.Function):
+    """One ConvLSTM step (models/convlstm.py:46-58) as ONE forward kernel: the gate conv on tcgen05 with sigmoid / tanh
+    and the cell update in its epilogue -- the gates never go to HBM. (comb bf16 [N,1,H,W,in+hid], c_cur fp32
+    [N,H,W,hid]) -> (h_next bf16 [N,1,H,W,hid], c_next fp32). Backward: the cell kernel turns (dh, dc) into the gate
+    gradients, then the ordinary conv dgrad / wgrad on the un-permuted weights."""
+
+    @staticmethod
+    def forward(ctx, comb, c_cur, weight, bias, w_perm, b_perm, kc):
+        N, _, H, W, _, _ = _check_cl(comb, "convlstm step input")
+        hid = weight.shape[0] // 4
+        c_cur = c_cur.contiguous()
+        h = cl_empty(N, 1, H, W, hid, comb.device)
+        c_next = torch.empty_like(c_cur)
+        act = torch.empty(N, H, W, 4 * hid, dtype=torch.float32, device=comb.device)
+        flops = 2.0 * N * H * W * weight.shape[0] * weight.shape[1] * weight.shape[2] * weight.shape[3]
+        _timed("conv_fwd", flops,
+               lambda: convlstm_step_fwd(comb, w_perm, b_perm, c_cur, c_next, h, act, weight.shape[2], weight.shape[3], kc),
+               2.0 * comb.numel() + 2.0 * h.numel() + 4.0 * (2 * c_cur.numel() + act.numel()))
+        pk = _packed(weight)
+        ctx.save_for_backward(comb, weight, act, c_cur, c_next)
+        ctx.w_dgrad, ctx.kc_d = pk.dgrad, pk.kc_d
+        ctx.bias_param = bias
+        STEP.count_use(weight)
+        STEP.count_use(bias)
+        return h, c_next
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        comb, weight, act, c_cur, c_next = ctx.saved_tensors
+        N, _, H, W, _, _ = _check_cl(comb, "convlstm step saved input")
+        hid = weight.shape[0] // 4
+        dgates = torch.zeros(N, 1, H, W, 4 * hid, dtype=torch.bfloat16, device=act.device)
+        dc_cur = torch.empty_like(c_cur)
+        dh32 = None if dh is None else dh.reshape(N, H, W, hid).float().contiguous()
+        convlstm_cell_bwd(act, c_cur, c_next, dh32, None if dc is None else dc.contiguous(), dgates, dc_cur)
+        gx, gw, gb = conv_backward(comb, weight, ctx.w_dgrad, ctx.kc_d, dgates, ctx.bias_param, False,
+                                   ctx.needs_input_grad[0], ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        return gx, dc_cur, gw, gb, None, None, None
 
 
 class BnActFn(torch.autograd.Function):
