@@ -89,6 +89,12 @@ VFD_API int vfd_convlstm_step_fwd(const void* comb, long long comb_ld, int cin, 
                                   long long h_ld, float* act, int N, int H, int W, int kh, int kw, int kc,
                                   void* stream);
 
+/* dgrad of the same layer: g bf16 channels-last [N][D][H][W][g_ld] whose column 0 is the gradient of the logit,
+ * w_dgrad_packed = the dgrad operand vfd_conv3d_fwd takes for this layer ([32][27 taps, mirrored][w_ck], column 0 used),
+ * dx bf16 [N][D][H][W][dx_ld] (32 channels). Same result as vfd_conv3d_fwd on (g, w_dgrad_packed) up to summation order. */
+VFD_API int vfd_conv3d_dgrad_narrow(const void* g, long long g_ld, const void* w_dgrad_packed, int w_rows, int w_ck,
+                                    void* dx, long long dx_ld, int N, int D, int H, int W, void* stream);
+
 /* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
  * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
  * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =

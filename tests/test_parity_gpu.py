@@ -108,6 +108,28 @@ def test_narrow_conv_last_forward(N, D, H, W):
     want = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
     assert rel(got, want) < 1e-5 and rel(got, tc) < 1e-5
     assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    # dgrad (one gradient channel in, 32 out): taps as the GEMM's K dimension, against the tcgen05 path and autograd
+    gy = torch.randn(N, 1, D, H, W, generator=g).to(DEV)
+
+    def run_dgrad():
+        xc = ops.PackFn.apply(x, 0).requires_grad_(True)
+        yc = ops.ConvFn.apply(xc, w, b, True, False)
+        yc.backward(ops.PackFn.apply(gy, 0))
+        gx = torch.empty_like(x)
+        ops.unpack_ncdhw(xc.grad, gx)
+        return gx
+
+    before = _lib_calls("vfd_conv3d_dgrad_narrow")
+    gx_narrow = run_dgrad()
+    assert _lib_calls("vfd_conv3d_dgrad_narrow") == before + 1
+    ops.NARROW_CONV = False
+    try:
+        gx_tc = run_dgrad()
+    finally:
+        ops.NARROW_CONV = True
+    xr = x.bfloat16().float().requires_grad_(True)
+    F.conv3d(xr, w.bfloat16().float(), b, padding=1).backward(gy.bfloat16().float())
+    assert rel(gx_narrow, xr.grad) < 3e-3 and rel(gx_narrow, gx_tc) < 3e-3      # bf16-stored gradient
 
 
 @pytest.mark.parametrize("cin,cout,N,D,H,W,bias", [(3, 2, 2, 5, 9, 11, False), (8, 8, 1, 3, 7, 5, True), (3, 2, 4, 16, 32, 32, False)])

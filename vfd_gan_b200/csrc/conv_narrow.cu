@@ -223,6 +223,151 @@ conv_narrow_fwd_kernel(const NarrowParams p) {
   }
 }
 
+// ---- dgrad of the same layer: dx[u][c] = sum_tap g[u + off(tap)] * Wd[c][tap], one gradient channel in, 32 out ------
+// Here the taps are the GEMM's K dimension: A[u][tap] = g[u + off(tap)] is an im2col of a SCALAR field, gathered
+// straight into mma.sync A fragments from a three-plane shared-memory ring of the gradient (16 two-byte reads per 16
+// voxels), B[tap][c] = the dgrad-packed filter (32 x 32, in registers). 8 MMAs per 16 voxels instead of 27 K16 MMAs per
+// 128 voxels of which one of 16 K columns is used.
+struct NarrowDgradParams {
+  const bf16* g;        // channels-last [N][D][H][W][g_ld], column 0 = the gradient of the logit
+  long long g_ld;
+  const bf16* w;        // dgrad-packed weights [32 rows = ci][27 taps (mirrored)][w_ck], column 0
+  int w_ck;
+  bf16* dx;             // channels-last [N][D][H][W][dx_ld], 32 channels
+  long long dx_ld;
+  int N, D, H, W, tilesH, tilesW;
+};
+
+__global__ void __launch_bounds__(kNarrowThreads)
+conv_narrow_dgrad_kernel(const NarrowDgradParams p) {
+  __shared__ __align__(16) unsigned short ring[3][kPVpad];   // gradient planes d-1, d, d+1 of the haloed window (bf16 bits)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const unsigned short* wbits = reinterpret_cast<const unsigned short*>(p.w);
+  const unsigned short* gbits = reinterpret_cast<const unsigned short*>(p.g);
+  // B fragments: B[k = tap][n = c] = w[c][tap][0]; [n-tile][k-step][2]
+  uint32_t bfr[4][2][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c = 8 * nt + gq;
+        uint32_t v = 0u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int tap = 16 * ks + 8 * h2 + 2 * tq + j;
+          if (tap < kTaps) v |= static_cast<uint32_t>(wbits[(static_cast<size_t>(c) * kTaps + tap) * p.w_ck]) << (16 * j);
+        }
+        bfr[nt][ks][h2] = v;
+      }
+  // this lane's eight A columns (taps): plane index a (-1 for taps 27..31) and offset inside a haloed plane
+  int ta[2][2][2], trel[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int tap = 16 * ks + 8 * h2 + 2 * tq + j;
+        ta[ks][h2][j] = tap < kTaps ? tap / 9 : -1;
+        trel[ks][h2][j] = ((tap / 3) % 3) * kPW + tap % 3;
+      }
+  for (int i = tid; i < 3 * kPVpad; i += kNarrowThreads) (&ring[0][0])[i] = 0;
+  __syncthreads();
+
+  const int ncols = p.N * p.tilesH * p.tilesW;
+#pragma unroll 1
+  for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+    int t = col;
+    const int w0 = (t % p.tilesW) * kTW;
+    t /= p.tilesW;
+    const int h0 = (t % p.tilesH) * kTH;
+    const int n = t / p.tilesH;
+    // this thread's (at most two) scalars of a plane window
+    long long soff[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pv = tid + k * kNarrowThreads;
+      const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
+      soff[k] = (pv < kPV && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                    ? (static_cast<long long>(hh) * p.W + ww) * p.g_ld : -1;
+    }
+    const long long plane_elems = static_cast<long long>(p.H) * p.W * p.g_ld;
+    auto load_scalars = [&](int d, unsigned short (&v)[2]) {
+      const bool ok = d >= 0 && d < p.D;
+      const unsigned short* base = gbits + (static_cast<long long>(n) * p.D + (ok ? d : 0)) * plane_elems;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) v[k] = (ok && soff[k] >= 0) ? __ldg(base + soff[k]) : static_cast<unsigned short>(0);
+    };
+    auto store_scalars = [&](int slot, const unsigned short (&v)[2]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (tid + k * kNarrowThreads < kPV) ring[slot][tid + k * kNarrowThreads] = v[k];
+    };
+    unsigned short nxt[2];
+    // ring slot of plane j is (j + 1) % 3; planes -1 and D are the zero padding
+    load_scalars(-1, nxt);
+    store_scalars(0, nxt);
+    load_scalars(0, nxt);
+    store_scalars(1, nxt);
+    load_scalars(1, nxt);
+    for (int d = 0; d < p.D; ++d) {
+      // plane d + 1 into its slot (that of plane d - 2, which nobody reads any more), then fetch plane d + 2
+      store_scalars((d + 2) % 3, nxt);
+      __syncthreads();
+      load_scalars(d + 2, nxt);
+      const unsigned short* s0 = ring[d % 3];          // plane d - 1
+      const unsigned short* s1 = ring[(d + 1) % 3];    // plane d
+      const unsigned short* s2 = ring[(d + 2) % 3];    // plane d + 1
+#pragma unroll 1
+      for (int mt = warp; mt < kTH; mt += kNarrowThreads / 32) {     // one m-tile = the 16 voxels of window row mt
+        float acc[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t a[4];   // a0: rows gq, cols 2tq..; a1: rows gq + 8; a2 / a3: cols + 8
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+              uint32_t v = 0u;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int aa = ta[ks][h2][j];
+                if (aa >= 0) {
+                  const unsigned short* sp = aa == 0 ? s0 : (aa == 1 ? s1 : s2);
+                  v |= static_cast<uint32_t>(sp[mt * kPW + gq + 8 * r2 + trel[ks][h2][j]]) << (16 * j);
+                }
+              }
+              a[2 * h2 + r2] = v;
+            }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if (ks == 0) mma16816_zero(acc[nt], a[0], a[1], a[2], a[3], bfr[nt][0][0], bfr[nt][0][1]);
+            else mma16816(acc[nt], a[0], a[1], a[2], a[3], bfr[nt][1][0], bfr[nt][1][1]);
+          }
+        }
+        const int hh = h0 + mt;
+        if (hh < p.H) {
+          const long long row = ((static_cast<long long>(n) * p.D + d) * p.H + hh) * p.W + w0;
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            const int ww = gq + 8 * r2;
+            if (w0 + ww < p.W) {
+              bf16* o = p.dx + (row + ww) * p.dx_ld + 2 * tq;
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                *reinterpret_cast<__nv_bfloat162*>(o + 8 * nt) = __floats2bfloat162_rn(acc[nt][2 * r2], acc[nt][2 * r2 + 1]);
+            }
+          }
+        }
+      }
+      __syncthreads();   // every warp is done with plane d - 1's slot before the next step overwrites it
+    }
+  }
+}
+
 }  // namespace
 
 }  // namespace vfd
@@ -274,4 +419,30 @@ VFD_API int vfd_conv3d_fwd_narrow(const void* x, long long x_ld, int cin, const 
   if (grid > 3LL * sms) grid = 3LL * sms;       // three resident CTAs per SM, each walks several columns
   conv_narrow_fwd_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, kNarrowSmem, static_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("conv_narrow_fwd");
+}
+
+VFD_API int vfd_conv3d_dgrad_narrow(const void* g, long long g_ld, const void* w_dgrad_packed, int w_rows, int w_ck,
+                                    void* dx, long long dx_ld, int N, int D, int H, int W, void* stream_) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  if (g == nullptr || w_dgrad_packed == nullptr || dx == nullptr)
+    return set_error(VFD_ERR_ARG, "conv3d_dgrad_narrow: null pointer");
+  if (w_rows != 32 || w_ck < 1) return set_error(VFD_ERR_ARG, "conv3d_dgrad_narrow: serves 32 input channels only");
+  if (g_ld < 1 || dx_ld < 32 || dx_ld % 2 || (reinterpret_cast<uintptr_t>(dx) & 3) || (reinterpret_cast<uintptr_t>(g) & 1))
+    return set_error(VFD_ERR_ARG, "conv3d_dgrad_narrow: bad tensor layout");
+  if (static_cast<long long>(N) * D * H * W >= (1LL << 31))
+    return set_error(VFD_ERR_ARG, "conv3d_dgrad_narrow: more than 2^31 voxels");
+  NarrowDgradParams p;
+  p.g = static_cast<const bf16*>(g); p.g_ld = g_ld; p.w = static_cast<const bf16*>(w_dgrad_packed); p.w_ck = w_ck;
+  p.dx = static_cast<bf16*>(dx); p.dx_ld = dx_ld;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.tilesH = (H + kTH - 1) / kTH; p.tilesW = (W + kTW - 1) / kTW;
+  long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (grid > 8LL * sms) grid = 8LL * sms;       // eight 128-thread CTAs per SM, each walks several columns
+  conv_narrow_dgrad_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("conv_narrow_dgrad");
 }

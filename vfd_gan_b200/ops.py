@@ -132,6 +132,12 @@ def _convlstm_step_fwd(comb, w_perm, bias_perm, c_cur, c_next, h_out, act, kh, k
               _stream())
 
 
+def _conv3d_dgrad_narrow(g, w_dgrad, gx):
+    N, D, H, W, _, ld = _check_cl(g, "conv3d_dgrad_narrow gradient")
+    _lib.call("vfd_conv3d_dgrad_narrow", g.data_ptr(), ld, w_dgrad.data_ptr(), w_dgrad.shape[0], w_dgrad.shape[2],
+              gx.data_ptr(), _ld(gx), N, D, H, W, _stream())
+
+
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
@@ -376,6 +382,7 @@ conv3d_fwd_narrow = _define("conv3d_fwd_narrow(Tensor x, Tensor w_packed, Tensor
 convlstm_step_fwd = _define(
     "convlstm_step_fwd(Tensor comb, Tensor w_perm, Tensor? bias_perm, Tensor c_cur, Tensor(a!) c_next, Tensor(b!) h_out, "
     "Tensor(c!)? act, int kh, int kw, int kc) -> ()", _convlstm_step_fwd)
+conv3d_dgrad_narrow = _define("conv3d_dgrad_narrow(Tensor g, Tensor w_dgrad, Tensor(a!) gx) -> ()", _conv3d_dgrad_narrow)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
@@ -942,9 +949,14 @@ def conv_backward(x, weight, w_dgrad, kc_d, g, bias, bias_zero, need_x, need_w, 
     if need_x:
         gx = cl_empty(N, D, H, W, x.shape[-1], g.device)
         flops = 2.0 * N * D * H * W * cin * cout * kd * kh * kw
-        _timed("conv_dgrad", flops,
-               lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
-                                  CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
+        narrow = (NARROW_CONV and cout == 1 and (kd, kh, kw) == (3, 3, 3) and x.shape[-1] == 32
+                  and tuple(w_dgrad.shape[:2]) == (32, 27) and not CONV_IMPL_DIRECT)
+        if narrow:   # conv_last: one gradient channel in, 32 out -- taps as the GEMM's K dimension (conv_narrow.cu)
+            _timed("conv_dgrad", flops, lambda: conv3d_dgrad_narrow(g, w_dgrad, gx), 2.0 * (g.numel() + gx.numel()))
+        else:
+            _timed("conv_dgrad", flops,
+                   lambda: conv3d_fwd(g, w_dgrad, None, gx, None, kd, kh, kw, kc_d, x.shape[-1],
+                                      CONV_IMPL_DIRECT), 2.0 * (g.numel() + gx.numel()))
     if bias is not None and need_b:
         dst = STEP.direct(bias)
         if bias_zero:
