@@ -95,6 +95,12 @@ VFD_API int vfd_convlstm_step_fwd(const void* comb, long long comb_ld, int cin, 
 VFD_API int vfd_conv3d_dgrad_narrow(const void* g, long long g_ld, const void* w_dgrad_packed, int w_rows, int w_ck,
                                     void* dx, long long dx_ld, int N, int D, int H, int W, void* stream);
 
+/* weight gradient of the same layer: acc[c][tap] += sum_u g[u - off(tap)] * x[u][c] (fp32 [32][acc_ld], the layout
+ * vfd_conv3d_wgrad_thin fills for the tap-folded gradient), g and x each read once. Uses fp32 atomics across CTAs; the
+ * deterministic mode keeps vfd_tap_gather + vfd_conv3d_wgrad_thin_det for this layer. */
+VFD_API int vfd_conv3d_wgrad_narrow(const void* g, long long g_ld, const void* x, long long x_ld, float* acc, int acc_ld,
+                                    int N, int D, int H, int W, void* stream);
+
 /* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
  * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
  * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =

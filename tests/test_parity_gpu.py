@@ -113,23 +113,26 @@ def test_narrow_conv_last_forward(N, D, H, W):
 
     def run_dgrad():
         xc = ops.PackFn.apply(x, 0).requires_grad_(True)
-        yc = ops.ConvFn.apply(xc, w, b, True, False)
+        wp = w.clone().requires_grad_(True)
+        yc = ops.ConvFn.apply(xc, wp, b, True, False)
         yc.backward(ops.PackFn.apply(gy, 0))
         gx = torch.empty_like(x)
         ops.unpack_ncdhw(xc.grad, gx)
-        return gx
+        return gx, wp.grad
 
-    before = _lib_calls("vfd_conv3d_dgrad_narrow")
-    gx_narrow = run_dgrad()
-    assert _lib_calls("vfd_conv3d_dgrad_narrow") == before + 1
+    before = _lib_calls("vfd_conv3d_dgrad_narrow"), _lib_calls("vfd_conv3d_wgrad_narrow")
+    gx_narrow, gw_narrow = run_dgrad()
+    assert _lib_calls("vfd_conv3d_dgrad_narrow") == before[0] + 1 and _lib_calls("vfd_conv3d_wgrad_narrow") == before[1] + 1
     ops.NARROW_CONV = False
     try:
-        gx_tc = run_dgrad()
+        gx_tc, gw_tc = run_dgrad()
     finally:
         ops.NARROW_CONV = True
     xr = x.bfloat16().float().requires_grad_(True)
-    F.conv3d(xr, w.bfloat16().float(), b, padding=1).backward(gy.bfloat16().float())
+    wr = w.bfloat16().float().requires_grad_(True)
+    F.conv3d(xr, wr, b, padding=1).backward(gy.bfloat16().float())
     assert rel(gx_narrow, xr.grad) < 3e-3 and rel(gx_narrow, gx_tc) < 3e-3      # bf16-stored gradient
+    assert rel(gw_narrow, wr.grad) < 1e-4 and rel(gw_narrow, gw_tc) < 1e-4      # fp32 weight gradient
 
 
 @pytest.mark.parametrize("cin,cout,N,D,H,W,bias", [(3, 2, 2, 5, 9, 11, False), (8, 8, 1, 3, 7, 5, True), (3, 2, 4, 16, 32, 32, False)])

@@ -368,6 +368,174 @@ conv_narrow_dgrad_kernel(const NarrowDgradParams p) {
   }
 }
 
+// ---- weight gradient of the same layer: dW[tap][c] = sum_u g[u - off(tap)] * x[u][c] ---------------------------------
+// M = taps (32 rows, 27 used), N = the 32 input channels, K = voxels. The A operand (taps x voxels) is gathered from the
+// three-plane ring of the scalar gradient like in the dgrad kernel, the B operand (voxels x channels) comes from the
+// staged x rows through ldmatrix.trans; the 32 x 32 fp32 accumulator lives in registers for the whole kernel and is
+// reduced block-wide in warp order before one atomic per element. x and g are each read once.
+struct NarrowWgradParams {
+  const bf16* g;        // channels-last [N][D][H][W][g_ld], column 0 = the gradient of the logit
+  long long g_ld;
+  const bf16* x;        // channels-last [N][D][H][W][x_ld], 32 channels
+  long long x_ld;
+  float* acc;           // fp32 [32 channels][acc_ld]: acc[c][tap] += dW[tap][c]
+  int acc_ld;
+  int N, D, H, W, tilesH, tilesW;
+};
+
+__global__ void __launch_bounds__(kNarrowThreads)
+conv_narrow_wgrad_kernel(const NarrowWgradParams p) {
+  __shared__ __align__(16) unsigned short ring[3][kPVpad];
+  __shared__ __align__(16) uint8_t xs[kTH * kTW * kXRow];        // 128 voxels x (64 B + 16 B pad)
+  __shared__ float red[32 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const unsigned short* gbits = reinterpret_cast<const unsigned short*>(p.g);
+  // A rows of this lane: taps gq, gq + 8 (m-tile 0) and 16 + gq, 24 + gq (m-tile 1): plane selector and window offset
+  int ta[2][2], trel[2][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const int tap = 16 * m + 8 * r2 + gq;
+      const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+      ta[m][r2] = tap < kTaps ? a : -1;
+      trel[m][r2] = (2 - b) * kPW + (2 - c);        // g[u - off(tap)] relative to x voxel (row, col) of the window
+    }
+  float acc[2][4][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][nt][j] = 0.f;
+  for (int i = tid; i < 3 * kPVpad; i += kNarrowThreads) (&ring[0][0])[i] = 0;
+  for (int i = tid; i < 32 * 32; i += kNarrowThreads) red[i] = 0.f;
+  __syncthreads();
+  const uint32_t xs_s = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
+  const int mat = lane >> 3, mrow = lane & 7;
+  const uint32_t b_off = ((mat & 1) * 8 + mrow) * kXRow + (mat >> 1) * 16;   // + n-tile pair * 32 bytes
+
+  const int ncols = p.N * p.tilesH * p.tilesW;
+#pragma unroll 1
+  for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+    int t = col;
+    const int w0 = (t % p.tilesW) * kTW;
+    t /= p.tilesW;
+    const int h0 = (t % p.tilesH) * kTH;
+    const int n = t / p.tilesH;
+    long long soff[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pv = tid + k * kNarrowThreads;
+      const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
+      soff[k] = (pv < kPV && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                    ? (static_cast<long long>(hh) * p.W + ww) * p.g_ld : -1;
+    }
+    // this thread's four 16-byte chunks of the 8 x 16 x-window (no halo): chunk c -> voxel c >> 2, part c & 3
+    int xoff[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = tid + k * kNarrowThreads;
+      const int v = c >> 2, hh = h0 + v / kTW, ww = w0 + v % kTW;
+      xoff[k] = (hh < p.H && ww < p.W) ? static_cast<int>((static_cast<long long>(hh) * p.W + ww) * p.x_ld + (c & 3) * 8) : -1;
+    }
+    const long long gplane = static_cast<long long>(p.H) * p.W * p.g_ld;
+    const long long xplane = static_cast<long long>(p.H) * p.W * p.x_ld;
+    auto load_scalars = [&](int d, unsigned short (&v)[2]) {
+      const bool ok = d >= 0 && d < p.D;
+      const unsigned short* base = gbits + (static_cast<long long>(n) * p.D + (ok ? d : 0)) * gplane;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) v[k] = (ok && soff[k] >= 0) ? __ldg(base + soff[k]) : static_cast<unsigned short>(0);
+    };
+    auto store_scalars = [&](int slot, const unsigned short (&v)[2]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (tid + k * kNarrowThreads < kPV) ring[slot][tid + k * kNarrowThreads] = v[k];
+    };
+    auto load_x = [&](int d, uint4 (&v)[4]) {
+      const bf16* base = p.x + (static_cast<long long>(n) * p.D + d) * xplane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = (d < p.D && xoff[k] >= 0) ? __ldg(reinterpret_cast<const uint4*>(base + xoff[k])) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    unsigned short nxt[2];
+    uint4 xn[4];
+    load_scalars(-1, nxt);
+    store_scalars(0, nxt);
+    load_scalars(0, nxt);
+    store_scalars(1, nxt);
+    load_scalars(1, nxt);
+    load_x(0, xn);
+    for (int d = 0; d < p.D; ++d) {
+      store_scalars((d + 2) % 3, nxt);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = tid + k * kNarrowThreads;
+        *reinterpret_cast<uint4*>(xs + (c >> 2) * kXRow + (c & 3) * 16) = xn[k];
+      }
+      __syncthreads();
+      load_scalars(d + 2, nxt);
+      load_x(d + 1, xn);
+      const unsigned short* s0 = ring[d % 3];          // plane d - 1
+      const unsigned short* s1 = ring[(d + 1) % 3];    // plane d
+      const unsigned short* s2 = ring[(d + 2) % 3];    // plane d + 1
+#pragma unroll 1
+      for (int mt = warp; mt < kTH; mt += kNarrowThreads / 32) {     // K step = the 16 voxels of window row mt
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {     // a[.][r2 + 2 * h2]: row gq + 8 r2, voxel columns 2tq + 8 h2, + 1
+              uint32_t v = 0u;
+              const int aa = ta[m][r2];
+              if (aa >= 0) {
+                const unsigned short* sp = aa == 0 ? s2 : (aa == 1 ? s1 : s0);   // tap plane a reads g plane d - a + 1
+                const unsigned short* q = sp + mt * kPW + trel[m][r2] + 2 * tq + 8 * h2;
+                v = static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 16);
+              }
+              a[m][r2 + 2 * h2] = v;
+            }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          uint32_t b0, b1, b2, b3;   // n-tile 2np: (b0, b1); n-tile 2np + 1: (b2, b3)
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(xs_s + mt * kTW * kXRow + b_off + np * 32));
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            mma16816(acc[m][2 * np], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
+            mma16816(acc[m][2 * np + 1], a[m][0], a[m][1], a[m][2], a[m][3], b2, b3);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // block reduction in warp order, then one atomic per valid (tap, channel)
+  for (int w = 0; w < kNarrowThreads / 32; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int tap = 16 * m + gq, c = 8 * nt + 2 * tq;
+          red[tap * 32 + c] += acc[m][nt][0];
+          red[tap * 32 + c + 1] += acc[m][nt][1];
+          red[(tap + 8) * 32 + c] += acc[m][nt][2];
+          red[(tap + 8) * 32 + c + 1] += acc[m][nt][3];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 32 * 32; i += kNarrowThreads) {
+    const int tap = i >> 5, c = i & 31;
+    if (tap < kTaps) atomicAdd(p.acc + static_cast<size_t>(c) * p.acc_ld + tap, red[i]);
+  }
+}
+
 }  // namespace
 
 }  // namespace vfd
@@ -445,4 +613,29 @@ VFD_API int vfd_conv3d_dgrad_narrow(const void* g, long long g_ld, const void* w
   if (grid > 8LL * sms) grid = 8LL * sms;       // eight 128-thread CTAs per SM, each walks several columns
   conv_narrow_dgrad_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("conv_narrow_dgrad");
+}
+
+VFD_API int vfd_conv3d_wgrad_narrow(const void* g, long long g_ld, const void* x, long long x_ld, float* acc, int acc_ld,
+                                    int N, int D, int H, int W, void* stream_) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  if (g == nullptr || x == nullptr || acc == nullptr) return set_error(VFD_ERR_ARG, "conv3d_wgrad_narrow: null pointer");
+  if (g_ld < 1 || x_ld < 32 || x_ld % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(g) & 1) ||
+      acc_ld < 27)
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_narrow: bad tensor layout");
+  if (static_cast<long long>(N) * D * H * W >= (1LL << 31))
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_narrow: more than 2^31 voxels");
+  NarrowWgradParams p;
+  p.g = static_cast<const bf16*>(g); p.g_ld = g_ld; p.x = static_cast<const bf16*>(x); p.x_ld = x_ld;
+  p.acc = acc; p.acc_ld = acc_ld;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.tilesH = (H + kTH - 1) / kTH; p.tilesW = (W + kTW - 1) / kTW;
+  long long grid = static_cast<long long>(N) * p.tilesH * p.tilesW;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (grid > 4LL * sms) grid = 4LL * sms;
+  conv_narrow_wgrad_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("conv_narrow_wgrad");
 }

@@ -138,6 +138,13 @@ def _conv3d_dgrad_narrow(g, w_dgrad, gx):
               gx.data_ptr(), _ld(gx), N, D, H, W, _stream())
 
 
+def _conv3d_wgrad_narrow(g, x, acc):
+    N, D, H, W, _, g_ld = _check_cl(g, "conv3d_wgrad_narrow gradient")
+    _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad_narrow input")
+    _lib.call("vfd_conv3d_wgrad_narrow", g.data_ptr(), g_ld, x.data_ptr(), x_ld, acc.data_ptr(), acc.shape[-1], N, D, H, W,
+              _stream())
+
+
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
@@ -383,6 +390,7 @@ convlstm_step_fwd = _define(
     "convlstm_step_fwd(Tensor comb, Tensor w_perm, Tensor? bias_perm, Tensor c_cur, Tensor(a!) c_next, Tensor(b!) h_out, "
     "Tensor(c!)? act, int kh, int kw, int kc) -> ()", _convlstm_step_fwd)
 conv3d_dgrad_narrow = _define("conv3d_dgrad_narrow(Tensor g, Tensor w_dgrad, Tensor(a!) gx) -> ()", _conv3d_dgrad_narrow)
+conv3d_wgrad_narrow = _define("conv3d_wgrad_narrow(Tensor g, Tensor x, Tensor(a!) acc) -> ()", _conv3d_wgrad_narrow)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
@@ -461,6 +469,7 @@ def set_deterministic(on=True):
 
 NARROW_CONV = os.environ.get("VFD_NARROW_CONV", "1") != "0"   # conv_last forward through csrc/conv_narrow.cu
 LSTM_FUSED = os.environ.get("VFD_LSTM_FUSED", "1") != "0"     # ConvLSTM step with the cell update in the gate conv's epilogue
+NARROW_WGRAD = os.environ.get("VFD_NARROW_WGRAD", "1") != "0"
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
@@ -856,7 +865,9 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     cols = round_up(taps * cs, 8)
     other = cout if mode == "x" else cin
     fused = THIN_WGRAD and other <= 32 and (mode, kd, kh, kw, cs) in _FUSED_FOLDS
-    folded = None if fused else cl_empty(N, D, H, W, cols, g.device)
+    narrow = (NARROW_CONV and NARROW_WGRAD and mode == "y" and (kd, kh, kw, cout) == (3, 3, 3, 1) and cin == 32
+              and x.shape[-1] == 32 and not DETERMINISTIC)
+    folded = None if (fused or narrow) else cl_empty(N, D, H, W, cols, g.device)
 
     def run():
         if mode == "x":     # X'[v][t*cin+ci] = x[v+off(t)][ci];  acc[0][t*cin+ci][co]
@@ -866,7 +877,9 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
                 tap_gather(x, cs, folded, kd, kh, kw, 1)
                 _wgrad_1x1(g, cout, folded, taps * cin, acc)
         else:               # Y'[u][t*cout+co] = dy[u-off(t)][co]; acc[0][ci][t*cout+co]
-            if fused:
+            if narrow:      # conv_last: the gather and the GEMM in one kernel (csrc/conv_narrow.cu)
+                conv3d_wgrad_narrow(g, x, acc)
+            elif fused:
                 conv3d_wgrad_thin(g, taps * cout, x, cin, acc, 2, cs, kd, kh, kw)
             else:
                 tap_gather(g, cs, folded, kd, kh, kw, -1)
