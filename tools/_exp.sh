@@ -1,6 +1,7 @@
-for rep in 1 2; do for f in 0 1; do
-VFD_NARROW_WGRAD=$f python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile --no-flow > gpurun_out/r2ak_bench_$f.json 2> gpurun_out/r2ak_bench.err
+python -m pytest tests/ -x -q -m gpu 2>&1 | grep -E "^E  |passed|failed" | head -8
+python bench.py > gpurun_out/r2al_bench_default.json 2> gpurun_out/r2al_bench_default.err; echo "bench rc=$?"
 python -c "
-import json,sys
-d=json.loads(open('gpurun_out/r2ak_bench_$f.json').read().strip().splitlines()[-1]); print('NARROW_WGRAD=$f ms_per_step', d['ms_per_step'])"
-done; done
+import json
+d=json.loads(open('gpurun_out/r2al_bench_default.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['cpu_baseline']['value'], d['roofline']['all_conv'], d['roofline']['frac'], d['clocks'])"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
