@@ -98,7 +98,7 @@ def lib():
                 "(vfd_gan_b200 has no CPU fallback)")
         # tools/gpu_stage_probe.py sets VFD_DEBUG_LIB=1: every entry point then comes from libvfd_b200_debug.so (a
         # superset of the product library), whose stage-isolation switches act on the kernels it launches
-        L = ctypes.CDLL(DEBUG_LIB_PATH if os.environ.get("VFD_DEBUG_LIB") == "1" else LIB_PATH)
+        L = ctypes.CDLL(os.environ.get("VFD_LIB_OVERRIDE") or (DEBUG_LIB_PATH if os.environ.get("VFD_DEBUG_LIB") == "1" else LIB_PATH))
         L.vfd_last_error.restype = ctypes.c_char_p
         L.vfd_last_error.argtypes = []
         L.vfd_abi_version.restype = ctypes.c_int

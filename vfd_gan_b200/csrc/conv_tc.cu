@@ -30,6 +30,11 @@
 
 namespace vfd {
 
+#ifdef VFD_TC_FLOAT_STATS
+typedef float tc_stat_t;   // experiment: fp32 shared statistics (order-dependent)
+#else
+typedef double tc_stat_t;  // exact sums of fp32 partials: order-independent
+#endif
 constexpr int kTileM = 128;
 constexpr int kFwdThreads = 192;  // warp0: TMA producer, warp1: MMA issuer, warps2-5: epilogue
 constexpr int kMaxStages = 8;
@@ -83,8 +88,8 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
 // One accumulator tile (this warp's 32 TMEM lanes x block_n columns) -> bias, convert, store, and
 // optionally per-channel statistics into the CTA's shared accumulators. Warp-collective.
 __device__ __forceinline__ void epilogue_tile(const Epilogue& e, uint32_t tacc, int block_n, int col0,
-                                              bool valid, long long vox, int lane, double* s_sum,
-                                              double* s_sq) {
+                                              bool valid, long long vox, int lane, tc_stat_t* s_sum,
+                                              tc_stat_t* s_sq) {
   for (int c = 0; c < block_n; c += 32) {
     float v[32];
     if (c + 32 <= block_n) {
@@ -142,22 +147,22 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& e, uint32_t tacc, 
       if (c + lane < block_n && col + lane < 1024) {
         // double accumulators: sums of fp32 partials are exact there (24-bit mantissas, a few thousand summands), so
         // the result does not depend on the order in which the epilogue warps arrive
-        atomicAdd(&s_sum[col + lane], static_cast<double>(cs));
-        atomicAdd(&s_sq[col + lane], static_cast<double>(cq));
+        atomicAdd(&s_sum[col + lane], static_cast<tc_stat_t>(cs));
+        atomicAdd(&s_sq[col + lane], static_cast<tc_stat_t>(cq));
       }
     }
   }
 }
 
 // After the last tile: the four epilogue warps publish the CTA's statistics.
-__device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_thread, const double* s_sum,
-                                                     const double* s_sq) {
+__device__ __forceinline__ void epilogue_flush_stats(const Epilogue& e, int epi_thread, const tc_stat_t* s_sum,
+                                                     const tc_stat_t* s_sq) {
   if (e.stats == nullptr) return;
   asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
   for (int j = epi_thread; j < e.stats_ld && j < 1024; j += 128) {
-    if (s_sum[j] != 0.0 || s_sq[j] != 0.0) {
-      atomicAdd(e.stats + j, s_sum[j]);
-      atomicAdd(e.stats + e.stats_ld + j, s_sq[j]);
+    if (s_sum[j] != 0 || s_sq[j] != 0) {
+      atomicAdd(e.stats + j, static_cast<double>(s_sum[j]));
+      atomicAdd(e.stats + e.stats_ld + j, static_cast<double>(s_sq[j]));
     }
   }
 }
@@ -260,13 +265,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ double s_sum[1024], s_sq[1024];
+  __shared__ tc_stat_t s_sum[1024], s_sq[1024];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
   if (p.epi.stats != nullptr)
-    for (int i = threadIdx.x; i < 1024; i += kFwdThreads) s_sum[i] = s_sq[i] = 0.0;
+    for (int i = threadIdx.x; i < 1024; i += kFwdThreads) s_sum[i] = s_sq[i] = 0;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -391,8 +396,11 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#ifndef VFD_TC_NO_LSTM
       if (p.epi.lstm_j > 0) epilogue_tile_lstm(p.epi, tacc, nt, valid, vox);
-      else epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
+      else
+#endif
+      epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -472,7 +480,7 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ uint64_t a_full[kResMaxASlots], a_empty[kResMaxASlots];
   __shared__ uint64_t b_full, acc_full[4], acc_empty[4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ double s_sum[256], s_sq[256];   // double: exact sums of the warps' fp32 partials, order-independent
+
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -498,7 +506,6 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 256; i += kRes2Threads) s_sum[i] = s_sq[i] = 0.0;
   if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -799,6 +806,15 @@ conv_fwd_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (lane == 0) bulk_wait_group<0>();
     if (do_stats) {
+      // The CTA's statistics meet in fp64 (exact sums of the warps' fp32 partials: order-independent). The 4 KB live in
+      // the epilogue staging area, which is free once every epilogue warp has drained its TMA stores -- static shared
+      // memory for them cost 2 KB of the input-slot budget and with it up to 3.7 % on the STCNN step.
+      double* s_sum = reinterpret_cast<double*>(smem_stage);
+      double* s_sq = s_sum + 256;
+      __syncwarp();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ew * 32 + lane; i < 512; i += 256) s_sum[i] = 0.0;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mma_stats) {
         if (lane < 4) {   // every accumulator row holds the same column sums: lanes 0-3 own columns 8n + 2t, +1
 #pragma unroll
@@ -1695,7 +1711,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   return check_launch("conv_fwd_tc");
 }
 
-constexpr int kResBudget = 221 * 1024;   // + 1 KB alignment slack + ~4.3 KB static (fp64 statistics) <= 227 KB
+constexpr int kResBudget = 223 * 1024;   // + 1 KB alignment slack + ~2.3 KB static <= 227 KB
 
 // 5-D map over the conv output for the epilogue's TMA stores: box = 32 channels x 8 (w) x 4 (h) voxels,
 // i.e. the 32 accumulator rows one epilogue warp owns.
@@ -1807,7 +1823,7 @@ static int try_launch_res(const void* x, long long x_ld, int cin, const void* w_
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_res_kernel<KC, KHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         222 * 1024);
+                                         224 * 1024);
     if (e != cudaSuccess) {
       *err = set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_res)");
       return 0;

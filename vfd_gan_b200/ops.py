@@ -239,7 +239,7 @@ def _bn_act_bwd(y, cvalid, mean, invstd, scale, shift, slope, g_full, g_pool, pd
               scale.data_ptr(), shift.data_ptr(), slope, _ptr(g_full), 0 if g_full is None else _ld(g_full),
               _ptr(g_pool), 0 if g_pool is None else _ld(g_pool), pd, ph, pw, drop_p, seed, _ptr(seed_dev),
               (1 if train else 0) | (2 if pool_bcast else 0) | (4 if accumulate else 0), sums.data_ptr(), c1.data_ptr(), c2.data_ptr(), dgamma.data_ptr(),
-              dbeta.data_ptr(), dy.data_ptr(), _ld(dy), bn_ticket(y.device).data_ptr(), _stream())
+              dbeta.data_ptr(), dy.data_ptr(), _ld(dy), bn_ticket(y.device).data_ptr() if BN_TICKET else None, _stream())
 
 
 def _tap_gather(src, cs, dst, kd, kh, kw, sign):
@@ -470,6 +470,7 @@ def set_deterministic(on=True):
 NARROW_CONV = os.environ.get("VFD_NARROW_CONV", "1") != "0"   # conv_last forward through csrc/conv_narrow.cu
 LSTM_FUSED = os.environ.get("VFD_LSTM_FUSED", "1") != "0"     # ConvLSTM step with the cell update in the gate conv's epilogue
 NARROW_WGRAD = os.environ.get("VFD_NARROW_WGRAD", "1") != "0"
+BN_TICKET = os.environ.get("VFD_BN_TICKET", "1") != "0"       # BatchNorm backward: last-block finalize instead of a launch
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
