@@ -30,11 +30,7 @@
 
 namespace vfd {
 
-#ifdef VFD_TC_FLOAT_STATS
-typedef float tc_stat_t;   // experiment: fp32 shared statistics (order-dependent)
-#else
-typedef double tc_stat_t;  // exact sums of fp32 partials: order-independent
-#endif
+typedef double tc_stat_t;  // shared statistics accumulators: exact sums of fp32 partials, hence order-independent
 constexpr int kTileM = 128;
 constexpr int kFwdThreads = 192;  // warp0: TMA producer, warp1: MMA issuer, warps2-5: epilogue
 constexpr int kMaxStages = 8;
@@ -396,11 +392,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-#ifndef VFD_TC_NO_LSTM
       if (p.epi.lstm_j > 0) epilogue_tile_lstm(p.epi, tacc, nt, valid, vox);
-      else
-#endif
-      epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
+      else epilogue_tile(p.epi, tacc, p.block_n, col0, valid, vox, lane, s_sum, s_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
