@@ -1677,13 +1677,29 @@ static int num_sms() {
   return sms;
 }
 
-constexpr int kSmemBudget = 200 * 1024;
+// ring-buffer budgets of the streaming kernels (diagnostics: VFD_TC_BUDGET_KB for conv_fwd_tc, <= 208 because of its 16 KB
+// of static statistics; VFD_WG_BUDGET_KB for the weight-gradient kernels, <= 222)
+static int env_kb(const char* name, int def_kb, int lo, int hi) {
+  if (const char* e = getenv(name)) {
+    const int kb = atoi(e);
+    if (kb >= lo && kb <= hi) return kb * 1024;
+  }
+  return def_kb * 1024;
+}
+static int tc_budget() {
+  static int b = env_kb("VFD_TC_BUDGET_KB", 200, 64, 208);
+  return b;
+}
+static int wg_budget() {
+  static int b = env_kb("VFD_WG_BUDGET_KB", 200, 64, 222);
+  return b;
+}
 
 template <int KC>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams& p,
                       cudaStream_t stream) {
   const int stage_bytes = ((kTileM + p.block_n) * KC * 2 + 1023) & ~1023;
-  int stages = kSmemBudget / stage_bytes;
+  int stages = tc_budget() / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VFD_ERR_ARG, "conv tile does not fit in shared memory");
   p.stages = stages;
@@ -1693,7 +1709,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, FwdParams&
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel<KC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024);   // + 16.2 KB static
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);   // + 16.2 KB static
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fwd_tc)");
     attr_set = true;
   }
@@ -2011,7 +2027,7 @@ static int launch_wgrad3(const void* dy, long long dy_ld, int cout, const void* 
   q.plane_bytes = (16 + kh - 1) * (8 + kh - 1) * 128;
   q.plane_stride = (q.plane_bytes + 1023) & ~1023;
   q.stage_bytes = 2 * q.plane_stride + q.nbY * kWgBoxBytes;
-  int stages = kSmemBudget / q.stage_bytes;
+  int stages = wg_budget() / q.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VFD_ERR_ARG, "conv3d_wgrad: swapped tile does not fit in shared memory");
   q.stages = stages;
@@ -2076,7 +2092,7 @@ static int wgrad_dispatch(const void* dy, long long dy_ld, int cout, const void*
     q.na = cout > 64 ? 2 : 1;
     q.nb = (q.ci_n + 63) / 64;
     q.stage_bytes = (q.na + q.nb) * kWgBoxBytes;
-    int stages = kSmemBudget / q.stage_bytes;
+    int stages = wg_budget() / q.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 4) {
       q.stages = stages;
@@ -2126,7 +2142,7 @@ static int wgrad_dispatch(const void* dy, long long dy_ld, int cout, const void*
       q.plane_bytes = (16 + kh - 1) * (8 + kw - 1) * 128;
       q.plane_stride = (q.plane_bytes + 1023) & ~1023;
       q.stage_bytes = 2 * kWgBoxBytes + q.nb * q.plane_stride;
-      int stages = kSmemBudget / q.stage_bytes;
+      int stages = wg_budget() / q.stage_bytes;
       if (stages > kMaxStages) stages = kMaxStages;
       q.tmem_cols = 32;
       while (q.tmem_cols < khw * q.ci_n) q.tmem_cols *= 2;
@@ -2176,7 +2192,7 @@ static int wgrad_dispatch(const void* dy, long long dy_ld, int cout, const void*
   p.det_stride = det_stride;
   const int nb_slots = (p.block_n + 63) / 64;
   const int stage_bytes = (2 + nb_slots) * kWgBoxBytes;
-  int stages = kSmemBudget / stage_bytes;
+  int stages = wg_budget() / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VFD_ERR_ARG, "wgrad tile does not fit in shared memory");
   p.stages = stages;
