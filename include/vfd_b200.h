@@ -101,6 +101,13 @@ VFD_API int vfd_conv3d_dgrad_narrow(const void* g, long long g_ld, const void* w
 VFD_API int vfd_conv3d_wgrad_narrow(const void* g, long long g_ld, const void* x, long long x_ld, float* acc, int acc_ld,
                                     int N, int D, int H, int W, void* stream);
 
+/* weight gradient of the first layers (1x3x3 over three input channels, cout <= 32; NetG / SDisc dconv1 spatial
+ * convs): acc[tap * 3 + c][co] += sum_v dy[v][co] * x[v + off(tap)][c] (fp32 [32][acc_ld], the layout of the tap-folded
+ * path), x and dy read once, no folded scratch tensor. fp32 atomics across CTAs; the deterministic mode keeps
+ * vfd_tap_gather + vfd_conv3d_wgrad_thin_det. */
+VFD_API int vfd_conv3d_wgrad_first(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, float* acc,
+                                   int acc_ld, int N, int D, int H, int W, void* stream);
+
 /* Deterministic variants (opt-in, VFD_DETERMINISTIC=1 / ops.set_deterministic): the voxel-range splits (thin
  * kernels: the blocks) keep their own partial accumulators in `workspace` instead of meeting in fp32 atomics, and an
  * ordered second pass adds them to acc. Same arguments and accumulator layout as the plain entry points; workspace =

@@ -135,6 +135,30 @@ def test_narrow_conv_last_forward(N, D, H, W):
     assert rel(gw_narrow, wr.grad) < 1e-4 and rel(gw_narrow, gw_tc) < 1e-4      # fp32 weight gradient
 
 
+@pytest.mark.parametrize("cout,N,D,H,W", [(21, 2, 4, 16, 16), (14, 1, 3, 20, 12), (8, 2, 1, 7, 33), (32, 1, 2, 9, 50),
+                                          (21, 2, 16, 112, 112)])
+def test_first_layer_weight_gradient_kernel(cout, N, D, H, W):
+    """dW of the 1x3x3 first-layer convs (3 input channels) from csrc/conv_narrow.cu (A fragments gathered from a haloed
+    three-channel window, no tap-folded scratch tensor) against autograd on the bf16-rounded operands and against the
+    tap_gather + thin-kernel path it replaces."""
+    g = torch.Generator().manual_seed(cout * 100 + H)
+    x = torch.randn(N, 3, D, H, W, generator=g).to(DEV)
+    w = (torch.randn(cout, 3, 1, 3, 3, generator=g) * 0.1).to(DEV)
+    b = torch.zeros(cout, device=DEV)
+    gy = torch.randn(N, cout, D, H, W, generator=g).to(DEV)
+    before = _lib_calls("vfd_conv3d_wgrad_first")
+    got = _conv_all(x, w, b, gy, direct=False)[2]
+    assert _lib_calls("vfd_conv3d_wgrad_first") == before + 1
+    ops.FIRST_WGRAD = False
+    try:
+        old = _conv_all(x, w, b, gy, direct=False)[2]
+    finally:
+        ops.FIRST_WGRAD = True
+    wr = w.bfloat16().float().requires_grad_(True)
+    F.conv3d(x.bfloat16().float(), wr, None, padding=(0, 1, 1)).backward(gy.bfloat16().float())
+    assert rel(got, wr.grad) < 1e-4 and rel(got, old) < 1e-4
+
+
 @pytest.mark.parametrize("cin,cout,N,D,H,W,bias", [(3, 2, 2, 5, 9, 11, False), (8, 8, 1, 3, 7, 5, True), (3, 2, 4, 16, 32, 32, False)])
 def test_tiny_pointwise_conv_and_fused_statistics(cin, cout, N, D, H, W, bias):
     """1x1x1 convs with <= 8 channels on both sides take the CUDA-core streaming kernel (bf16 output): same

@@ -22,6 +22,7 @@ SIGNATURES = {
     "vfd_conv3d_fwd_narrow": [_p, _ll, _i, _p, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_dgrad_narrow": [_p, _ll, _p, _i, _i, _p, _ll, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_narrow": [_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _i, _p],
+    "vfd_conv3d_wgrad_first": [_p, _ll, _i, _p, _ll, _p, _i, _i, _i, _i, _i, _p],
     "vfd_convlstm_step_fwd": [_p, _ll, _i, _p, _i, _p, _p, _i, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p],
     "vfd_conv3d_wgrad_det_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
     "vfd_conv3d_wgrad_det": [_p, _ll, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],

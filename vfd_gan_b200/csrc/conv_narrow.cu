@@ -536,6 +536,160 @@ conv_narrow_wgrad_kernel(const NarrowWgradParams p) {
   }
 }
 
+// ---- weight gradient of the FIRST layers: 1x3x3, three input channels (NetG dconv1 / SDisc dconv1 spatial convs,
+// models/mygannet.py:37,130 through models/spatiotempconv.py:49-50) --------------------------------------------------
+//   dW[co][c][tap] = sum_v dy[v][co] * x[v + off(tap)][c]        M = (tap, c) = 27 rows, N = cout <= 32, K = voxels
+// The tap-folded path writes x as a 27-channel tensor (411 MB at the bench size) and reads it back; here the A operand
+// is gathered from a haloed three-channel window in shared memory straight into mma.sync fragments, the B operand is the
+// staged dy rows through ldmatrix.trans, and x (16 bytes per voxel) and dy are read once.
+struct FirstWgradParams {
+  const bf16* x;        // channels-last [N][D][H][W][x_ld], 3 valid channels
+  long long x_ld;
+  const bf16* dy;       // channels-last [N][D][H][W][dy_ld], cout valid channels
+  long long dy_ld;
+  int cout;
+  float* acc;           // fp32 [32 rows = tap * 3 + c][acc_ld]: acc[r][co] += dW
+  int acc_ld;
+  int N, D, H, W, tilesH, tilesW;
+};
+
+__global__ void __launch_bounds__(kNarrowThreads)
+conv_first_wgrad_kernel(const FirstWgradParams p) {
+  __shared__ __align__(16) unsigned short xw[3][kPVpad];           // haloed window, one plane per input channel
+  __shared__ __align__(16) uint8_t ys[kTH * kTW * kXRow];          // 128 dy rows x (64 B + 16 B pad)
+  __shared__ float red[32 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int ychunks = (p.cout + 7) >> 3;                            // 16-byte chunks of a dy row
+  // A rows of this lane: r = 16 m + 8 r2 + gq = tap * 3 + c (27 used)
+  int rc[2][2], rrel[2][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const int r = 16 * m + 8 * r2 + gq;
+      const int tap = r / 3;
+      rc[m][r2] = r < 27 ? r % 3 : -1;
+      rrel[m][r2] = (tap / 3) * kPW + tap % 3;
+    }
+  float acc[2][4][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][nt][j] = 0.f;
+  for (int i = tid; i < 3 * kPVpad; i += kNarrowThreads) (&xw[0][0])[i] = 0;
+  for (int i = tid; i < kTH * kTW * kXRow / 4; i += kNarrowThreads) reinterpret_cast<uint32_t*>(ys)[i] = 0u;
+  for (int i = tid; i < 32 * 32; i += kNarrowThreads) red[i] = 0.f;
+  __syncthreads();
+  const uint32_t ys_s = static_cast<uint32_t>(__cvta_generic_to_shared(ys));
+  const int mat = lane >> 3, mrow = lane & 7;
+  const uint32_t b_off = ((mat & 1) * 8 + mrow) * kXRow + (mat >> 1) * 16;   // + n-tile pair * 32 bytes
+
+  const long long ncols = static_cast<long long>(p.N) * p.D * p.tilesH * p.tilesW;   // one (n, d, window) per step
+  // this thread's two voxels of the haloed x window and its (at most) four 16-byte chunks of the dy window
+  uint2 xn[2];
+  uint4 yn[4];
+  auto load = [&](long long col, uint2 (&xv)[2], uint4 (&yv)[4]) {
+    long long t = col;
+    const int w0 = static_cast<int>(t % p.tilesW) * kTW;
+    t /= p.tilesW;
+    const int h0 = static_cast<int>(t % p.tilesH) * kTH;
+    t /= p.tilesH;                                                   // t = n * D + d
+    const bf16* xb = p.x + t * p.H * p.W * p.x_ld;
+    const bf16* yb = p.dy + t * p.H * p.W * p.dy_ld;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pv = tid + k * kNarrowThreads;
+      const int hh = h0 - 1 + pv / kPW, ww = w0 - 1 + pv % kPW;
+      xv[k] = make_uint2(0u, 0u);
+      if (col < ncols && pv < kPV && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+        xv[k] = __ldg(reinterpret_cast<const uint2*>(xb + (static_cast<long long>(hh) * p.W + ww) * p.x_ld));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = tid + k * kNarrowThreads;
+      const int v = c >> 2, part = c & 3;
+      const int hh = h0 + v / kTW, ww = w0 + v % kTW;
+      yv[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (col < ncols && part < ychunks && hh < p.H && ww < p.W)
+        yv[k] = __ldg(reinterpret_cast<const uint4*>(yb + (static_cast<long long>(hh) * p.W + ww) * p.dy_ld + part * 8));
+    }
+  };
+  load(blockIdx.x, xn, yn);
+#pragma unroll 1
+  for (long long col = blockIdx.x; col < ncols; col += gridDim.x) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pv = tid + k * kNarrowThreads;
+      if (pv < kPV) {
+        xw[0][pv] = static_cast<unsigned short>(xn[k].x & 0xFFFFu);
+        xw[1][pv] = static_cast<unsigned short>(xn[k].x >> 16);
+        xw[2][pv] = static_cast<unsigned short>(xn[k].y & 0xFFFFu);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = tid + k * kNarrowThreads;
+      if ((c & 3) < ychunks) *reinterpret_cast<uint4*>(ys + (c >> 2) * kXRow + (c & 3) * 16) = yn[k];
+    }
+    __syncthreads();
+    load(col + gridDim.x, xn, yn);                                   // the next window while this one is multiplied
+#pragma unroll 1
+    for (int mt = warp; mt < kTH; mt += kNarrowThreads / 32) {       // K step = the 16 voxels of window row mt
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {     // a[.][r2 + 2 h2]: row gq + 8 r2, voxel columns 2tq + 8 h2, + 1
+            uint32_t v = 0u;
+            const int cc = rc[m][r2];
+            if (cc >= 0) {
+              const unsigned short* q = (cc == 0 ? xw[0] : (cc == 1 ? xw[1] : xw[2])) + mt * kPW + rrel[m][r2] + 2 * tq + 8 * h2;
+              v = static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 16);
+            }
+            a[m][r2 + 2 * h2] = v;
+          }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        if (np * 16 >= p.cout) break;
+        uint32_t b0, b1, b2, b3;   // n-tile 2np: (b0, b1); n-tile 2np + 1: (b2, b3)
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(ys_s + mt * kTW * kXRow + b_off + np * 32));
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma16816(acc[m][2 * np], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
+          mma16816(acc[m][2 * np + 1], a[m][0], a[m][1], a[m][2], a[m][3], b2, b3);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int w = 0; w < kNarrowThreads / 32; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r = 16 * m + gq, c = 8 * nt + 2 * tq;
+          red[r * 32 + c] += acc[m][nt][0];
+          red[r * 32 + c + 1] += acc[m][nt][1];
+          red[(r + 8) * 32 + c] += acc[m][nt][2];
+          red[(r + 8) * 32 + c + 1] += acc[m][nt][3];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 32 * 32; i += kNarrowThreads) {
+    const int r = i >> 5, c = i & 31;
+    if (r < 27 && c < p.cout) atomicAdd(p.acc + static_cast<size_t>(r) * p.acc_ld + c, red[i]);
+  }
+}
+
 }  // namespace
 
 }  // namespace vfd
@@ -638,4 +792,30 @@ VFD_API int vfd_conv3d_wgrad_narrow(const void* g, long long g_ld, const void* x
   if (grid > 4LL * sms) grid = 4LL * sms;
   conv_narrow_wgrad_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("conv_narrow_wgrad");
+}
+
+VFD_API int vfd_conv3d_wgrad_first(const void* dy, long long dy_ld, int cout, const void* x, long long x_ld, float* acc,
+                                   int acc_ld, int N, int D, int H, int W, void* stream_) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  if (dy == nullptr || x == nullptr || acc == nullptr) return set_error(VFD_ERR_ARG, "conv3d_wgrad_first: null pointer");
+  if (cout < 1 || cout > 32 || acc_ld < cout) return set_error(VFD_ERR_ARG, "conv3d_wgrad_first: needs 1 <= cout <= 32");
+  if (x_ld < 8 || x_ld % 4 || (reinterpret_cast<uintptr_t>(x) & 7) || dy_ld % 8 || dy_ld < ((cout + 7) & ~7) ||
+      (reinterpret_cast<uintptr_t>(dy) & 15))
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_first: tensors must be aligned channels-last bf16");
+  if (static_cast<long long>(N) * D * H * W >= (1LL << 31))
+    return set_error(VFD_ERR_ARG, "conv3d_wgrad_first: more than 2^31 voxels");
+  FirstWgradParams p;
+  p.x = static_cast<const bf16*>(x); p.x_ld = x_ld; p.dy = static_cast<const bf16*>(dy); p.dy_ld = dy_ld; p.cout = cout;
+  p.acc = acc; p.acc_ld = acc_ld;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.tilesH = (H + kTH - 1) / kTH; p.tilesW = (W + kTW - 1) / kTW;
+  long long grid = static_cast<long long>(N) * D * p.tilesH * p.tilesW;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (grid > 4LL * sms) grid = 4LL * sms;
+  conv_first_wgrad_kernel<<<static_cast<unsigned>(grid), kNarrowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("conv_first_wgrad");
 }

@@ -145,6 +145,13 @@ def _conv3d_wgrad_narrow(g, x, acc):
               _stream())
 
 
+def _conv3d_wgrad_first(dy, cout, x, acc):
+    N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad_first gradient")
+    _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad_first input")
+    _lib.call("vfd_conv3d_wgrad_first", dy.data_ptr(), dy_ld, cout, x.data_ptr(), x_ld, acc.data_ptr(), acc.shape[-1],
+              N, D, H, W, _stream())
+
+
 def _conv3d_wgrad(dy, cout, x, cin, acc, kd, kh, kw, direct, layout=0):
     N, D, H, W, _, dy_ld = _check_cl(dy, "conv3d_wgrad dy")
     _, _, _, _, _, x_ld = _check_cl(x, "conv3d_wgrad x")
@@ -391,6 +398,8 @@ convlstm_step_fwd = _define(
     "Tensor(c!)? act, int kh, int kw, int kc) -> ()", _convlstm_step_fwd)
 conv3d_dgrad_narrow = _define("conv3d_dgrad_narrow(Tensor g, Tensor w_dgrad, Tensor(a!) gx) -> ()", _conv3d_dgrad_narrow)
 conv3d_wgrad_narrow = _define("conv3d_wgrad_narrow(Tensor g, Tensor x, Tensor(a!) acc) -> ()", _conv3d_wgrad_narrow)
+conv3d_wgrad_first = _define("conv3d_wgrad_first(Tensor dy, int cout, Tensor x, Tensor(a!) acc) -> ()",
+                             _conv3d_wgrad_first)
 conv3d_wgrad = _define(
     "conv3d_wgrad(Tensor dy, int cout, Tensor x, int cin, Tensor(a!) acc, int kd, int kh, int kw, bool direct, "
     "int layout=0) -> ()", _conv3d_wgrad)
@@ -471,6 +480,7 @@ NARROW_CONV = os.environ.get("VFD_NARROW_CONV", "1") != "0"   # conv_last forwar
 LSTM_FUSED = os.environ.get("VFD_LSTM_FUSED", "1") != "0"     # ConvLSTM step with the cell update in the gate conv's epilogue
 NARROW_WGRAD = os.environ.get("VFD_NARROW_WGRAD", "1") != "0"
 BN_TICKET = os.environ.get("VFD_BN_TICKET", "1") != "0"       # BatchNorm backward: last-block finalize instead of a launch
+FIRST_WGRAD = os.environ.get("VFD_FIRST_WGRAD", "1") != "0"
 CONV_IMPL_DIRECT = False  # tests flip this to cross-check the tcgen05 path against the CUDA-core convs of libvfd_b200_debug.so
 PROFILER = None           # bench.py installs an object with .run(kind, work, thunk) to time kernels
 
@@ -868,11 +878,15 @@ def _folded_wgrad(mode, g, x, cin, cout, kd, kh, kw, flops):
     fused = THIN_WGRAD and other <= 32 and (mode, kd, kh, kw, cs) in _FUSED_FOLDS
     narrow = (NARROW_CONV and NARROW_WGRAD and mode == "y" and (kd, kh, kw, cout) == (3, 3, 3, 1) and cin == 32
               and x.shape[-1] == 32 and not DETERMINISTIC)
-    folded = None if (fused or narrow) else cl_empty(N, D, H, W, cols, g.device)
+    first = (NARROW_CONV and FIRST_WGRAD and mode == "x" and (kd, kh, kw, cin) == (1, 3, 3, 3) and cout <= 32
+             and not DETERMINISTIC)
+    folded = None if (fused or narrow or first) else cl_empty(N, D, H, W, cols, g.device)
 
     def run():
         if mode == "x":     # X'[v][t*cin+ci] = x[v+off(t)][ci];  acc[0][t*cin+ci][co]
-            if fused:
+            if first:       # 1x3x3 over three channels: gather + GEMM in one kernel (csrc/conv_narrow.cu)
+                conv3d_wgrad_first(g, cout, x, acc)
+            elif fused:
                 conv3d_wgrad_thin(g, cout, x, taps * cin, acc, 1, cs, kd, kh, kw)
             else:
                 tap_gather(x, cs, folded, kd, kh, kw, 1)
